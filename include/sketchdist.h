@@ -1,0 +1,168 @@
+/*
+ * sketchdist.h -- C ABI of libsketchdist.so, the B200 (sm_100a) implementation of the pairwise
+ * sketch-distance path of bacpop/sketchlib.rust.
+ *
+ * The reference has no FFI seam for this path; its seam is the public Rust API of
+ * `sketchlib::distances` as called from `main` (reference src/lib.rs:341-451).  Every entry point
+ * below names the reference function it replaces (file:line relative to the reference checkout).
+ * A Rust `-sys` crate binding these is sketched in INTEGRATION.md; in this repository the host
+ * layer above the ABI is C++ (sketchlib.rust_b200/csrc/host) and Python ctypes
+ * (sketchlib.rust_b200/__init__.py).
+ *
+ * Conventions
+ *   - every function returns an skd_status (0 = ok); no exception or unwind crosses the boundary;
+ *     where the reference panics, the matching status is returned and skd_last_error() holds the
+ *     reference's message;
+ *   - all pointers are caller-owned; sizes are in elements unless the name says bytes;
+ *   - "loc" arguments say where a caller buffer lives: SKD_HOST (pageable or pinned host memory)
+ *     or SKD_DEVICE (memory of the context's GPU);
+ *   - one context per GPU per process (one process per GPU for multi-GPU runs; rows are sharded by
+ *     the row/ref/query ranges every compute call takes); a context is not thread-safe.
+ *   - there is no CPU fallback: without a CUDA device skd_ctx_create fails.
+ */
+#ifndef SKETCHDIST_H
+#define SKETCHDIST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum skd_status {
+    SKD_OK = 0,
+    SKD_ERR_INVALID = 1,      /* bad argument */
+    SKD_ERR_CUDA = 2,         /* CUDA runtime error, text in skd_last_error */
+    SKD_ERR_NEED_TWO_K = 3,   /* reference panic: src/distances/jaccard.rs:70-72 */
+    SKD_ERR_K_NOT_FOUND = 4,  /* reference Err: src/distances/mod.rs:28-30 */
+    SKD_ERR_EMPTY_DB = 5,     /* reference panic: src/distances/mod.rs:318-323 */
+    SKD_ERR_INCOMPATIBLE = 6, /* ref/query sketch size or k-mer list differ (multisketch.rs:222-226) */
+    SKD_ERR_UNSUPPORTED = 7,  /* outside the implemented envelope */
+    SKD_ERR_IO = 8,           /* file could not be read */
+    SKD_ERR_NOMEM = 9
+} skd_status;
+
+typedef enum skd_loc { SKD_HOST = 0, SKD_DEVICE = 1 } skd_loc;
+
+/* DistType: src/distances/distance_matrix.rs:55-60 */
+typedef enum skd_dist_kind { SKD_CORE_ACC = 0, SKD_JACCARD = 1, SKD_ANI = 2 } skd_dist_kind;
+typedef struct skd_dist_type {
+    int32_t kind;  /* skd_dist_kind */
+    int32_t k_idx; /* index into the k-mer list for SKD_JACCARD / SKD_ANI; ignored for SKD_CORE_ACC */
+} skd_dist_type;
+
+typedef struct skd_ctx skd_ctx;
+typedef struct skd_db skd_db; /* a MultiSketch resident in HBM (src/sketch/multisketch.rs:23-43) */
+
+/* ---- context ---------------------------------------------------------------------------- */
+skd_status skd_ctx_create(int device, skd_ctx **out);
+void skd_ctx_destroy(skd_ctx *ctx);
+/* Message of the last failing call on this context (or of a failed skd_ctx_create when ctx == NULL). */
+const char *skd_last_error(const skd_ctx *ctx);
+int skd_ctx_device(const skd_ctx *ctx);
+/* Kernels launched by this context since creation (bench.py's gpu_launches). */
+uint64_t skd_ctx_launch_count(const skd_ctx *ctx);
+/* Device time in ms of the distance kernels of the last compute call, measured with CUDA events on
+ * the context's compute stream (the stream the kernels are launched on). */
+float skd_ctx_last_kernel_ms(const skd_ctx *ctx);
+/* Block until all work queued by this context is complete. */
+skd_status skd_ctx_synchronize(skd_ctx *ctx);
+/* The context's compute stream as a cudaStream_t (for callers that time with their own events). */
+void *skd_ctx_stream(const skd_ctx *ctx);
+
+/* Pinned host memory for inputs/results (plays the part of the Vec<f32> the reference's
+ * DistanceMatrix::new allocates, src/distances/distance_matrix.rs:148-152). */
+skd_status skd_host_alloc(skd_ctx *ctx, size_t bytes, void **out);
+void skd_host_free(skd_ctx *ctx, void *ptr);
+/* Device memory helpers for callers without a CUDA runtime binding. */
+skd_status skd_device_alloc(skd_ctx *ctx, size_t bytes, void **out);
+void skd_device_free(skd_ctx *ctx, void *ptr);
+skd_status skd_memcpy(skd_ctx *ctx, void *dst, skd_loc dst_loc, const void *src, skd_loc src_loc, size_t bytes);
+
+/* ---- sketch database loader ---------------------------------------------------------------
+ * Replaces MultiSketch::read_sketch_data / get_sketch_slice (src/sketch/multisketch.rs:167-184,
+ * 213-219).  `bins` is the reference's flat u64 array: word
+ * [s*sample_stride + k_idx*kmer_stride + w*14 + p] = bit plane p of bins 64w..64w+63 of sample s at
+ * k-mer index k_idx.  The library keeps its own re-tiled copy in HBM (k-major, 64-sample blocks,
+ * plane pairs interleaved); the caller's buffer is not referenced afterwards. */
+skd_status skd_db_upload(skd_ctx *ctx, const uint64_t *bins, skd_loc bins_loc, uint64_t n_samples,
+                         uint64_t sample_stride, uint64_t kmer_stride, uint64_t sketchsize64,
+                         uint64_t sketch_size, const uint64_t *kmer_lengths, uint32_t n_kmers, skd_db **out);
+/* Replaces read_sketch_data / read_sketch_data_block + SketchArrayReader (multisketch.rs:167-210,
+ * src/sketch/sketch_datafile.rs:159-194): streams an .skd file into HBM through pinned staging.
+ * `sample_indices` (nullable) lists the FILE positions (Sketch::index) of the samples to load, in the
+ * order they are to appear (the --subset order, block_reindex); NULL loads samples 0..n_samples-1. */
+skd_status skd_db_load_skd(skd_ctx *ctx, const char *skd_path, const uint64_t *sample_indices,
+                           uint64_t n_samples, uint64_t sample_stride, uint64_t kmer_stride,
+                           uint64_t sketchsize64, uint64_t sketch_size, const uint64_t *kmer_lengths,
+                           uint32_t n_kmers, skd_db **out);
+void skd_db_free(skd_db *db);
+uint64_t skd_db_n_samples(const skd_db *db);       /* number_samples_loaded, multisketch.rs:106-111 */
+uint32_t skd_db_n_kmers(const skd_db *db);
+uint64_t skd_db_sketch_size(const skd_db *db);     /* bins */
+uint64_t skd_db_hbm_bytes(const skd_db *db);
+/* is_compatible_with (multisketch.rs:222-226) minus the hash type, which the ABI does not see. */
+int skd_db_compatible(const skd_db *a, const skd_db *b);
+
+/* set_k: src/distances/mod.rs:25-37.  kmer < 0 means "no -k given" => core/accessory. */
+skd_status skd_set_k(skd_ctx *ctx, const skd_db *db, int64_t kmer, int ani, skd_dist_type *out);
+
+/* ---- distances --------------------------------------------------------------------------------
+ * completeness vectors are host arrays of n_samples doubles or NULL (Option<&Vec<f64>>).        */
+
+/* self_dists_all: src/distances/mod.rs:58-130, restricted to rows [row_begin, row_end) of the upper
+ * triangle.  `out` receives, in condensed row-major order, the distances of all pairs (i, j) with
+ * row_begin <= i < row_end, i < j < n: element 0 is pair (row_begin, row_begin+1).  1 float per pair
+ * (Jaccard distance 1-J, or ANI) or 2 interleaved (core, accessory).  row range (0, n) is the whole
+ * matrix of the reference. */
+skd_status skd_self_dists_all(skd_ctx *ctx, const skd_db *db, skd_dist_type dist, const double *completeness,
+                              double completeness_cutoff, uint64_t row_begin, uint64_t row_end, float *out,
+                              skd_loc out_loc);
+/* Number of pairs skd_self_dists_all writes for a row range (square_to_condensed arithmetic,
+ * src/distances/distance_matrix.rs:11-14). */
+uint64_t skd_self_pairs_in_rows(uint64_t n, uint64_t row_begin, uint64_t row_end);
+
+/* cross_dists_all: src/distances/mod.rs:227-297, refs [ref_begin, ref_end).  Ref-major:
+ * out[((i - ref_begin) * n_query + j) * ncols]. */
+skd_status skd_cross_dists_all(skd_ctx *ctx, const skd_db *ref, const skd_db *query, skd_dist_type dist,
+                               const double *ref_completeness, const double *query_completeness,
+                               double completeness_cutoff, uint64_t ref_begin, uint64_t ref_end, float *out,
+                               skd_loc out_loc);
+
+/* self_dists_knn: src/distances/mod.rs:133-224, rows [row_begin, row_end).  Outputs are row-major
+ * (row_end-row_begin) x knn: neighbour index, first distance (Jaccard dist / ANI / core), second
+ * distance (accessory; may be NULL unless core/acc).  Rows ascend by the reference's key (1-J, 1-ANI,
+ * core); ties are broken by neighbour index.  Requires 1 <= knn <= n-1 (the CLI clamps,
+ * src/lib.rs:379-382). */
+skd_status skd_self_dists_knn(skd_ctx *ctx, const skd_db *db, uint64_t knn, skd_dist_type dist,
+                              const double *completeness, double completeness_cutoff, uint64_t row_begin,
+                              uint64_t row_end, uint64_t *idx_out, float *d0_out, float *d1_out, skd_loc out_loc);
+
+/* cross_dists_knn: src/distances/mod.rs:306-395, one row per query in [query_begin, query_end), each
+ * scanning all refs; knn is clamped to n_ref like the reference (:325) and returned in *knn_used, which
+ * is also the row pitch of the outputs. */
+skd_status skd_cross_dists_knn(skd_ctx *ctx, const skd_db *ref, const skd_db *query, uint64_t knn,
+                               skd_dist_type dist, const double *ref_completeness,
+                               const double *query_completeness, double completeness_cutoff,
+                               uint64_t query_begin, uint64_t query_end, uint64_t *idx_out, float *d0_out,
+                               float *d1_out, skd_loc out_loc, uint64_t *knn_used);
+
+/* Distances for an explicit list of (ref_idx, query_idx) pairs (the per-pair calls inside
+ * self_dists_knn_precluster, src/distances/mod.rs:399-553).  out: 1 or 2 floats per pair. */
+skd_status skd_pair_dists(skd_ctx *ctx, const skd_db *ref, const skd_db *query, skd_dist_type dist,
+                          const double *ref_completeness, const double *query_completeness,
+                          double completeness_cutoff, const uint64_t *pairs, uint64_t n_pairs, float *out);
+
+/* Parity/debug: raw per-k bin-match counts (`samebits`, src/distances/jaccard.rs:15-25) for explicit
+ * pairs, counts[p * n_kmers + k]; and for a dense tile range exactly as the tiled kernel computes them:
+ * counts[((i - ref_begin) * n_query + j) * n_kmers + k]. */
+skd_status skd_match_counts(skd_ctx *ctx, const skd_db *ref, const skd_db *query, const uint64_t *pairs,
+                            uint64_t n_pairs, uint32_t *counts);
+skd_status skd_match_counts_dense(skd_ctx *ctx, const skd_db *ref, const skd_db *query, uint64_t ref_begin,
+                                  uint64_t ref_end, uint32_t *counts);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SKETCHDIST_H */

@@ -1,0 +1,890 @@
+// C ABI of libsketchdist.so (include/sketchdist.h): context, sketch-database loader, and the host side of
+// the distance drivers (tile schedules, chunked result streaming).  No CPU fallback exists: every compute
+// entry point launches the CUDA kernels of kernels.cu or fails.
+#include <cuda_runtime.h>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/sketchdist.h"
+#include "kernels.h"
+#include "layout.h"
+
+using namespace skd;
+
+namespace {
+thread_local std::string g_create_error;
+constexpr size_t kMaxSmem = 232448;           // 227 KB opt-in dynamic shared memory per CTA on sm_100
+constexpr size_t kUploadChunkBytes = 64ull << 20;
+constexpr size_t kResultChunkBytes = 256ull << 20;
+constexpr uint32_t kGroup = 8;                // row blocks per L2 group
+}  // namespace
+
+struct skd_ctx {
+    int device = 0;
+    cudaStream_t compute = nullptr, copy = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+    float last_ms = 0.f;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timers;  // event pairs around kernel launches of a call
+    size_t timers_used = 0;
+    cudaEvent_t ev_a[2] = {nullptr, nullptr}, ev_b[2] = {nullptr, nullptr};
+    std::map<std::string, std::pair<void *, size_t>> scratch;  // named device buffers reused across calls
+    void *pinned[2] = {nullptr, nullptr};
+    size_t pinned_bytes = 0;
+    int sm_count = 148;
+};
+
+struct skd_db {
+    skd_ctx *ctx = nullptr;
+    DevDb dev{};
+    uint32_t *tiled = nullptr;
+    size_t tiled_bytes = 0;
+    std::vector<uint64_t> kmers;
+    uint64_t sketch_size = 0, W = 0, n = 0;
+    double *lny_dev = nullptr;  // [nbins + 1]
+};
+
+namespace {
+
+skd_status fail(skd_ctx *ctx, skd_status st, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx)
+        ctx->err = buf;
+    else
+        g_create_error = buf;
+    return st;
+}
+
+#define CU(ctx, expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (expr);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return fail(ctx, SKD_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                        __LINE__);                                                                      \
+    } while (0)
+
+skd_status scratch_get(skd_ctx *ctx, const char *name, size_t bytes, void **out) {
+    auto &slot = ctx->scratch[name];
+    if (slot.second < bytes) {
+        if (slot.first) cudaFree(slot.first);
+        slot = {nullptr, 0};
+        size_t want = std::max<size_t>(bytes, 256);
+        CU(ctx, cudaMalloc(&slot.first, want));
+        slot.second = want;
+    }
+    *out = slot.first;
+    return SKD_OK;
+}
+
+skd_status pinned_get(skd_ctx *ctx, size_t bytes) {
+    if (ctx->pinned_bytes >= bytes) return SKD_OK;
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
+        ctx->pinned[i] = nullptr;
+    }
+    ctx->pinned_bytes = 0;
+    for (int i = 0; i < 2; ++i) CU(ctx, cudaMallocHost(&ctx->pinned[i], bytes));
+    ctx->pinned_bytes = bytes;
+    return SKD_OK;
+}
+
+void timers_reset(skd_ctx *ctx) { ctx->timers_used = 0; }
+skd_status timer_begin(skd_ctx *ctx) {
+    if (ctx->timers_used == ctx->timers.size()) {
+        cudaEvent_t a, b;
+        CU(ctx, cudaEventCreate(&a));
+        CU(ctx, cudaEventCreate(&b));
+        ctx->timers.push_back({a, b});
+    }
+    CU(ctx, cudaEventRecord(ctx->timers[ctx->timers_used].first, ctx->compute));
+    return SKD_OK;
+}
+skd_status timer_end(skd_ctx *ctx) {
+    CU(ctx, cudaEventRecord(ctx->timers[ctx->timers_used].second, ctx->compute));
+    ctx->timers_used++;
+    return SKD_OK;
+}
+// Call after the compute stream is idle.
+skd_status timers_collect(skd_ctx *ctx) {
+    float total = 0.f;
+    for (size_t i = 0; i < ctx->timers_used; ++i) {
+        float ms = 0.f;
+        CU(ctx, cudaEventElapsedTime(&ms, ctx->timers[i].first, ctx->timers[i].second));
+        total += ms;
+    }
+    ctx->last_ms = total;
+    return SKD_OK;
+}
+
+uint64_t condensed(uint64_t i, uint64_t j, uint64_t n) {  // square_to_condensed, distance_matrix.rs:11-14
+    return n * i - ((i * (i + 1)) >> 1) + j - 1 - i;
+}
+
+// ---- epilogue parameter block --------------------------------------------------------------------
+// Host side of jaccard_index's float tail (jaccard.rs:26-33) for the tables.
+double host_jaccard(uint32_t c, uint32_t nbins) {
+    uint32_t expected = nbins >> BBITS;
+    uint32_t diff = c > expected ? c - expected : 0;
+    double intersize = ((double)diff * (double)nbins) / (double)(nbins - expected);
+    return intersize / (double)nbins;
+}
+
+skd_status build_epi(skd_ctx *ctx, const skd_db *A, const skd_db *B, skd_dist_type dist, const double *a_comp,
+                     const double *b_comp, double cutoff, EpiParams *E) {
+    memset(E, 0, sizeof *E);
+    const uint32_t nbins = (uint32_t)(64 * A->W);
+    const int K = (int)A->kmers.size();
+    E->kind = dist.kind;
+    E->nbins = nbins;
+    E->expected = nbins >> BBITS;
+    E->cutoff = cutoff;
+    E->tolerance = std::log(2.0 / (double)(A->sketch_size * 64));  // jaccard.rs:75 (sketch_size = bins)
+    E->lny = A->lny_dev;
+    if (dist.kind == KIND_CORE_ACC) {
+        if (K < 2)
+            return fail(ctx, SKD_ERR_NEED_TWO_K, "Need at least two k-mer lengths to calculate core/accessory distances");
+        if (K > MAXK) return fail(ctx, SKD_ERR_UNSUPPORTED, "core/accessory supports at most %d k-mer lengths", MAXK);
+        E->k0 = 0;
+        E->nk = K;
+        double xsum = 0.0, xsq = 0.0;
+        for (int n = 0; n <= K; ++n) {
+            if (n > 0) {  // running sums in the reference's order (jaccard.rs:92-97)
+                double kf = (double)A->kmers[n - 1];
+                E->kf[n - 1] = kf;
+                xsum += kf;
+                xsq += kf * kf;
+            }
+            E->xsum[n] = xsum;
+            if (n > 0) {  // jaccard.rs:121-125
+                double dn = (double)n;
+                E->xbar[n] = xsum / dn;
+                E->x_diff[n] = xsq - xsum * xsum / dn;
+                E->xstddev[n] = std::sqrt((xsq - xsum * xsum / dn) / dn);
+            }
+        }
+    } else if (dist.kind == KIND_JACCARD || dist.kind == KIND_ANI) {
+        if (dist.k_idx < 0 || dist.k_idx >= K) return fail(ctx, SKD_ERR_INVALID, "k_idx %d out of range", dist.k_idx);
+        E->k0 = dist.k_idx;
+        E->nk = 1;
+        E->k_single = (double)A->kmers[dist.k_idx];
+        // value/key tables by match count, computed with the host libm like the reference does per pair
+        std::vector<float> tab(2 * ((size_t)nbins + 1));
+        for (uint32_t c = 0; c <= nbins; ++c) {
+            double j = host_jaccard(c, nbins);
+            if (dist.kind == KIND_ANI) {
+                double ani = std::fmax(0.0, 1.0 + 1.0 / E->k_single * std::log((2.0 * j) / (1.0 + j)));
+                tab[c] = (float)ani;                       // mod.rs:97-98
+                tab[nbins + 1 + c] = (float)(1.0 - ani);   // mod.rs:175
+            } else {
+                tab[c] = (float)(1.0 - j);                 // mod.rs:100
+                tab[nbins + 1 + c] = (float)(1.0 - j);     // mod.rs:177
+            }
+        }
+        void *dtab;
+        skd_status st = scratch_get(ctx, "valtab", tab.size() * sizeof(float), &dtab);
+        if (st) return st;
+        CU(ctx, cudaMemcpyAsync(dtab, tab.data(), tab.size() * sizeof(float), cudaMemcpyHostToDevice, ctx->compute));
+        CU(ctx, cudaStreamSynchronize(ctx->compute));  // `tab` is stack-scoped pageable memory
+        E->val_tab = (const float *)dtab;
+        E->key_tab = (const float *)dtab + nbins + 1;
+    } else {
+        return fail(ctx, SKD_ERR_INVALID, "unknown distance kind %d", dist.kind);
+    }
+    // Completeness applies only when both vectors are given (jaccard.rs:36)
+    if (a_comp && b_comp) {
+        E->has_c = 1;
+        void *da, *dbp;
+        skd_status st = scratch_get(ctx, "acomp", std::max<uint64_t>(1, A->n) * sizeof(double), &da);
+        if (st) return st;
+        st = scratch_get(ctx, "bcomp", std::max<uint64_t>(1, B->n) * sizeof(double), &dbp);
+        if (st) return st;
+        CU(ctx, cudaMemcpyAsync(da, a_comp, A->n * sizeof(double), cudaMemcpyHostToDevice, ctx->compute));
+        CU(ctx, cudaMemcpyAsync(dbp, b_comp, B->n * sizeof(double), cudaMemcpyHostToDevice, ctx->compute));
+        CU(ctx, cudaStreamSynchronize(ctx->compute));
+        E->a_comp = (const double *)da;
+        E->b_comp = (const double *)dbp;
+    }
+    return SKD_OK;
+}
+
+skd_status check_pair(skd_ctx *ctx, const skd_db *A, const skd_db *B) {
+    if (!ctx || !A || !B) return fail(ctx, SKD_ERR_INVALID, "null context or database");
+    if (A->ctx != ctx || B->ctx != ctx) return fail(ctx, SKD_ERR_INVALID, "database belongs to another context");
+    if (A != B && !skd_db_compatible(A, B))
+        return fail(ctx, SKD_ERR_INCOMPATIBLE, "reference and query databases differ in sketch size or k-mer lengths");
+    return SKD_OK;
+}
+
+// Group offsets for a dense launch over row blocks [rb0, rb0 + n_rb).
+void build_groups(bool self, uint32_t rb0, uint32_t n_rb, uint32_t nbB, std::vector<uint64_t> *off) {
+    uint32_t n_groups = (n_rb + kGroup - 1) / kGroup;
+    off->assign(n_groups + 1, 0);
+    for (uint32_t g = 0; g < n_groups; ++g) {
+        uint32_t rows = std::min(kGroup, n_rb - g * kGroup);
+        uint64_t cols = self ? (uint64_t)nbB - (rb0 + g * kGroup) : nbB;
+        (*off)[g + 1] = (*off)[g] + (uint64_t)rows * cols;
+    }
+}
+
+// Launch the tile kernel for rows [r0, r1) writing to device memory `dout`.  `d_grp_off` is the device copy
+// of `off` (group offsets built by build_groups for exactly this row range).
+skd_status launch_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, const EpiParams &E, int mode, uint64_t r0,
+                        uint64_t r1, float *dout, const std::vector<uint64_t> &off, const uint64_t *d_grp_off) {
+    SchedParams S{};
+    S.mode = mode;
+    S.self_mode = mode == MODE_DENSE_SELF;
+    S.rb0 = (uint32_t)(r0 / TS);
+    S.n_rb = (uint32_t)((r1 + TS - 1) / TS) - S.rb0;
+    S.group = kGroup;
+    S.n_groups = (uint32_t)off.size() - 1;
+    S.grp_off = d_grp_off;
+    S.row_begin = r0;
+    S.row_end = r1;
+    S.out_base = S.self_mode ? condensed(r0, r0 + 1, A->n) : 0;
+    S.out = dout;
+    const bool count32 = E.nbins >= 65536;
+    size_t smem = tile_kernel_smem(E.nk, count32, false, 0, false);
+    if (smem > kMaxSmem)
+        return fail(ctx, SKD_ERR_UNSUPPORTED, "%d k-mer lengths at %u bins need %zu B of shared memory per tile", E.nk,
+                    E.nbins, smem);
+    skd_status st = timer_begin(ctx);
+    if (st) return st;
+    CU(ctx, launch_tiles(A->dev, B->dev, E, S, off.back(), count32, smem, ctx->compute));
+    ctx->launches++;
+    return timer_end(ctx);
+}
+
+// Rows [row_begin, row_end) of a dense matrix, streamed to host in chunks or written in place on the device.
+skd_status run_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, bool self, const EpiParams &E, int mode,
+                     uint64_t row_begin, uint64_t row_end, float *out, skd_loc out_loc) {
+    const uint64_t ncols = mode == MODE_COUNTS ? (uint64_t)E.nk : (E.kind == KIND_CORE_ACC ? 2 : 1);
+    auto elems_before = [&](uint64_t r) -> uint64_t {  // output elements (pairs) of rows [row_begin, r)
+        if (self) return skd_self_pairs_in_rows(A->n, row_begin, r);
+        return (r - row_begin) * B->n;
+    };
+    timers_reset(ctx);
+    // Plan: one chunk when the result stays on the device; otherwise row chunks of about kResultChunkBytes
+    // on two device buffers, so that the D2H copy of chunk c overlaps the kernel of chunk c+1.
+    struct Chunk {
+        uint64_t r0, r1;
+        std::vector<uint64_t> off;
+        size_t off_pos;
+    };
+    std::vector<Chunk> chunks;
+    uint64_t rows_per_chunk = row_end - row_begin + TS;
+    if (out_loc == SKD_HOST) {
+        const uint64_t widest = self ? (A->n - 1 - std::min(row_begin, A->n - 1)) : B->n;
+        rows_per_chunk = kResultChunkBytes / std::max<uint64_t>(1, widest * ncols * 4);
+        rows_per_chunk = std::max<uint64_t>(TS, rows_per_chunk / TS * TS);
+    }
+    size_t chunk_elems = 0, off_total = 0;
+    for (uint64_t r = row_begin; r < row_end;) {
+        Chunk c;
+        c.r0 = r;
+        c.r1 = std::min(row_end, (r / TS) * TS + rows_per_chunk);
+        build_groups(self, (uint32_t)(c.r0 / TS), (uint32_t)((c.r1 + TS - 1) / TS) - (uint32_t)(c.r0 / TS), B->dev.nb,
+                     &c.off);
+        c.off_pos = off_total;
+        off_total += c.off.size();
+        chunk_elems = std::max<size_t>(chunk_elems, elems_before(c.r1) - elems_before(c.r0));
+        r = c.r1;
+        chunks.push_back(std::move(c));
+    }
+    std::vector<uint64_t> all_off;
+    all_off.reserve(off_total);
+    for (auto &c : chunks) all_off.insert(all_off.end(), c.off.begin(), c.off.end());
+    void *doff;
+    skd_status st = scratch_get(ctx, "grp_off", all_off.size() * sizeof(uint64_t), &doff);
+    if (st) return st;
+    CU(ctx, cudaMemcpyAsync(doff, all_off.data(), all_off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice,
+                            ctx->compute));
+    CU(ctx, cudaStreamSynchronize(ctx->compute));  // all_off is pageable
+    const uint64_t *d_off = (const uint64_t *)doff;
+
+    if (out_loc == SKD_DEVICE) {
+        for (auto &c : chunks) {
+            st = launch_dense(ctx, A, B, E, mode, c.r0, c.r1, out + elems_before(c.r0) * ncols, c.off, d_off + c.off_pos);
+            if (st) return st;
+        }
+        CU(ctx, cudaStreamSynchronize(ctx->compute));
+        return timers_collect(ctx);
+    }
+    void *dbuf[2];
+    st = scratch_get(ctx, "dense0", chunk_elems * ncols * 4, &dbuf[0]);
+    if (st) return st;
+    dbuf[1] = dbuf[0];
+    if (chunks.size() > 1) {
+        st = scratch_get(ctx, "dense1", chunk_elems * ncols * 4, &dbuf[1]);
+        if (st) return st;
+    }
+    for (size_t ci = 0; ci < chunks.size(); ++ci) {
+        const Chunk &c = chunks[ci];
+        const int b = (int)(ci & 1);
+        if (ci >= 2) CU(ctx, cudaStreamWaitEvent(ctx->compute, ctx->ev_b[b], 0));  // D2H of chunk ci-2 done
+        st = launch_dense(ctx, A, B, E, mode, c.r0, c.r1, (float *)dbuf[b], c.off, d_off + c.off_pos);
+        if (st) return st;
+        CU(ctx, cudaEventRecord(ctx->ev_a[b], ctx->compute));
+        CU(ctx, cudaStreamWaitEvent(ctx->copy, ctx->ev_a[b], 0));
+        const uint64_t e0 = elems_before(c.r0), e1 = elems_before(c.r1);
+        CU(ctx, cudaMemcpyAsync(out + e0 * ncols, dbuf[b], (e1 - e0) * ncols * 4, cudaMemcpyDeviceToHost, ctx->copy));
+        CU(ctx, cudaEventRecord(ctx->ev_b[b], ctx->copy));
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->copy));
+    CU(ctx, cudaStreamSynchronize(ctx->compute));
+    return timers_collect(ctx);
+}
+
+skd_status run_knn(skd_ctx *ctx, const skd_db *R, const skd_db *Q, bool self, const EpiParams &E, uint64_t knn,
+                   uint64_t row_begin, uint64_t row_end, uint64_t *idx_out, float *d0_out, float *d1_out,
+                   skd_loc out_loc) {
+    // Rows are the A side of the tile kernel (self: the database; cross: queries), columns the refs.
+    const skd_db *A = self ? R : Q, *B = R;
+    const uint64_t n_rows = row_end - row_begin;
+    timers_reset(ctx);
+    if (n_rows == 0) return SKD_OK;
+    const bool with_aux = E.kind == KIND_CORE_ACC;
+    uint32_t cap = 128;
+    while (cap < knn + TS) cap <<= 1;
+    const bool count32 = E.nbins >= 65536;
+    size_t smem = tile_kernel_smem(E.nk, count32, true, cap, with_aux);
+    if (smem > kMaxSmem)
+        return fail(ctx, SKD_ERR_UNSUPPORTED,
+                    "knn=%llu with %d k-mer lengths needs %zu B of shared memory per CTA (limit %zu); use a smaller "
+                    "--knn or the dense output",
+                    (unsigned long long)knn, E.nk, smem, kMaxSmem);
+    SchedParams S{};
+    S.mode = MODE_KNN;
+    S.self_mode = self;
+    S.rb0 = (uint32_t)(row_begin / TS);
+    S.n_rb = (uint32_t)((row_end + TS - 1) / TS) - S.rb0;
+    S.row_begin = row_begin;
+    S.row_end = row_end;
+    S.knn = (uint32_t)knn;
+    S.cap = cap;
+    uint32_t want = (uint32_t)((8ull * ctx->sm_count + S.n_rb - 1) / S.n_rb);  // aim for >= 8 waves of CTAs
+    // every split must be able to fill knn slots or be merged with padding; keep splits coarse
+    S.n_split = std::max(1u, std::min(want, B->dev.nb));
+    S.cb_per_split = (B->dev.nb + S.n_split - 1) / S.n_split;
+    S.n_split = (B->dev.nb + S.cb_per_split - 1) / S.cb_per_split;
+    const size_t part = (size_t)S.n_rb * TS * S.n_split * knn;
+    void *pk, *pa = nullptr;
+    skd_status st = scratch_get(ctx, "knn_key", part * 8, &pk);
+    if (st) return st;
+    if (with_aux) {
+        st = scratch_get(ctx, "knn_aux", part * 4, &pa);
+        if (st) return st;
+    }
+    S.part_key = (unsigned long long *)pk;
+    S.part_aux = (float *)pa;
+    unsigned long long *didx = (unsigned long long *)idx_out;
+    float *dd0 = d0_out, *dd1 = d1_out;
+    if (out_loc == SKD_HOST) {
+        void *p;
+        st = scratch_get(ctx, "knn_idx", n_rows * knn * 8, &p);
+        if (st) return st;
+        didx = (unsigned long long *)p;
+        st = scratch_get(ctx, "knn_d0", n_rows * knn * 4, &p);
+        if (st) return st;
+        dd0 = (float *)p;
+        if (d1_out) {
+            st = scratch_get(ctx, "knn_d1", n_rows * knn * 4, &p);
+            if (st) return st;
+            dd1 = (float *)p;
+        }
+    }
+    st = timer_begin(ctx);
+    if (st) return st;
+    CU(ctx, launch_tiles(A->dev, B->dev, E, S, (uint64_t)S.n_rb * S.n_split, count32, smem, ctx->compute));
+    launch_knn_merge(S.part_key, S.part_aux, S.n_split, S.knn, row_begin - (uint64_t)S.rb0 * TS, n_rows, E.kind, didx,
+                     dd0, dd1, ctx->compute);
+    CU(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    st = timer_end(ctx);
+    if (st) return st;
+    if (out_loc == SKD_HOST) {
+        CU(ctx, cudaMemcpyAsync(idx_out, didx, n_rows * knn * 8, cudaMemcpyDeviceToHost, ctx->compute));
+        CU(ctx, cudaMemcpyAsync(d0_out, dd0, n_rows * knn * 4, cudaMemcpyDeviceToHost, ctx->compute));
+        if (d1_out) CU(ctx, cudaMemcpyAsync(d1_out, dd1, n_rows * knn * 4, cudaMemcpyDeviceToHost, ctx->compute));
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->compute));
+    return timers_collect(ctx);
+}
+
+// Shared by skd_db_upload (host or device array) and skd_db_load_skd (file): `fill` stages samples
+// [s0, s1) into pinned memory, or is null when `direct` already points at them.
+struct ChunkSource {
+    const uint64_t *direct = nullptr;  // array in the reference layout (host or device)
+    skd_loc loc = SKD_HOST;
+    int fd = -1;                       // .skd file
+    const uint64_t *indices = nullptr; // file positions, nullable
+};
+
+skd_status db_build(skd_ctx *ctx, const ChunkSource &src, uint64_t n, uint64_t sample_stride, uint64_t kmer_stride,
+                    uint64_t W, uint64_t sketch_size, const uint64_t *kmers, uint32_t K, skd_db **out) {
+    if (!ctx || !out) return fail(ctx, SKD_ERR_INVALID, "null argument");
+    if (K == 0 || !kmers) return fail(ctx, SKD_ERR_INVALID, "database has no k-mer lengths");
+    if (W == 0 || W > 65535) return fail(ctx, SKD_ERR_UNSUPPORTED, "sketchsize64 %llu outside [1, 65535]", (unsigned long long)W);
+    if (K > 65535) return fail(ctx, SKD_ERR_UNSUPPORTED, "too many k-mer lengths");
+    if (sketch_size == 0) sketch_size = 64 * W;
+    if (kmer_stride < W * BBITS || sample_stride < (uint64_t)(K - 1) * kmer_stride + W * BBITS)
+        return fail(ctx, SKD_ERR_INVALID, "strides too small for sketchsize64=%llu, %u k-mers", (unsigned long long)W, K);
+    if (n >= (1ull << 32) - TS) return fail(ctx, SKD_ERR_UNSUPPORTED, "more than 2^32 samples");
+    CU(ctx, cudaSetDevice(ctx->device));
+    skd_db *db = new (std::nothrow) skd_db;
+    if (!db) return fail(ctx, SKD_ERR_NOMEM, "out of host memory");
+    db->ctx = ctx;
+    db->kmers.assign(kmers, kmers + K);
+    db->sketch_size = sketch_size;
+    db->W = W;
+    db->n = n;
+    db->dev.n = n;
+    db->dev.nb = (uint32_t)((n + TS - 1) / TS);
+    db->dev.W = (uint32_t)W;
+    db->dev.K = K;
+    db->tiled_bytes = (size_t)K * W * db->dev.nb * STAGE_BYTES;
+    auto bail = [&](skd_status st) {
+        skd_db_free(db);
+        return st;
+    };
+#define CUB(expr)                                                                                       \
+    do {                                                                                                \
+        cudaError_t e__ = (expr);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return bail(fail(ctx, SKD_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                             __LINE__));                                                                \
+    } while (0)
+    if (db->tiled_bytes) CUB(cudaMalloc(&db->tiled, db->tiled_bytes));
+    db->dev.tiled = db->tiled;
+    {   // ln J by match count with the host libm (the reference calls f64::ln per pair, jaccard.rs:88)
+        const uint32_t nbins = (uint32_t)(64 * W);
+        std::vector<double> lny((size_t)nbins + 1);
+        for (uint32_t c = 0; c <= nbins; ++c) lny[c] = std::log(host_jaccard(c, nbins));
+        CUB(cudaMalloc(&db->lny_dev, lny.size() * sizeof(double)));
+        CUB(cudaMemcpy(db->lny_dev, lny.data(), lny.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    if (n > 0) {
+        if (src.direct && src.loc == SKD_DEVICE) {
+            launch_repack(src.direct, n, sample_stride, kmer_stride, db->tiled, db->dev, 0, db->dev.nb, ctx->compute);
+            CUB(cudaGetLastError());
+            ctx->launches++;
+            CUB(cudaStreamSynchronize(ctx->compute));
+        } else {
+            // chunks of whole sample blocks: host -> (pinned) -> device raw -> repack, double buffered
+            const size_t block_bytes = (size_t)TS * sample_stride * 8;
+            const uint32_t blocks_per_chunk = (uint32_t)std::max<size_t>(1, kUploadChunkBytes / block_bytes);
+            const size_t chunk_bytes = (size_t)blocks_per_chunk * block_bytes;
+            void *raw[2];
+            skd_status st = scratch_get(ctx, "raw0", chunk_bytes, &raw[0]);
+            if (st) return bail(st);
+            st = scratch_get(ctx, "raw1", chunk_bytes, &raw[1]);
+            if (st) return bail(st);
+            const bool staged = src.fd >= 0;
+            if (staged) {
+                st = pinned_get(ctx, chunk_bytes);
+                if (st) return bail(st);
+            }
+            int c = 0;
+            for (uint32_t b0 = 0; b0 < db->dev.nb; b0 += blocks_per_chunk, ++c) {
+                const int bi = c & 1;
+                const uint32_t nblk = std::min(blocks_per_chunk, db->dev.nb - b0);
+                const uint64_t s0 = (uint64_t)b0 * TS, s1 = std::min<uint64_t>(n, s0 + (uint64_t)nblk * TS);
+                const size_t bytes = (size_t)(s1 - s0) * sample_stride * 8;
+                if (c >= 2) CUB(cudaEventSynchronize(ctx->ev_b[bi]));  // repack of chunk c-2 finished with raw[bi]
+                const void *hsrc;
+                if (staged) {
+                    if (c >= 2) CUB(cudaEventSynchronize(ctx->ev_a[bi]));  // H2D of chunk c-2 finished with pinned[bi]
+                    char *dst = (char *)ctx->pinned[bi];
+                    const size_t sbytes = sample_stride * 8;
+                    if (!src.indices) {
+                        size_t got = 0;
+                        while (got < bytes) {
+                            ssize_t r = pread(src.fd, dst + got, bytes - got, (off_t)(s0 * sbytes + got));
+                            if (r <= 0) return bail(fail(ctx, SKD_ERR_IO, "short read from .skd file"));
+                            got += (size_t)r;
+                        }
+                    } else {
+                        for (uint64_t s = s0; s < s1; ++s) {  // read_batch_from_skd, sketch_datafile.rs:172-194
+                            size_t got = 0;
+                            while (got < sbytes) {
+                                ssize_t r = pread(src.fd, dst + (s - s0) * sbytes + got, sbytes - got,
+                                                  (off_t)(src.indices[s] * sbytes + got));
+                                if (r <= 0) return bail(fail(ctx, SKD_ERR_IO, "short read from .skd file"));
+                                got += (size_t)r;
+                            }
+                        }
+                    }
+                    hsrc = dst;
+                } else {
+                    hsrc = src.direct + s0 * sample_stride;
+                }
+                CUB(cudaMemcpyAsync(raw[bi], hsrc, bytes, cudaMemcpyHostToDevice, ctx->copy));
+                CUB(cudaEventRecord(ctx->ev_a[bi], ctx->copy));
+                CUB(cudaStreamWaitEvent(ctx->compute, ctx->ev_a[bi], 0));
+                launch_repack((const uint64_t *)raw[bi], s1 - s0, sample_stride, kmer_stride, db->tiled, db->dev, b0, nblk,
+                              ctx->compute);
+                CUB(cudaGetLastError());
+                ctx->launches++;
+                CUB(cudaEventRecord(ctx->ev_b[bi], ctx->compute));
+            }
+            CUB(cudaStreamSynchronize(ctx->copy));
+            CUB(cudaStreamSynchronize(ctx->compute));
+        }
+    }
+#undef CUB
+    *out = db;
+    return SKD_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+skd_status skd_ctx_create(int device, skd_ctx **out) {
+    if (!out) return fail(nullptr, SKD_ERR_INVALID, "null output pointer");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, SKD_ERR_CUDA, "no CUDA device available (%s); libsketchdist has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (device < 0 || device >= count) return fail(nullptr, SKD_ERR_INVALID, "device %d out of range [0, %d)", device, count);
+    skd_ctx *ctx = new (std::nothrow) skd_ctx;
+    if (!ctx) return fail(nullptr, SKD_ERR_NOMEM, "out of host memory");
+    ctx->device = device;
+    cudaDeviceProp prop;
+    if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking)) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, SKD_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(e));
+    }
+    if (prop.major != 10) {
+        cudaStreamDestroy(ctx->compute);
+        cudaStreamDestroy(ctx->copy);
+        delete ctx;
+        return fail(nullptr, SKD_ERR_UNSUPPORTED, "device %d is sm_%d%d; libsketchdist is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    for (int i = 0; i < 2; ++i) {
+        cudaEventCreateWithFlags(&ctx->ev_a[i], cudaEventDisableTiming);
+        cudaEventCreateWithFlags(&ctx->ev_b[i], cudaEventDisableTiming);
+    }
+    *out = ctx;
+    return SKD_OK;
+}
+
+void skd_ctx_destroy(skd_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto &kv : ctx->scratch)
+        if (kv.second.first) cudaFree(kv.second.first);
+    for (int i = 0; i < 2; ++i) {
+        if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
+        if (ctx->ev_a[i]) cudaEventDestroy(ctx->ev_a[i]);
+        if (ctx->ev_b[i]) cudaEventDestroy(ctx->ev_b[i]);
+    }
+    for (auto &t : ctx->timers) {
+        cudaEventDestroy(t.first);
+        cudaEventDestroy(t.second);
+    }
+    if (ctx->compute) cudaStreamDestroy(ctx->compute);
+    if (ctx->copy) cudaStreamDestroy(ctx->copy);
+    delete ctx;
+}
+
+const char *skd_last_error(const skd_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+int skd_ctx_device(const skd_ctx *ctx) { return ctx ? ctx->device : -1; }
+uint64_t skd_ctx_launch_count(const skd_ctx *ctx) { return ctx ? ctx->launches : 0; }
+float skd_ctx_last_kernel_ms(const skd_ctx *ctx) { return ctx ? ctx->last_ms : 0.f; }
+void *skd_ctx_stream(const skd_ctx *ctx) { return ctx ? (void *)ctx->compute : nullptr; }
+
+skd_status skd_ctx_synchronize(skd_ctx *ctx) {
+    if (!ctx) return SKD_ERR_INVALID;
+    CU(ctx, cudaStreamSynchronize(ctx->copy));
+    CU(ctx, cudaStreamSynchronize(ctx->compute));
+    return SKD_OK;
+}
+
+skd_status skd_host_alloc(skd_ctx *ctx, size_t bytes, void **out) {
+    if (!ctx || !out) return SKD_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMallocHost(out, std::max<size_t>(bytes, 1)));
+    return SKD_OK;
+}
+void skd_host_free(skd_ctx *ctx, void *ptr) {
+    (void)ctx;
+    if (ptr) cudaFreeHost(ptr);
+}
+skd_status skd_device_alloc(skd_ctx *ctx, size_t bytes, void **out) {
+    if (!ctx || !out) return SKD_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    CU(ctx, cudaMalloc(out, std::max<size_t>(bytes, 1)));
+    return SKD_OK;
+}
+void skd_device_free(skd_ctx *ctx, void *ptr) {
+    (void)ctx;
+    if (ptr) cudaFree(ptr);
+}
+skd_status skd_memcpy(skd_ctx *ctx, void *dst, skd_loc dst_loc, const void *src, skd_loc src_loc, size_t bytes) {
+    if (!ctx) return SKD_ERR_INVALID;
+    (void)dst_loc;
+    (void)src_loc;
+    CU(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->compute));
+    CU(ctx, cudaStreamSynchronize(ctx->compute));
+    return SKD_OK;
+}
+
+skd_status skd_db_upload(skd_ctx *ctx, const uint64_t *bins, skd_loc bins_loc, uint64_t n_samples,
+                         uint64_t sample_stride, uint64_t kmer_stride, uint64_t sketchsize64, uint64_t sketch_size,
+                         const uint64_t *kmer_lengths, uint32_t n_kmers, skd_db **out) {
+    if (!ctx) return fail(nullptr, SKD_ERR_INVALID, "null context");
+    if (n_samples > 0 && !bins) return fail(ctx, SKD_ERR_INVALID, "null bins");
+    ChunkSource src;
+    src.direct = bins;
+    src.loc = bins_loc;
+    return db_build(ctx, src, n_samples, sample_stride, kmer_stride, sketchsize64, sketch_size, kmer_lengths, n_kmers,
+                    out);
+}
+
+skd_status skd_db_load_skd(skd_ctx *ctx, const char *skd_path, const uint64_t *sample_indices, uint64_t n_samples,
+                           uint64_t sample_stride, uint64_t kmer_stride, uint64_t sketchsize64, uint64_t sketch_size,
+                           const uint64_t *kmer_lengths, uint32_t n_kmers, skd_db **out) {
+    if (!ctx) return fail(nullptr, SKD_ERR_INVALID, "null context");
+    if (!skd_path) return fail(ctx, SKD_ERR_INVALID, "null path");
+    int fd = open(skd_path, O_RDONLY);
+    if (fd < 0) return fail(ctx, SKD_ERR_IO, "Could not read from %s", skd_path);  // sketch_datafile.rs:123-125
+    struct stat sb;
+    if (fstat(fd, &sb) != 0) {
+        close(fd);
+        return fail(ctx, SKD_ERR_IO, "Could not stat %s", skd_path);
+    }
+    const uint64_t file_samples = sample_stride ? (uint64_t)sb.st_size / (sample_stride * 8) : 0;
+    for (uint64_t s = 0; s < n_samples; ++s) {
+        uint64_t fi = sample_indices ? sample_indices[s] : s;
+        if (fi >= file_samples) {
+            close(fd);
+            return fail(ctx, SKD_ERR_IO, "%s holds %llu samples; sample index %llu requested", skd_path,
+                        (unsigned long long)file_samples, (unsigned long long)fi);
+        }
+    }
+    ChunkSource src;
+    src.fd = fd;
+    src.indices = sample_indices;
+    skd_status st = db_build(ctx, src, n_samples, sample_stride, kmer_stride, sketchsize64, sketch_size, kmer_lengths,
+                             n_kmers, out);
+    close(fd);
+    return st;
+}
+
+void skd_db_free(skd_db *db) {
+    if (!db) return;
+    if (db->ctx) cudaSetDevice(db->ctx->device);
+    if (db->tiled) cudaFree(db->tiled);
+    if (db->lny_dev) cudaFree(db->lny_dev);
+    delete db;
+}
+uint64_t skd_db_n_samples(const skd_db *db) { return db ? db->n : 0; }
+uint32_t skd_db_n_kmers(const skd_db *db) { return db ? (uint32_t)db->kmers.size() : 0; }
+uint64_t skd_db_sketch_size(const skd_db *db) { return db ? db->sketch_size : 0; }
+uint64_t skd_db_hbm_bytes(const skd_db *db) { return db ? db->tiled_bytes : 0; }
+int skd_db_compatible(const skd_db *a, const skd_db *b) {
+    return a && b && a->kmers == b->kmers && a->sketch_size == b->sketch_size && a->W == b->W;
+}
+
+skd_status skd_set_k(skd_ctx *ctx, const skd_db *db, int64_t kmer, int ani, skd_dist_type *out) {
+    if (!ctx || !db || !out) return fail(ctx, SKD_ERR_INVALID, "null argument");
+    if (kmer < 0) {
+        out->kind = SKD_CORE_ACC;
+        out->k_idx = 0;
+        return SKD_OK;
+    }
+    for (size_t i = 0; i < db->kmers.size(); ++i)
+        if (db->kmers[i] == (uint64_t)kmer) {  // get_k_idx: first match, multisketch.rs:115-121
+            out->kind = ani ? SKD_ANI : SKD_JACCARD;
+            out->k_idx = (int32_t)i;
+            return SKD_OK;
+        }
+    return fail(ctx, SKD_ERR_K_NOT_FOUND, "K-mer size %lld not found in file", (long long)kmer);
+}
+
+uint64_t skd_self_pairs_in_rows(uint64_t n, uint64_t row_begin, uint64_t row_end) {
+    if (n < 2 || row_begin >= row_end) return 0;
+    row_end = std::min(row_end, n);
+    if (row_begin >= row_end) return 0;
+    // sum_{i=row_begin}^{row_end-1} (n - 1 - i)
+    uint64_t cnt = row_end - row_begin;
+    return cnt * (n - 1) - (row_begin + row_end - 1) * cnt / 2;
+}
+
+skd_status skd_self_dists_all(skd_ctx *ctx, const skd_db *db, skd_dist_type dist, const double *completeness,
+                              double cutoff, uint64_t row_begin, uint64_t row_end, float *out, skd_loc out_loc) {
+    skd_status st = check_pair(ctx, db, db);
+    if (st) return st;
+    CU(ctx, cudaSetDevice(ctx->device));
+    EpiParams E;
+    st = build_epi(ctx, db, db, dist, completeness, completeness, cutoff, &E);
+    if (st) return st;
+    row_end = std::min(row_end, db->n);
+    if (db->n < 2 || row_begin >= row_end) {
+        timers_reset(ctx);
+        ctx->last_ms = 0.f;
+        return SKD_OK;
+    }
+    if (!out) return fail(ctx, SKD_ERR_INVALID, "null output");
+    return run_dense(ctx, db, db, true, E, MODE_DENSE_SELF, row_begin, row_end, out, out_loc);
+}
+
+skd_status skd_cross_dists_all(skd_ctx *ctx, const skd_db *ref, const skd_db *query, skd_dist_type dist,
+                               const double *ref_c, const double *query_c, double cutoff, uint64_t ref_begin,
+                               uint64_t ref_end, float *out, skd_loc out_loc) {
+    skd_status st = check_pair(ctx, ref, query);
+    if (st) return st;
+    CU(ctx, cudaSetDevice(ctx->device));
+    EpiParams E;
+    st = build_epi(ctx, ref, query, dist, ref_c, query_c, cutoff, &E);
+    if (st) return st;
+    ref_end = std::min(ref_end, ref->n);
+    if (ref_begin >= ref_end || query->n == 0) {
+        timers_reset(ctx);
+        ctx->last_ms = 0.f;
+        return SKD_OK;
+    }
+    if (!out) return fail(ctx, SKD_ERR_INVALID, "null output");
+    return run_dense(ctx, ref, query, false, E, MODE_DENSE_CROSS, ref_begin, ref_end, out, out_loc);
+}
+
+skd_status skd_self_dists_knn(skd_ctx *ctx, const skd_db *db, uint64_t knn, skd_dist_type dist,
+                              const double *completeness, double cutoff, uint64_t row_begin, uint64_t row_end,
+                              uint64_t *idx_out, float *d0_out, float *d1_out, skd_loc out_loc) {
+    skd_status st = check_pair(ctx, db, db);
+    if (st) return st;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (db->n < 2 || knn == 0 || knn > db->n - 1)
+        return fail(ctx, SKD_ERR_INVALID, "knn must be in [1, n-1] (n = %llu, knn = %llu)", (unsigned long long)db->n,
+                    (unsigned long long)knn);
+    EpiParams E;
+    st = build_epi(ctx, db, db, dist, completeness, completeness, cutoff, &E);
+    if (st) return st;
+    row_end = std::min(row_end, db->n);
+    if (row_begin > row_end) row_begin = row_end;
+    if (!idx_out || !d0_out) return fail(ctx, SKD_ERR_INVALID, "null output");
+    return run_knn(ctx, db, db, true, E, knn, row_begin, row_end, idx_out, d0_out, d1_out, out_loc);
+}
+
+skd_status skd_cross_dists_knn(skd_ctx *ctx, const skd_db *ref, const skd_db *query, uint64_t knn, skd_dist_type dist,
+                               const double *ref_c, const double *query_c, double cutoff, uint64_t query_begin,
+                               uint64_t query_end, uint64_t *idx_out, float *d0_out, float *d1_out, skd_loc out_loc,
+                               uint64_t *knn_used) {
+    skd_status st = check_pair(ctx, ref, query);
+    if (st) return st;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (ref->n == 0) return fail(ctx, SKD_ERR_EMPTY_DB, "Reference database has no loaded samples");
+    if (query->n == 0) return fail(ctx, SKD_ERR_EMPTY_DB, "Query database has no loaded samples");
+    if (knn == 0) return fail(ctx, SKD_ERR_INVALID, "knn must be at least 1");
+    knn = std::min<uint64_t>(knn, ref->n);  // mod.rs:325
+    if (knn_used) *knn_used = knn;
+    EpiParams E;
+    // tile rows are queries (A side), columns refs (B side): completeness sides swap accordingly
+    st = build_epi(ctx, query, ref, dist, query_c, ref_c, cutoff, &E);
+    if (st) return st;
+    query_end = std::min(query_end, query->n);
+    if (query_begin > query_end) query_begin = query_end;
+    if (!idx_out || !d0_out) return fail(ctx, SKD_ERR_INVALID, "null output");
+    return run_knn(ctx, ref, query, false, E, knn, query_begin, query_end, idx_out, d0_out, d1_out, out_loc);
+}
+
+static skd_status pairs_common(skd_ctx *ctx, const skd_db *ref, const skd_db *query, const EpiParams &E,
+                               const uint64_t *pairs, uint64_t n_pairs, uint32_t *counts, float *dists, int ncols) {
+    timers_reset(ctx);
+    if (n_pairs == 0) return SKD_OK;
+    for (uint64_t p = 0; p < n_pairs; ++p)
+        if (pairs[2 * p] >= ref->n || pairs[2 * p + 1] >= query->n)
+            return fail(ctx, SKD_ERR_INVALID, "pair %llu out of range", (unsigned long long)p);
+    void *dp, *dc = nullptr, *dd = nullptr;
+    skd_status st = scratch_get(ctx, "pairs", n_pairs * 16, &dp);
+    if (st) return st;
+    if (counts) {
+        st = scratch_get(ctx, "pair_counts", n_pairs * ref->kmers.size() * 4, &dc);
+        if (st) return st;
+    }
+    if (dists) {
+        st = scratch_get(ctx, "pair_dists", n_pairs * ncols * 4, &dd);
+        if (st) return st;
+    }
+    CU(ctx, cudaMemcpyAsync(dp, pairs, n_pairs * 16, cudaMemcpyHostToDevice, ctx->compute));
+    st = timer_begin(ctx);
+    if (st) return st;
+    launch_pairs(ref->dev, query->dev, E, (const uint64_t *)dp, n_pairs, (uint32_t *)dc, (float *)dd, ctx->compute);
+    CU(ctx, cudaGetLastError());
+    ctx->launches++;
+    st = timer_end(ctx);
+    if (st) return st;
+    if (counts)
+        CU(ctx, cudaMemcpyAsync(counts, dc, n_pairs * ref->kmers.size() * 4, cudaMemcpyDeviceToHost, ctx->compute));
+    if (dists) CU(ctx, cudaMemcpyAsync(dists, dd, n_pairs * ncols * 4, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(ctx, cudaStreamSynchronize(ctx->compute));
+    return timers_collect(ctx);
+}
+
+skd_status skd_pair_dists(skd_ctx *ctx, const skd_db *ref, const skd_db *query, skd_dist_type dist, const double *ref_c,
+                          const double *query_c, double cutoff, const uint64_t *pairs, uint64_t n_pairs, float *out) {
+    skd_status st = check_pair(ctx, ref, query);
+    if (st) return st;
+    CU(ctx, cudaSetDevice(ctx->device));
+    EpiParams E;
+    st = build_epi(ctx, ref, query, dist, ref_c, query_c, cutoff, &E);
+    if (st) return st;
+    if (n_pairs && (!pairs || !out)) return fail(ctx, SKD_ERR_INVALID, "null argument");
+    return pairs_common(ctx, ref, query, E, pairs, n_pairs, nullptr, out, dist.kind == SKD_CORE_ACC ? 2 : 1);
+}
+
+skd_status skd_match_counts(skd_ctx *ctx, const skd_db *ref, const skd_db *query, const uint64_t *pairs,
+                            uint64_t n_pairs, uint32_t *counts) {
+    skd_status st = check_pair(ctx, ref, query);
+    if (st) return st;
+    CU(ctx, cudaSetDevice(ctx->device));
+    EpiParams E;
+    memset(&E, 0, sizeof E);
+    E.kind = KIND_JACCARD;
+    E.nbins = (uint32_t)(64 * ref->W);
+    E.nk = 1;
+    if (n_pairs && (!pairs || !counts)) return fail(ctx, SKD_ERR_INVALID, "null argument");
+    return pairs_common(ctx, ref, query, E, pairs, n_pairs, counts, nullptr, 0);
+}
+
+skd_status skd_match_counts_dense(skd_ctx *ctx, const skd_db *ref, const skd_db *query, uint64_t ref_begin,
+                                  uint64_t ref_end, uint32_t *counts) {
+    skd_status st = check_pair(ctx, ref, query);
+    if (st) return st;
+    CU(ctx, cudaSetDevice(ctx->device));
+    EpiParams E;
+    memset(&E, 0, sizeof E);
+    E.kind = KIND_CORE_ACC;  // visit every k
+    E.nbins = (uint32_t)(64 * ref->W);
+    E.k0 = 0;
+    E.nk = (int)ref->kmers.size();
+    ref_end = std::min(ref_end, ref->n);
+    if (ref_begin >= ref_end || query->n == 0) return SKD_OK;
+    if (!counts) return fail(ctx, SKD_ERR_INVALID, "null output");
+    return run_dense(ctx, ref, query, false, E, MODE_COUNTS, ref_begin, ref_end, (float *)counts, SKD_HOST);
+}
+
+}  // extern "C"

@@ -1,0 +1,602 @@
+// CUDA kernels (sm_100a) for the pairwise sketch-distance path.
+//
+//   repack_kernel      reference .skd layout -> tiled HBM layout (layout.h)            [HBM bound]
+//   tile_kernel        64x64 pair tiles: TMA-staged bit planes, LOP3/POPC match counts,
+//                      fused Jaccard / ANI / core-accessory epilogue, dense or kNN output [INT-ALU bound]
+//   knn_merge_kernel   merges per-split candidate lists into the final sparse rows
+//   pair_kernel        explicit (ref, query) pair list: counts and distances (debug / candidate lists)
+//
+// Arithmetic restated from the reference: src/distances/jaccard.rs (whole file).
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "kernels.h"
+#include "layout.h"
+
+namespace skd {
+
+// ------------------------------------------------------------------------------------------------
+// PTX helpers: mbarrier + bulk async copy (TMA, SASS UBLKCP)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Loader: reference layout (u64 [sample][k][w][plane]) -> tiled layout.  One CTA per (block, w, k).
+__global__ void __launch_bounds__(256) repack_kernel(const uint64_t *__restrict__ raw, uint64_t raw_samples,
+                                                     uint64_t sample_stride, uint64_t kmer_stride,
+                                                     uint32_t *__restrict__ tiled, DevDb db, uint32_t b0) {
+    __shared__ uint64_t sh[TS][BBITS + 1];
+    const uint32_t b = b0 + blockIdx.x, w = blockIdx.y, k = blockIdx.z;
+    for (int t = threadIdx.x; t < TS * BBITS; t += blockDim.x) {
+        int s = t / BBITS, p = t % BBITS;
+        uint64_t ls = (uint64_t)blockIdx.x * TS + s;  // sample index inside `raw`
+        uint64_t v = 0;
+        if (ls < raw_samples) v = raw[ls * sample_stride + (uint64_t)k * kmer_stride + (uint64_t)w * BBITS + p];
+        sh[s][p] = v;
+    }
+    __syncthreads();
+    uint2 *dst = reinterpret_cast<uint2 *>(tiled + slab_index(db, k, w, b) * STAGE_U32);
+    for (int e = threadIdx.x; e < 2 * PP * TS; e += blockDim.x) {
+        int half = e / (PP * TS), pp = (e / TS) % PP, s = e % TS;
+        uint64_t lo = sh[s][2 * pp], hi = sh[s][2 * pp + 1];
+        uint2 v;
+        v.x = (uint32_t)(lo >> (32 * half));
+        v.y = (uint32_t)(hi >> (32 * half));
+        dst[e] = v;
+    }
+}
+
+void launch_repack(const uint64_t *raw, uint64_t raw_samples, uint64_t sample_stride, uint64_t kmer_stride,
+                   uint32_t *tiled, const DevDb &db, uint32_t b0, uint32_t n_blocks, cudaStream_t st) {
+    dim3 grid(n_blocks, db.W, db.K);
+    repack_kernel<<<grid, 256, 0, st>>>(raw, raw_samples, sample_stride, kmer_stride, tiled, db, b0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue arithmetic.  All f64 operations use the explicit round-to-nearest intrinsics so that no
+// FMA contraction can change a rounding relative to the reference's (jaccard.rs) operation order.
+__device__ __forceinline__ double jaccard_from_count(uint32_t c, const EpiParams &E) {
+    // jaccard.rs:26-33
+    uint32_t diff = c > E.expected ? c - E.expected : 0u;
+    double intersize = __ddiv_rn(__dmul_rn((double)diff, (double)E.nbins), (double)(E.nbins - E.expected));
+    return __ddiv_rn(intersize, (double)E.nbins);
+}
+__device__ __forceinline__ double corrected_jaccard(uint32_t c, double c1, double c2, const EpiParams &E) {
+    // jaccard.rs:36-42, 55-57
+    double j = jaccard_from_count(c, E);
+    double c12 = __dmul_rn(c1, c2);
+    if (c12 >= E.cutoff) {
+        j = __ddiv_rn(j, __ddiv_rn(c12, __dsub_rn(__dadd_rn(c1, c2), c12)));
+        j = fmin(j, 1.0);
+    }
+    return j;
+}
+__device__ __forceinline__ double ani_pois_dev(double j, double k) {
+    // jaccard.rs:49-51
+    double q = __ddiv_rn(__dmul_rn(2.0, j), __dadd_rn(1.0, j));
+    return fmax(0.0, __dadd_rn(1.0, __dmul_rn(__ddiv_rn(1.0, k), log(q))));
+}
+
+// simple_linear_regression (jaccard.rs:105-142) with the x statistics tabulated per n.
+__device__ __forceinline__ void regress(double ysum, double xysum, double ysq, int n, const EpiParams &E,
+                                        float &core_out, float &acc_out) {
+    if (n < 3) {  // ysum cannot be NaN or -inf here: such a y breaks the loop first
+        core_out = 1.0f;
+        acc_out = 1.0f;
+        return;
+    }
+    const double dn = (double)n;
+    const double xsum = E.xsum[n];
+    double ybar = __ddiv_rn(ysum, dn);
+    double y_diff = __dsub_rn(ysq, __ddiv_rn(__dmul_rn(ysum, ysum), dn));
+    double ystddev = __dsqrt_rn(__ddiv_rn(y_diff, dn));
+    double r = __ddiv_rn(__dsub_rn(xysum, __ddiv_rn(__dmul_rn(xsum, ysum), dn)),
+                         __dsqrt_rn(__dmul_rn(E.x_diff[n], y_diff)));
+    double beta = __ddiv_rn(__dmul_rn(r, ystddev), E.xstddev[n]);
+    double alpha = __dadd_rn(__dmul_rn(-beta, E.xbar[n]), ybar);
+    double core = 0.0, acc = 0.0;
+    if (beta < 0.0) {
+        core = __dsub_rn(1.0, exp(beta));
+    } else if (r > 0.0) {
+        core = 1.0;
+    }
+    if (alpha < 0.0) acc = __dsub_rn(1.0, exp(alpha));
+    core_out = (float)core;
+    acc_out = (float)acc;
+}
+
+// Total-order key for non-NaN floats, so that (key, idx) sorts as one u64.
+__device__ __forceinline__ uint32_t float_order_bits(float f) {
+    uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float float_from_order_bits(uint32_t b) {
+    return __uint_as_float((b & 0x80000000u) ? (b & 0x7fffffffu) : ~b);
+}
+
+// ------------------------------------------------------------------------------------------------
+// The tile kernel.
+//
+// Shared memory:  [NST stages x (A slab 7168 B + B slab 7168 B)] [counts nk x 4096 x CountT]
+//                 [mbarriers] [kNN candidate lists]
+// Thread tile: rows  arow0 + 4*i (i<4), cols bcol0 + 8*j (j<4) with arow0 = 16*(warp/2) + lane/8,
+// bcol0 = 32*(warp%2) + lane%8.  For one plane pair a warp's four A loads are 4 distinct 8-byte words
+// (broadcast) and its B loads 8 adjacent ones: no bank conflicts.
+struct TileCoord {
+    uint32_t rb, cb;
+};
+
+template <typename CountT>
+__device__ __forceinline__ void tile_counts(const DevDb &A, const DevDb &B, uint32_t rb, uint32_t cb, int k0, int nk,
+                                            uint32_t *stage_mem, uint64_t *full_bar, CountT *counts, uint32_t &git) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int arow0 = 16 * (warp >> 1) + (lane >> 3);
+    const int bcol0 = 32 * (warp & 1) + (lane & 7);
+    const uint32_t W = A.W;
+    const uint32_t n_it = (uint32_t)nk * W;
+
+    auto issue = [&](uint32_t it) {
+        uint32_t k = (uint32_t)k0 + it / W, w = it % W;
+        uint32_t g = git + it;
+        uint32_t *dst = stage_mem + (g % NST) * (2 * STAGE_U32);
+        uint64_t *bar = &full_bar[g % NST];
+        mbar_expect_tx(bar, 2 * STAGE_BYTES);
+        bulk_g2s(dst, A.tiled + slab_index(A, k, w, rb) * STAGE_U32, STAGE_BYTES, bar);
+        bulk_g2s(dst + STAGE_U32, B.tiled + slab_index(B, k, w, cb) * STAGE_U32, STAGE_BYTES, bar);
+    };
+
+    if (tid == 0) {
+        uint32_t pre = n_it < (uint32_t)(NST - 1) ? n_it : (uint32_t)(NST - 1);
+        for (uint32_t p = 0; p < pre; ++p) issue(p);
+    }
+
+    uint32_t mism[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mism[i][j] = 0;
+
+    uint32_t w_in_k = 0, kk = 0;
+    for (uint32_t it = 0; it < n_it; ++it) {
+        if (it > 0) __syncthreads();  // every warp is done with iteration it-1: its stage may be refilled
+        if (tid == 0 && it + NST - 1 < n_it) issue(it + NST - 1);
+        const uint32_t g = git + it;
+        mbar_wait(&full_bar[g % NST], (g / NST) & 1u);
+        const uint2 *sa = reinterpret_cast<const uint2 *>(stage_mem + (g % NST) * (2 * STAGE_U32));
+        const uint2 *sb = sa + STAGE_U32 / 2;
+
+        uint32_t pc0[4][4];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t d[4][4];
+#pragma unroll
+            for (int pp = 0; pp < PP; ++pp) {
+                uint2 av[4], bv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) av[i] = sa[(half * PP + pp) * TS + arow0 + 4 * i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bv[j] = sb[(half * PP + pp) * TS + bcol0 + 8 * j];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (pp == 0)
+                            d[i][j] = av[i].x ^ bv[j].x;
+                        else
+                            d[i][j] |= av[i].x ^ bv[j].x;
+                        d[i][j] |= av[i].y ^ bv[j].y;
+                    }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    if (half == 0)
+                        pc0[i][j] = __popc(d[i][j]);
+                    else
+                        mism[i][j] += pc0[i][j] + __popc(d[i][j]);  // one 3-input add per 64 bins
+                }
+        }
+
+        if (++w_in_k == W) {  // finished this k: park the match counts in shared memory
+            const uint32_t nbins = 64u * W;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    counts[kk * (TS * TS) + (arow0 + 4 * i) * TS + bcol0 + 8 * j] = (CountT)(nbins - mism[i][j]);
+                    mism[i][j] = 0;
+                }
+            w_in_k = 0;
+            ++kk;
+        }
+    }
+    git += n_it;
+    __syncthreads();  // counts visible to all; all stages consumed
+}
+
+// One pair's distances from its counts in shared memory.  Returns key (first distance) and aux.
+template <typename CountT>
+__device__ __forceinline__ void pair_epilogue(const CountT *counts, int pair, const EpiParams &E, uint64_t gi,
+                                              uint64_t gj, bool for_knn, float &d0, float &d1) {
+    const bool comp = E.has_c != 0;
+    double c1 = 0.0, c2 = 0.0;
+    if (comp) {
+        c1 = E.a_comp[gi];
+        c2 = E.b_comp[gj];
+    }
+    if (E.kind == KIND_CORE_ACC) {
+        // core_acc_dist, jaccard.rs:73-100
+        double ysum = 0.0, xysum = 0.0, ysq = 0.0;
+        int n = 0;
+        for (int k = 0; k < E.nk; ++k) {
+            uint32_t c = counts[k * (TS * TS) + pair];
+            double y = comp ? log(corrected_jaccard(c, c1, c2, E)) : __ldg(&E.lny[c]);
+            if (y < E.tolerance) break;
+            ysum = __dadd_rn(ysum, y);
+            xysum = __dadd_rn(xysum, __dmul_rn(E.kf[k], y));
+            ysq = __dadd_rn(ysq, __dmul_rn(y, y));
+            ++n;
+        }
+        regress(ysum, xysum, ysq, n, E, d0, d1);
+    } else {
+        uint32_t c = counts[pair];
+        d1 = 0.0f;
+        if (!comp) {
+            d0 = for_knn ? __ldg(&E.key_tab[c]) : __ldg(&E.val_tab[c]);
+        } else {
+            double j = corrected_jaccard(c, c1, c2, E);
+            if (E.kind == KIND_ANI) {
+                double a = ani_pois_dev(j, E.k_single);
+                d0 = for_knn ? (float)__dsub_rn(1.0, a) : (float)a;
+            } else {
+                d0 = (float)__dsub_rn(1.0, j);
+            }
+        }
+    }
+}
+
+// Warp-level bitonic sort of P (power of two) u64 keys (+ optional aux payload) in shared memory.
+__device__ __forceinline__ void warp_bitonic_sort(unsigned long long *key, float *aux, int P, int lane) {
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncwarp();
+            for (int t = lane; t < P / 2; t += 32) {
+                int lo = 2 * t - (t & (stride - 1));  // index with bit `stride` clear
+                int hi = lo + stride;
+                bool up = (lo & size) == 0;
+                unsigned long long a = key[lo], b = key[hi];
+                if ((a > b) == up) {
+                    key[lo] = b;
+                    key[hi] = a;
+                    if (aux) {
+                        float x = aux[lo];
+                        aux[lo] = aux[hi];
+                        aux[hi] = x;
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+}
+
+template <typename CountT>
+__global__ void __launch_bounds__(THREADS, 2)
+    tile_kernel(const __grid_constant__ DevDb A, const __grid_constant__ DevDb B, const __grid_constant__ EpiParams E,
+                const __grid_constant__ SchedParams S) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t *stage_mem = reinterpret_cast<uint32_t *>(smem_raw);
+    CountT *counts = reinterpret_cast<CountT *>(smem_raw + NST * 2 * STAGE_BYTES);
+    size_t off = (size_t)NST * 2 * STAGE_BYTES + (size_t)E.nk * TS * TS * sizeof(CountT);
+    off = (off + 15) & ~(size_t)15;
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_raw + off);
+    off += 64;
+
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        for (int s = 0; s < NST; ++s) mbar_init(&full_bar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    uint32_t git = 0;
+
+    if (S.mode != MODE_KNN) {
+        // ---- dense / counts: one tile per CTA; linear tile id -> (row block, col block) through L2 groups
+        const uint64_t t = blockIdx.x;
+        uint32_t lo = 0, hi = S.n_groups;  // largest g with grp_off[g] <= t
+        while (hi - lo > 1) {
+            uint32_t mid = (lo + hi) >> 1;
+            if (S.grp_off[mid] <= t) lo = mid; else hi = mid;
+        }
+        const uint32_t g = lo;
+        const uint32_t rows_in_g = min(S.group, S.n_rb - g * S.group);
+        const uint64_t local = t - S.grp_off[g];
+        const uint32_t rb = S.rb0 + g * S.group + (uint32_t)(local % rows_in_g);
+        const uint32_t cb_first = S.mode == MODE_DENSE_SELF ? S.rb0 + g * S.group : 0u;
+        const uint32_t cb = cb_first + (uint32_t)(local / rows_in_g);
+        if (S.mode == MODE_DENSE_SELF && cb < rb) return;  // below the diagonal (only inside a diagonal group)
+
+        tile_counts<CountT>(A, B, rb, cb, E.k0, E.nk, stage_mem, full_bar, counts, git);
+
+        const uint64_t nA = A.n, nB = B.n;
+        for (int m = 0; m < (TS * TS) / THREADS; ++m) {
+            const int pair = m * THREADS + tid;
+            const uint64_t gi = (uint64_t)rb * TS + pair / TS, gj = (uint64_t)cb * TS + pair % TS;
+            if (gi < S.row_begin || gi >= S.row_end || gj >= nB) continue;
+            if (S.mode == MODE_COUNTS) {
+                uint32_t *o = reinterpret_cast<uint32_t *>(S.out) + ((gi - S.row_begin) * nB + gj) * (uint64_t)E.nk;
+                for (int k = 0; k < E.nk; ++k) o[k] = counts[k * (TS * TS) + pair];
+                continue;
+            }
+            uint64_t idx;
+            if (S.mode == MODE_DENSE_SELF) {
+                if (gj <= gi) continue;
+                idx = nA * gi - ((gi * (gi + 1)) >> 1) + gj - 1 - gi - S.out_base;  // square_to_condensed
+            } else {
+                idx = (gi - S.row_begin) * nB + gj;  // ref-major
+            }
+            float d0, d1;
+            pair_epilogue<CountT>(counts, pair, E, gi, gj, false, d0, d1);
+            if (E.kind == KIND_CORE_ACC)
+                reinterpret_cast<float2 *>(S.out)[idx] = make_float2(d0, d1);
+            else
+                S.out[idx] = d0;
+        }
+        return;
+    }
+
+    // ---- kNN: this CTA owns row block rb and scans column blocks [cb_lo, cb_hi)
+    const bool with_aux = E.kind == KIND_CORE_ACC;
+    unsigned long long *cand_key = reinterpret_cast<unsigned long long *>(smem_raw + off);
+    off += (size_t)TS * S.cap * sizeof(unsigned long long);
+    float *cand_aux = reinterpret_cast<float *>(smem_raw + off);
+    if (with_aux) off += (size_t)TS * S.cap * sizeof(float);
+    unsigned long long *thr = reinterpret_cast<unsigned long long *>(smem_raw + off);
+    off += TS * sizeof(unsigned long long);
+    uint32_t *cand_cnt = reinterpret_cast<uint32_t *>(smem_raw + off);
+
+    const uint32_t rbl = blockIdx.x / S.n_split, split = blockIdx.x % S.n_split;
+    const uint32_t rb = S.rb0 + rbl;
+    const uint32_t cb_lo = split * S.cb_per_split;
+    const uint32_t cb_hi = min(B.nb, cb_lo + S.cb_per_split);
+    const int warp = tid >> 5, lane = tid & 31;
+    const uint32_t cap = S.cap, knn = S.knn;
+
+    for (int r = tid; r < TS; r += THREADS) {
+        thr[r] = ~0ull;
+        cand_cnt[r] = 0;
+    }
+    for (uint32_t e = tid; e < TS * cap; e += THREADS) cand_key[e] = ~0ull;
+    __syncthreads();
+
+    for (uint32_t cb = cb_lo; cb < cb_hi; ++cb) {
+        tile_counts<CountT>(A, B, rb, cb, E.k0, E.nk, stage_mem, full_bar, counts, git);
+        for (int m = 0; m < (TS * TS) / THREADS; ++m) {
+            const int pair = m * THREADS + tid;
+            const int row = pair / TS;
+            const uint64_t gi = (uint64_t)rb * TS + row, gj = (uint64_t)cb * TS + pair % TS;
+            if (gi < S.row_begin || gi >= S.row_end || gj >= B.n) continue;
+            if (S.self_mode && gi == gj) continue;
+            float d0, d1;
+            pair_epilogue<CountT>(counts, pair, E, gi, gj, true, d0, d1);
+            unsigned long long comp = ((unsigned long long)float_order_bits(d0) << 32) | (uint32_t)gj;
+            if (comp < thr[row]) {
+                uint32_t slot = atomicAdd(&cand_cnt[row], 1u);
+                cand_key[row * cap + slot] = comp;
+                if (with_aux) cand_aux[row * cap + slot] = d1;
+            }
+        }
+        __syncthreads();
+        // compact rows that could overflow during the next tile
+        for (int row = warp; row < TS; row += THREADS / 32) {
+            uint32_t c = cand_cnt[row];
+            if (c + TS > cap) {
+                warp_bitonic_sort(cand_key + row * cap, with_aux ? cand_aux + row * cap : nullptr, (int)cap, lane);
+                for (uint32_t e = knn + lane; e < cap; e += 32) cand_key[row * cap + e] = ~0ull;
+                if (lane == 0) {
+                    cand_cnt[row] = knn;
+                    thr[row] = cand_key[row * cap + knn - 1];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // final sort and hand-off of this split's best knn per row
+    for (int row = warp; row < TS; row += THREADS / 32) {
+        warp_bitonic_sort(cand_key + row * cap, with_aux ? cand_aux + row * cap : nullptr, (int)cap, lane);
+        const uint64_t lrow = (uint64_t)rbl * TS + row;
+        unsigned long long *pk = S.part_key + (lrow * S.n_split + split) * knn;
+        float *pa = with_aux ? S.part_aux + (lrow * S.n_split + split) * knn : nullptr;
+        for (uint32_t e = lane; e < knn; e += 32) {
+            pk[e] = cand_key[row * cap + e];
+            if (with_aux) pa[e] = cand_aux[row * cap + e];
+        }
+    }
+}
+
+size_t tile_kernel_smem(int nk, bool count32, bool knn_mode, uint32_t cap, bool with_aux) {
+    size_t off = (size_t)NST * 2 * STAGE_BYTES + (size_t)nk * TS * TS * (count32 ? 4 : 2);
+    off = (off + 15) & ~(size_t)15;
+    off += 64;
+    if (knn_mode) {
+        off += (size_t)TS * cap * 8;
+        if (with_aux) off += (size_t)TS * cap * 4;
+        off += TS * 8 + TS * 4;
+    }
+    return off;
+}
+
+cudaError_t launch_tiles(const DevDb &A, const DevDb &B, const EpiParams &E, const SchedParams &S, uint64_t n_ctas,
+                         bool count32, size_t smem, cudaStream_t st) {
+    if (n_ctas == 0) return cudaSuccess;
+    if (n_ctas > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    cudaError_t err;
+    if (count32) {
+        err = cudaFuncSetAttribute(tile_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        tile_kernel<uint32_t><<<(unsigned)n_ctas, THREADS, smem, st>>>(A, B, E, S);
+    } else {
+        err = cudaFuncSetAttribute(tile_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        tile_kernel<uint16_t><<<(unsigned)n_ctas, THREADS, smem, st>>>(A, B, E, S);
+    }
+    return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------
+// kNN merge: one warp per row merges n_split ascending lists of knn composites and writes the final
+// sparse row (neighbour index, first distance, second distance).  ANI keys are un-transformed as
+// 1.0f - key like the reference (src/distances/mod.rs:183-189).
+__global__ void knn_merge_kernel(const unsigned long long *__restrict__ part_key, const float *__restrict__ part_aux,
+                                 uint32_t n_split, uint32_t knn, uint64_t first_lrow, uint64_t n_rows, int kind,
+                                 unsigned long long *__restrict__ idx_out, float *__restrict__ d0_out,
+                                 float *__restrict__ d1_out) {
+    const uint64_t row = (uint64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x & 31;
+    if (row >= n_rows) return;
+    const uint64_t lrow = first_lrow + row;
+    const unsigned long long *pk = part_key + lrow * n_split * knn;
+    const float *pa = part_aux ? part_aux + lrow * n_split * knn : nullptr;
+    const uint32_t total = n_split * knn;
+    // rank of element e = number of elements smaller than it (composites are unique per row except padding)
+    for (uint32_t e = lane; e < total; e += 32) {
+        unsigned long long v = pk[e];
+        if (v == ~0ull) continue;
+        uint32_t rank = 0;
+        for (uint32_t s = 0; s < n_split; ++s) {
+            // binary search in list s for the number of entries < v
+            const unsigned long long *l = pk + s * knn;
+            uint32_t lo = 0, hi = knn;
+            while (lo < hi) {
+                uint32_t mid = (lo + hi) >> 1;
+                if (l[mid] < v) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < knn) {
+            float key = float_from_order_bits((uint32_t)(v >> 32));
+            idx_out[row * knn + rank] = (unsigned long long)(uint32_t)v;
+            d0_out[row * knn + rank] = kind == KIND_ANI ? 1.0f - key : key;
+            if (d1_out) d1_out[row * knn + rank] = pa ? pa[e] : 0.0f;
+        }
+    }
+}
+
+void launch_knn_merge(const unsigned long long *part_key, const float *part_aux, uint32_t n_split, uint32_t knn,
+                      uint64_t first_lrow, uint64_t n_rows, int kind, unsigned long long *idx_out, float *d0_out,
+                      float *d1_out, cudaStream_t st) {
+    if (n_rows == 0) return;
+    const int warps = 8;
+    knn_merge_kernel<<<(unsigned)((n_rows + warps - 1) / warps), warps * 32, 0, st>>>(
+        part_key, part_aux, n_split, knn, first_lrow, n_rows, kind, idx_out, d0_out, d1_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Explicit pair list: one warp per pair.  counts_out (nullable): [pair][K]; dist_out (nullable): 1 or 2 floats.
+__global__ void pair_kernel(const __grid_constant__ DevDb A, const __grid_constant__ DevDb B,
+                            const __grid_constant__ EpiParams E, const uint64_t *__restrict__ pairs, uint64_t n_pairs,
+                            uint32_t *__restrict__ counts_out, float *__restrict__ dist_out) {
+    const uint64_t p = (uint64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x & 31;
+    if (p >= n_pairs) return;
+    const uint64_t gi = pairs[2 * p], gj = pairs[2 * p + 1];
+    const uint32_t ba = (uint32_t)(gi / TS), sa = (uint32_t)(gi % TS), bb = (uint32_t)(gj / TS), sb = (uint32_t)(gj % TS);
+    const bool all_k = counts_out != nullptr || E.kind == KIND_CORE_ACC;
+    const int k_lo = all_k ? 0 : E.k0, k_hi = all_k ? (int)A.K : E.k0 + 1;
+    double ysum = 0.0, xysum = 0.0, ysq = 0.0;
+    int n = 0;
+    bool broke = false;
+    const bool comp = E.has_c != 0;
+    double c1 = 0.0, c2 = 0.0;
+    if (comp) {
+        c1 = E.a_comp[gi];
+        c2 = E.b_comp[gj];
+    }
+    float d0 = 0.0f, d1 = 0.0f;
+    for (int k = k_lo; k < k_hi; ++k) {
+        uint32_t mism = 0;
+        for (uint32_t wc = lane; wc < 2 * A.W; wc += 32) {
+            const uint2 *pa = reinterpret_cast<const uint2 *>(A.tiled + slab_index(A, k, wc >> 1, ba) * STAGE_U32 +
+                                                               (wc & 1) * HALF_U32);
+            const uint2 *pb = reinterpret_cast<const uint2 *>(B.tiled + slab_index(B, k, wc >> 1, bb) * STAGE_U32 +
+                                                               (wc & 1) * HALF_U32);
+            uint32_t d = 0;
+#pragma unroll
+            for (int pp = 0; pp < PP; ++pp) {
+                uint2 a = pa[pp * TS + sa], b = pb[pp * TS + sb];
+                d |= (a.x ^ b.x) | (a.y ^ b.y);
+            }
+            mism += __popc(d);
+        }
+        for (int o = 16; o > 0; o >>= 1) mism += __shfl_xor_sync(0xffffffffu, mism, o);
+        const uint32_t c = E.nbins - mism;
+        if (counts_out && lane == 0) counts_out[p * A.K + k] = c;
+        if (!dist_out) continue;
+        if (E.kind == KIND_CORE_ACC) {
+            if (!broke) {
+                double y = comp ? log(corrected_jaccard(c, c1, c2, E)) : E.lny[c];
+                if (y < E.tolerance) {
+                    broke = true;
+                } else {
+                    ysum = __dadd_rn(ysum, y);
+                    xysum = __dadd_rn(xysum, __dmul_rn(E.kf[k], y));
+                    ysq = __dadd_rn(ysq, __dmul_rn(y, y));
+                    ++n;
+                }
+            }
+        } else if (k == E.k0) {
+            if (!comp) {
+                d0 = E.val_tab[c];
+            } else {
+                double j = corrected_jaccard(c, c1, c2, E);
+                d0 = E.kind == KIND_ANI ? (float)ani_pois_dev(j, E.k_single) : (float)__dsub_rn(1.0, j);
+            }
+        }
+    }
+    if (dist_out && lane == 0) {
+        if (E.kind == KIND_CORE_ACC) {
+            regress(ysum, xysum, ysq, n, E, d0, d1);
+            dist_out[2 * p] = d0;
+            dist_out[2 * p + 1] = d1;
+        } else {
+            dist_out[p] = d0;
+        }
+    }
+}
+
+void launch_pairs(const DevDb &A, const DevDb &B, const EpiParams &E, const uint64_t *pairs, uint64_t n_pairs,
+                  uint32_t *counts_out, float *dist_out, cudaStream_t st) {
+    if (n_pairs == 0) return;
+    const int warps = 8;
+    pair_kernel<<<(unsigned)((n_pairs + warps - 1) / warps), warps * 32, 0, st>>>(A, B, E, pairs, n_pairs, counts_out,
+                                                                                   dist_out);
+}
+
+}  // namespace skd

@@ -1,0 +1,84 @@
+// Shared host/device definitions: the HBM layout of a sketch database and the kernel parameter blocks.
+#pragma once
+#include <cstdint>
+
+namespace skd {
+
+constexpr int BBITS = 14;                  // bit planes per bin (reference src/sketch/mod.rs:34)
+constexpr int PP = BBITS / 2;              // plane pairs (one 64-bit shared-memory load each)
+constexpr int TS = 64;                     // samples per block = tile edge
+constexpr int HALF_U32 = PP * TS * 2;      // u32 per (32-bin word column, sample block) = 896 (3584 B)
+constexpr int STAGE_U32 = 2 * HALF_U32;    // u32 per (64-bin word, sample block): one pipeline stage operand
+constexpr int STAGE_BYTES = STAGE_U32 * 4; // 7168 B
+constexpr int NST = 3;                     // pipeline stages
+constexpr int THREADS = 256;               // 8 warps, warp tile 16x32, thread tile 4x4
+constexpr int MAXK = 32;                   // k-mer lengths supported by the fused core/accessory epilogue
+
+// Tiled layout ("k-major, 64-bin-word, sample-block"):
+//   u32 index = (((k * W + w) * nb + b) * 2 + half) * HALF_U32 + (pp * TS + s) * 2 + h
+// holds bits [32*half, 32*half+32) of bit plane 2*pp+h of 64-bin word w of sample b*TS+s at k-mer k.
+// One (k, w, b) slab is a contiguous 7168 B: exactly what one bulk (TMA) copy moves into shared memory,
+// and inside it the 64 samples of a plane pair are adjacent 8-byte items, so a warp's 64-bit
+// shared-memory loads are conflict free.  Samples past n in the last block are zero.
+struct DevDb {
+    const uint32_t *tiled;
+    uint64_t n;   // samples
+    uint32_t nb;  // sample blocks
+    uint32_t W;   // 64-bin words per sketch (sketchsize64)
+    uint32_t K;   // k-mer lengths
+    uint32_t pad_;
+};
+
+__host__ __device__ inline uint64_t slab_index(const DevDb &d, uint32_t k, uint32_t w, uint32_t b) {
+    return ((uint64_t)k * d.W + w) * d.nb + b;
+}
+
+enum : int { KIND_CORE_ACC = 0, KIND_JACCARD = 1, KIND_ANI = 2 };
+
+// Everything the fused epilogue needs.  Tables are indexed by the per-k match count (`samebits`).
+struct EpiParams {
+    int kind;
+    int k0;          // first k index the tile loop visits
+    int nk;          // number of k indices visited (K for core/acc, 1 for single-k modes)
+    int has_c;       // completeness vectors supplied for both sides
+    uint32_t nbins;  // 64 * W
+    uint32_t expected; // expected_samebits = nbins >> 14
+    double cutoff;
+    double k_single;   // k as f64 for ANI
+    double tolerance;  // ln(2 / (sketch_size * 64)), jaccard.rs:75
+    const double *a_comp; // device, per row-side sample (nullable)
+    const double *b_comp; // device, per column-side sample (nullable)
+    const double *lny;    // [nbins+1] ln(J(count)) computed on the host with the platform libm
+    const float *val_tab; // [nbins+1] dense single-k output: (f32)(1-J) or (f32)ani
+    const float *key_tab; // [nbins+1] kNN key: (f32)(1-J) or (f32)(1-ani)
+    double kf[MAXK];          // k-mer lengths as f64
+    double xsum[MAXK + 1];    // running sums after n k-mers, accumulated in the reference's order
+    double xbar[MAXK + 1];
+    double x_diff[MAXK + 1];
+    double xstddev[MAXK + 1];
+};
+
+enum : int { MODE_DENSE_SELF = 0, MODE_DENSE_CROSS = 1, MODE_COUNTS = 2, MODE_KNN = 3 };
+
+// Tile schedule of one launch.  Rows are the A side (self: the database, cross: refs), columns the B side.
+struct SchedParams {
+    int mode;
+    int self_mode;        // knn: skip i == j; dense self: only j > i
+    uint32_t rb0;         // first row block
+    uint32_t n_rb;        // row blocks
+    uint32_t group;       // row blocks per L2 group
+    uint32_t n_groups;
+    const uint64_t *grp_off; // [n_groups + 1] first linear tile of each group
+    uint64_t row_begin, row_end; // sample-level row range (clips the first/last block)
+    uint64_t out_base;    // dense self: condensed index of (row_begin, row_begin+1)
+    float *out;           // dense: distances; counts mode: reinterpret as uint32_t*
+    // kNN: each CTA owns one row block and column blocks [split * cb_per_split, ...)
+    uint32_t knn;
+    uint32_t n_split;
+    uint32_t cb_per_split;
+    uint32_t cap;         // candidate slots per row (>= knn + TS)
+    unsigned long long *part_key; // [n_rb * TS][n_split][knn] composite (key bits << 32 | idx), ascending
+    float *part_aux;              // same shape: accessory distance (core/acc only)
+};
+
+}  // namespace skd

@@ -1,0 +1,388 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the CPU oracle and the
+reference's golden outputs.  Run on the B200 box: python -m pytest tests -m gpu."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import FIXTURES, fixture_db, load_json_db, subset_db, synth_db
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-6  # BASELINE.json: Jaccard / core / accessory / ANI within 1e-6 absolute of the reference arithmetic
+
+
+@pytest.fixture(scope="module")
+def sk():
+    import sketchlib.rust_b200 as sk
+    return sk
+
+
+@pytest.fixture(scope="module")
+def ctx(sk):
+    c = sk.Context(0)
+    yield c
+    c.close()
+
+
+def up(sk, ctx, db):
+    return sk.SketchDb.upload(ctx, db.bins, db.n, db.kmers, db.W, db.sketch_size, db.sample_stride, db.kmer_stride,
+                              db.names)
+
+
+def golden(name):
+    return open(os.path.join(FIXTURES, name + ".stdout")).read()
+
+
+def all_pairs(n, m=None):
+    m = n if m is None else m
+    return np.array([(i, j) for i in range(n) for j in range(m)], dtype=np.uint64)
+
+
+# ------------------------------------------------------------------ integer parity (bit exact)
+@pytest.mark.parametrize("n,W,kmers", [(200, 16, [15, 19, 23, 27]), (65, 3, [21]), (130, 160, [21]), (7, 1, [11, 13])])
+def test_match_counts_bit_exact(sk, ctx, n, W, kmers):
+    db = synth_db(n, W, kmers, seed=n + W)
+    g = up(sk, ctx, db)
+    dense = sk.match_counts(g, g)  # tiled kernel: [n, n, K]
+    pairs = all_pairs(n)
+    ref = oracle.match_counts(db, db, pairs).reshape(n, n, len(kmers))
+    assert np.array_equal(dense, ref)
+    sel = pairs[:: max(1, len(pairs) // 997)]
+    assert np.array_equal(sk.match_counts(g, g, pairs=sel), oracle.match_counts(db, db, sel))  # pair kernel
+
+
+def test_match_counts_known_answers(sk, ctx):
+    big = load_json_db("s10048")
+    g = up(sk, ctx, big)
+    c = sk.match_counts(g, g, pairs=[(0, 1), (2, 3), (1, 3), (0, 2)])
+    assert c[0].tolist() == [6811, 6547, 6310, 6127]
+    assert c[1].tolist() == [7167, 6871, 6623, 6342]
+    assert c[2].tolist() == [7, 1, 1, 3]
+    d = sk.match_counts(g, g)
+    assert d[0, 1].tolist() == [6811, 6547, 6310, 6127] and d[3, 1].tolist() == [7, 1, 1, 3]
+    g3 = up(sk, ctx, fixture_db("sketches3"))
+    assert sk.match_counts(g3, g3, pairs=[(0, 1), (2, 3)]).ravel().tolist() == [660, 722]
+
+
+def test_cross_match_counts_ragged(sk, ctx):
+    a = synth_db(150, 16, [17, 21, 25], seed=5, n_families=3)
+    b = synth_db(70, 16, [17, 21, 25], seed=6, n_families=3)
+    ga, gb = up(sk, ctx, a), up(sk, ctx, b)
+    got = sk.match_counts(ga, gb, rows=(10, 140))
+    ref = oracle.match_counts(a, b, all_pairs(150, 70)).reshape(150, 70, 3)[10:140]
+    assert np.array_equal(got, ref)
+
+
+# ------------------------------------------------------------------ the reference's golden stdout files
+def test_golden_knn_ca_jaccard_ani(sk, ctx):
+    db = load_json_db("s10048")
+    g = up(sk, ctx, db)
+    assert str(sk.self_dists_knn(g, knn=1, dist_type=sk.set_k(g))) == golden("dists_knn_ca")
+    assert str(sk.self_dists_knn(g, knn=1, dist_type=sk.set_k(g, 21))) == golden("dists_knn_jaccard")
+    assert str(sk.self_dists_knn(g, knn=1, dist_type=sk.set_k(g, 21, ani=True))) == golden("dists_knn_ani")
+
+
+def test_golden_subset_dense(sk, ctx):
+    db = load_json_db("s10048")
+    names = [l.strip() for l in open(os.path.join(FIXTURES, "subset.txt")) if l.strip()]
+    g = up(sk, ctx, subset_db(db, names))
+    assert str(sk.self_dists_all(g, dist_type=sk.set_k(g))) == golden("dists_subset")
+
+
+def test_golden_precluster_values(sk, ctx):
+    g = up(sk, ctx, fixture_db("sketches3"))
+    assert str(sk.self_dists_knn(g, knn=1, dist_type=sk.set_k(g, 21))) == golden("inverted_precluster")
+    assert str(sk.self_dists_knn(g, knn=1, dist_type=sk.set_k(g, 21, ani=True))) == golden("inverted_precluster_ani")
+
+
+# ------------------------------------------------------------------ dense layouts and values vs the oracle
+def check_close(got, ref):
+    assert got.shape == ref.shape
+    assert np.isfinite(got).all()
+    assert np.abs(got.astype(np.float64) - ref.astype(np.float64)).max() <= TOL
+
+
+@pytest.mark.parametrize("n,W,kmers", [(300, 16, [15, 17, 19, 21, 23, 25, 27, 29]), (70, 2, [17, 21, 25]), (2, 16, [13, 17, 21])])
+def test_dense_self_core_acc(sk, ctx, n, W, kmers):
+    db = synth_db(n, W, kmers, seed=1, unrelated_frac=0.1)
+    g = up(sk, ctx, db)
+    got = sk.self_dists_all(g, dist_type=sk.set_k(g)).distances
+    ref = oracle.self_dists_all(db, threads=8)
+    check_close(got, ref)
+    # the discrete outcomes (early break -> (1,1), exact zero core) must agree exactly
+    assert np.array_equal(got == 1.0, ref == 1.0) and np.array_equal(got == 0.0, ref == 0.0)
+    # and in fact the f64 epilogue is restated op for op: expect bit equality almost everywhere
+    assert (got == ref).mean() > 0.999
+
+
+@pytest.mark.parametrize("ani", [False, True])
+def test_dense_self_single_k_bit_exact(sk, ctx, ani):
+    db = synth_db(257, 16, [15, 21, 27], seed=2, unrelated_frac=0.05)
+    g = up(sk, ctx, db)
+    got = sk.self_dists_all(g, dist_type=sk.set_k(g, 21, ani=ani)).distances
+    ref = oracle.self_dists_all(db, k_idx=1, ani=ani, threads=8)
+    assert np.array_equal(got, ref)  # tables come from the host libm: identical f32
+
+
+def test_dense_self_row_shards_concatenate(sk, ctx):
+    db = synth_db(333, 16, [17, 21, 25, 29], seed=3)
+    g = up(sk, ctx, db)
+    dt = sk.set_k(g)
+    whole = sk.self_dists_all(g, dist_type=dt).distances
+    parts = [sk.self_dists_all(g, dist_type=dt, rows=r).distances for r in ((0, 64), (64, 100), (100, 101), (101, 333))]
+    assert np.array_equal(np.concatenate(parts), whole)
+    for world in (2, 3, 8):
+        shards = [sk.triangle_row_partition(333, r, world) for r in range(world)]
+        assert shards[0][0] == 0 and shards[-1][1] == 333
+        cat = np.concatenate([sk.self_dists_all(g, dist_type=dt, rows=s).distances for s in shards])
+        assert np.array_equal(cat, whole)
+
+
+def test_dense_cross_layout_and_values(sk, ctx):
+    a = synth_db(130, 16, [17, 21, 25, 29], seed=7, n_families=2)
+    b = synth_db(75, 16, [17, 21, 25, 29], seed=8, n_families=2)
+    ga, gb = up(sk, ctx, a), up(sk, ctx, b)
+    got = sk.cross_dists_all(ga, gb, dist_type=sk.set_k(ga))
+    check_close(got.distances, oracle.cross_dists_all(a, b, threads=8))
+    gotj = sk.cross_dists_all(ga, gb, dist_type=sk.set_k(ga, 21)).distances
+    assert np.array_equal(gotj, oracle.cross_dists_all(a, b, k_idx=1, threads=8))
+    part = sk.cross_dists_all(ga, gb, dist_type=sk.set_k(ga), rows=(60, 129)).distances
+    assert np.array_equal(part, got.distances.reshape(130, 75, 2)[60:129].ravel())
+    # text: ref-outer / query-inner (distance_matrix.rs:178-189)
+    first = str(got).split("\n")[0].split("\t")
+    assert first[0] == a.names[0] and first[1] == b.names[0] and len(first) == 4
+
+
+def test_self_equals_cross_on_same_db(sk, ctx):
+    db = synth_db(100, 16, [15, 19, 23, 27], seed=9)
+    g = up(sk, ctx, db)
+    s = sk.self_dists_all(g, dist_type=sk.set_k(g)).distances.reshape(-1, 2)
+    x = sk.cross_dists_all(g, g, dist_type=sk.set_k(g)).distances.reshape(100, 100, 2)
+    iu = np.triu_indices(100, 1)
+    assert np.array_equal(x[iu], s) and np.array_equal(x.transpose(1, 0, 2)[iu], s)
+    assert np.array_equal(x[np.arange(100), np.arange(100)], np.zeros((100, 2), np.float32))  # NaN r -> (0, 0)
+
+
+# ------------------------------------------------------------------ degenerate and guard cases
+def test_need_two_kmers_and_unknown_k(sk, ctx):
+    g = up(sk, ctx, fixture_db("sketches3"))
+    with pytest.raises(sk.SketchDistError, match="Need at least two k-mer lengths"):
+        sk.self_dists_all(g, dist_type=sk.set_k(g))
+    with pytest.raises(sk.SketchDistError, match="K-mer size 33 not found in file"):
+        sk.set_k(g, 33)
+
+
+def test_two_kmers_gives_ones(sk, ctx):
+    leg = fixture_db("legacy_db")
+    two = oracle.Db(leg.bins, 2, [17, 21], 2, 128, leg.sample_stride, leg.kmer_stride)
+    g = up(sk, ctx, two)
+    assert sk.self_dists_all(g, dist_type=sk.set_k(g)).distances.tolist() == [1.0, 1.0]
+    g3 = up(sk, ctx, leg)  # legacy layout, K=3, 128 bins
+    check_close(sk.self_dists_all(g3, dist_type=sk.set_k(g3)).distances, oracle.self_dists_all(leg))
+
+
+def test_expected_samebits_nonzero(sk, ctx):
+    db = synth_db(20, 256, [21, 31], seed=11, n_families=1)  # 16384 bins -> expected_samebits = 1
+    g = up(sk, ctx, db)
+    got = sk.self_dists_all(g, dist_type=sk.set_k(g, 21)).distances
+    assert np.array_equal(got, oracle.self_dists_all(db, k_idx=0))
+    gota = sk.self_dists_all(g, dist_type=sk.set_k(g, 31, ani=True)).distances
+    assert np.array_equal(gota, oracle.self_dists_all(db, k_idx=1, ani=True))
+
+
+def test_large_sketch_uses_32bit_counts(sk, ctx):
+    db = synth_db(6, 1100, [21], seed=12, n_families=1)  # 70400 bins > 65535
+    g = up(sk, ctx, db)
+    assert np.array_equal(sk.match_counts(g, g), oracle.match_counts(db, db, all_pairs(6)).reshape(6, 6, 1))
+    assert np.array_equal(sk.self_dists_all(g, dist_type=sk.set_k(g, 21)).distances, oracle.self_dists_all(db, k_idx=0))
+
+
+def test_completeness(sk, ctx):
+    db = synth_db(90, 16, [17, 21, 25, 29], seed=13, n_families=2)
+    rng = np.random.default_rng(0)
+    cv = rng.uniform(0.6, 1.0, size=90)
+    g = up(sk, ctx, db)
+    for kidx, ani in ((-1, False), (1, False), (1, True)):
+        dt = sk.set_k(g) if kidx < 0 else sk.set_k(g, 21, ani=ani)
+        got = sk.self_dists_all(g, dist_type=dt, completeness_vec=cv).distances
+        ref = oracle.self_dists_all(db, k_idx=kidx, ani=ani, completeness=cv)
+        check_close(got, ref)
+        plain = sk.self_dists_all(g, dist_type=dt).distances
+        assert not np.array_equal(plain, got)
+    # below the cutoff nothing changes (jaccard.rs:37)
+    low = np.full(90, 0.5)
+    a = sk.self_dists_all(g, dist_type=sk.set_k(g, 21), completeness_vec=low).distances
+    assert np.array_equal(a, sk.self_dists_all(g, dist_type=sk.set_k(g, 21)).distances)
+    # cross: separate vectors per side
+    b = synth_db(40, 16, [17, 21, 25, 29], seed=14, n_families=2)
+    gb = up(sk, ctx, b)
+    cq = rng.uniform(0.7, 1.0, size=40)
+    got = sk.cross_dists_all(g, gb, dist_type=sk.set_k(g), ref_completeness_vec=cv, query_completeness_vec=cq).distances
+    check_close(got, oracle.cross_dists_all(db, b, ref_c=cv, query_c=cq))
+
+
+# ------------------------------------------------------------------ kNN
+def assert_knn_matches(idx, d0, d1, oidx, od0, od1, exact_values):
+    """Rows must hold the same distances in the same ascending order; neighbour sets may differ only
+    inside groups of exactly tied keys (BASELINE.json: identical apart from exact ties)."""
+    assert idx.shape == oidx.shape
+    if exact_values:
+        assert np.array_equal(d0, od0)
+    else:
+        assert np.abs(d0.astype(np.float64) - od0).max() <= TOL
+    for r in range(idx.shape[0]):
+        if exact_values:
+            last = od0[r, -1]
+            strict = od0[r] != last  # entries not tied with the boundary value must be the same set
+            assert set(idx[r][d0[r] != last].tolist()) == set(oidx[r][strict].tolist())
+        if d1 is not None:
+            same = idx[r] == oidx[r]
+            assert np.abs(d1[r][same].astype(np.float64) - od1[r][same]).max(initial=0.0) <= TOL
+
+
+@pytest.mark.parametrize("knn", [1, 5, 50, 64])
+def test_self_knn_jaccard(sk, ctx, knn):
+    db = synth_db(500, 16, [15, 21, 27], seed=20, n_families=8, unrelated_frac=0.05)
+    g = up(sk, ctx, db)
+    got = sk.self_dists_knn(g, knn=knn, dist_type=sk.set_k(g, 21))
+    oidx, od0, _ = oracle.self_dists_knn(db, knn, k_idx=1, threads=8)
+    assert_knn_matches(got.idx, got.d0, None, oidx, od0, None, True)
+    assert (np.diff(got.d0, axis=1) >= 0).all()
+    assert (got.idx != np.arange(500)[:, None]).all()  # never its own neighbour
+
+
+def test_self_knn_ani_roundtrip(sk, ctx):
+    db = synth_db(300, 16, [15, 21, 27], seed=21, n_families=5)
+    g = up(sk, ctx, db)
+    got = sk.self_dists_knn(g, knn=10, dist_type=sk.set_k(g, 21, ani=True))
+    oidx, od0, _ = oracle.self_dists_knn(db, 10, k_idx=1, ani=True, threads=8)
+    assert np.array_equal(got.d0, od0)  # includes the f32 1-(1-ani) round trip (mod.rs:183-189)
+    assert (np.diff(got.d0, axis=1) <= 0).all()  # highest ANI first
+
+
+def test_self_knn_core_acc_and_row_shards(sk, ctx):
+    db = synth_db(400, 16, [15, 17, 19, 21, 23, 25, 27, 29], seed=22, n_families=6, unrelated_frac=0.05)
+    g = up(sk, ctx, db)
+    got = sk.self_dists_knn(g, knn=50, dist_type=sk.set_k(g))
+    oidx, od0, od1 = oracle.self_dists_knn(db, 50, threads=8)
+    assert_knn_matches(got.idx, got.d0, got.d1, oidx, od0, od1, False)
+    # the kNN rows must be the dense rows' smallest entries
+    dense = sk.cross_dists_all(g, g, dist_type=sk.set_k(g)).distances.reshape(400, 400, 2)
+    for r in (0, 63, 64, 399):
+        row = dense[r, :, 0].copy()
+        row[r] = np.inf
+        assert np.array_equal(np.sort(row)[:50], got.d0[r])
+        assert np.array_equal(dense[r, got.idx[r].astype(int), 1], got.d1[r])
+    parts = [sk.self_dists_knn(g, knn=50, dist_type=sk.set_k(g), rows=rows) for rows in ((0, 100), (100, 130), (130, 400))]
+    assert np.array_equal(np.concatenate([p.idx for p in parts]), got.idx)
+    assert np.array_equal(np.concatenate([p.d0 for p in parts]), got.d0)
+
+
+def test_cross_knn(sk, ctx):
+    ref = synth_db(700, 16, [17, 21, 25, 29], seed=23, n_families=10)
+    qry = synth_db(90, 16, [17, 21, 25, 29], seed=23, n_families=10)
+    gr, gq = up(sk, ctx, ref), up(sk, ctx, qry)
+    got = sk.cross_dists_knn(gr, gq, knn=7, dist_type=sk.set_k(gr, 21))
+    oidx, od0, _ = oracle.cross_dists_knn(ref, qry, 7, k_idx=1, threads=8)
+    assert got.idx.shape == (90, 7)
+    assert_knn_matches(got.idx, got.d0, None, oidx, od0, None, True)
+    gotc = sk.cross_dists_knn(gr, gq, knn=7, dist_type=sk.set_k(gr))
+    oidx, od0, od1 = oracle.cross_dists_knn(ref, qry, 7, threads=8)
+    assert_knn_matches(gotc.idx, gotc.d0, gotc.d1, oidx, od0, od1, False)
+    # rows are queries, columns refs (tests/distance.rs:465-490)
+    line = str(gotc).split("\n")[0].split("\t")
+    assert line[0] == qry.names[0] and line[1] in ref.names and len(line) == 4
+    # knn >= n_ref is clamped to n_ref and returns every ref (tests/distance.rs:665-687)
+    small = synth_db(5, 16, [17, 21, 25, 29], seed=24, n_families=1)
+    gs = up(sk, ctx, small)
+    allr = sk.cross_dists_knn(gs, gq, knn=50, dist_type=sk.set_k(gs, 21))
+    assert allr.knn == 5 and allr.idx.shape == (90, 5)
+    assert all(sorted(r.tolist()) == [0, 1, 2, 3, 4] for r in allr.idx)
+
+
+def test_knn_many_exact_ties(sk, ctx):
+    # identical sketches in groups: lots of exactly tied keys; ordering must still be total and valid
+    base = synth_db(12, 4, [21, 25, 29], seed=30, n_families=12)
+    reps = np.repeat(np.arange(12), 20)
+    bins = base.bins.reshape(12, -1)[reps].reshape(-1)
+    db = oracle.Db(bins, 240, base.kmers, 4)
+    g = up(sk, ctx, db)
+    got = sk.self_dists_knn(g, knn=19, dist_type=sk.set_k(g, 21))
+    assert (got.d0 == 0.0).all()  # the 19 other copies
+    assert all(set(got.idx[r].tolist()) == set(np.nonzero(reps == reps[r])[0].tolist()) - {r} for r in range(240))
+    oidx, od0, _ = oracle.self_dists_knn(db, 25, k_idx=0, threads=4)
+    got25 = sk.self_dists_knn(g, knn=25, dist_type=sk.set_k(g, 21))
+    assert np.array_equal(got25.d0, od0)
+
+
+def test_knn_errors(sk, ctx):
+    db = synth_db(10, 16, [17, 21, 25], seed=31)
+    g = up(sk, ctx, db)
+    with pytest.raises(sk.SketchDistError):
+        sk.self_dists_knn(g, knn=10, dist_type=sk.set_k(g))  # knn must be <= n-1 (CLI clamps, lib.rs:379-382)
+    got = sk.self_dists_knn(g, knn=9, dist_type=sk.set_k(g, 21))
+    assert all(sorted(r.tolist()) == [x for x in range(10) if x != i] for i, r in enumerate(got.idx))
+    empty = sk.SketchDb.upload(ctx, np.zeros(0, np.uint64), 0, [17, 21, 25], 16)
+    with pytest.raises(sk.SketchDistError, match="Reference database has no loaded samples"):
+        sk.cross_dists_knn(empty, g, knn=3, dist_type=sk.set_k(g, 21))
+    with pytest.raises(sk.SketchDistError, match="Query database has no loaded samples"):
+        sk.cross_dists_knn(g, empty, knn=3, dist_type=sk.set_k(g, 21))
+    other = up(sk, ctx, synth_db(10, 8, [17, 21, 25], seed=32))
+    with pytest.raises(sk.SketchDistError, match="differ in sketch size"):
+        sk.cross_dists_all(g, other, dist_type=sk.set_k(g, 21))
+
+
+# ------------------------------------------------------------------ loader
+def test_load_skd_file_and_subset(sk, ctx, tmp_path):
+    db = synth_db(150, 16, [17, 21, 25], seed=40)
+    path = str(tmp_path / "db.skd")
+    db.bins.astype("<u8").tofile(path)
+    g_file = sk.SketchDb.load_skd(ctx, path, 150, db.kmers, 16)
+    g_mem = up(sk, ctx, db)
+    dt = sk.set_k(g_mem)
+    assert np.array_equal(sk.self_dists_all(g_file, dist_type=dt).distances, sk.self_dists_all(g_mem, dist_type=dt).distances)
+    order = [149, 3, 77, 5, 64, 0]
+    g_sub = sk.SketchDb.load_skd(ctx, path, len(order), db.kmers, 16, sample_indices=order)
+    sub = subset_db(db, [db.names[i] for i in order])
+    check_close(sk.self_dists_all(g_sub, dist_type=dt).distances, oracle.self_dists_all(sub))
+    with pytest.raises(sk.SketchDistError):
+        sk.SketchDb.load_skd(ctx, path, 151, db.kmers, 16)
+    with pytest.raises(sk.SketchDistError, match="Could not read from"):
+        sk.SketchDb.load_skd(ctx, str(tmp_path / "missing.skd"), 1, db.kmers, 16)
+
+
+def test_fixture_skd_files_direct(sk, ctx):
+    ms = oracle.MultiSketch(os.path.join(FIXTURES, "sketches2")).read_sketch_data()
+    g = sk.SketchDb.load_skd(ctx, os.path.join(FIXTURES, "sketches2.skd"), 4, ms.kmer_lengths, ms.sketchsize64,
+                             ms.sketch_size, ms.sample_stride, ms.kmer_stride, ms.names())
+    got = sk.self_dists_all(g, dist_type=sk.set_k(g, 31)).distances
+    assert np.array_equal(got, oracle.self_dists_all(oracle.Db.from_multisketch(ms), k_idx=0))
+    # tests/distance.rs:206-217 expects roughly [0.40755, 1, 1, 1, 1, 0.37049] (+-0.05) for this database
+    assert np.abs(got - np.array([0.40755, 1, 1, 1, 1, 0.37049], np.float32)).max() < 0.05
+
+
+# ------------------------------------------------------------------ scale: size-independent properties
+def test_scale_properties(sk, ctx):
+    n = 3000
+    db = synth_db(n, 16, [15, 17, 19, 21, 23, 25, 27, 29], seed=50, n_families=40)
+    g = up(sk, ctx, db)
+    dm = sk.self_dists_all(g, dist_type=sk.set_k(g))
+    d = dm.distances.reshape(-1, 2)
+    assert d.shape[0] == n * (n - 1) // 2 and np.isfinite(d).all() and d.min() >= 0.0 and d.max() <= 1.0
+    # spot rows against the oracle
+    rng = np.random.default_rng(1)
+    for i in rng.integers(0, n - 1, size=6):
+        first = int(oracle.lib().oracle_square_to_condensed(int(i), int(i) + 1, n))
+        cnt = n - 1 - int(i)
+        ref = oracle.self_dists_all(db, first=first - first % 1000, count=cnt + first % 1000, threads=8)
+        ref = ref[2 * (first % 1000):]
+        check_close(d[first:first + cnt].ravel(), ref)
+    # kNN agrees with the dense matrix at this size
+    knn = sk.self_dists_knn(g, knn=50, dist_type=sk.set_k(g))
+    full = np.full((n, n), np.inf, dtype=np.float32)
+    iu = np.triu_indices(n, 1)
+    full[iu] = d[:, 0]
+    full.T[iu] = d[:, 0]
+    assert np.array_equal(np.sort(full, axis=1)[:, :50], knn.d0)
