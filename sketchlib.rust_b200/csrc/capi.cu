@@ -10,6 +10,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -26,7 +27,7 @@ namespace {
 thread_local std::string g_create_error;
 constexpr size_t kMaxSmem = 232448;           // 227 KB opt-in dynamic shared memory per CTA on sm_100
 constexpr size_t kUploadChunkBytes = 64ull << 20;
-constexpr size_t kResultChunkBytes = 256ull << 20;
+size_t kResultChunkBytes = 64ull << 20;       // SKD_RESULT_CHUNK_MB overrides
 constexpr uint32_t kGroup = 8;                // row blocks per L2 group
 }  // namespace
 
@@ -43,6 +44,7 @@ struct skd_ctx {
     void *pinned[2] = {nullptr, nullptr};
     size_t pinned_bytes = 0;
     int sm_count = 148;
+    bool zero_copy = true;   // dense kernels store straight into pinned host results (SKD_ZEROCOPY=0 disables)
 };
 
 struct skd_db {
@@ -175,6 +177,7 @@ skd_status build_epi(skd_ctx *ctx, const skd_db *A, const skd_db *B, skd_dist_ty
                 E->xbar[n] = xsum / dn;
                 E->x_diff[n] = xsq - xsum * xsum / dn;
                 E->xstddev[n] = std::sqrt((xsq - xsum * xsum / dn) / dn);
+                E->rcp_n[n] = 1.0 / dn;
             }
         }
     } else if (dist.kind == KIND_JACCARD || dist.kind == KIND_ANI) {
@@ -205,6 +208,7 @@ skd_status build_epi(skd_ctx *ctx, const skd_db *A, const skd_db *B, skd_dist_ty
     } else {
         return fail(ctx, SKD_ERR_INVALID, "unknown distance kind %d", dist.kind);
     }
+    E->kp = counts_per_pair(E->nk, nbins >= 65536);
     // Completeness applies only when both vectors are given (jaccard.rs:36)
     if (a_comp && b_comp) {
         E->has_c = 1;
@@ -278,6 +282,18 @@ skd_status run_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, bool self, 
         return (r - row_begin) * B->n;
     };
     timers_reset(ctx);
+    // A pinned (page-locked, mapped) host destination can be written by the kernel directly: the result stores
+    // stream over PCIe while later tiles are still being computed, with no staging copy at all.
+    if (out_loc == SKD_HOST && ctx->zero_copy) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, out) == cudaSuccess && attr.type == cudaMemoryTypeHost &&
+            attr.devicePointer != nullptr) {
+            out = (float *)attr.devicePointer;
+            out_loc = SKD_DEVICE;
+        } else {
+            (void)cudaGetLastError();
+        }
+    }
     // Plan: one chunk when the result stays on the device; otherwise row chunks of about kResultChunkBytes
     // on two device buffers, so that the D2H copy of chunk c overlaps the kernel of chunk c+1.
     struct Chunk {
@@ -360,6 +376,9 @@ skd_status run_knn(skd_ctx *ctx, const skd_db *R, const skd_db *Q, bool self, co
     const bool with_aux = E.kind == KIND_CORE_ACC;
     uint32_t cap = 128;
     while (cap < knn + TS) cap <<= 1;
+    if ((size_t)cap * 12 > (size_t)NST * 2 * STAGE_BYTES)
+        return fail(ctx, SKD_ERR_UNSUPPORTED, "knn=%llu exceeds the device top-k capacity (%d); use the dense output",
+                    (unsigned long long)knn, (int)((size_t)NST * 2 * STAGE_BYTES / 12 / 2 - TS));
     const bool count32 = E.nbins >= 65536;
     size_t smem = tile_kernel_smem(E.nk, count32, true, cap, with_aux);
     if (smem > kMaxSmem)
@@ -381,7 +400,7 @@ skd_status run_knn(skd_ctx *ctx, const skd_db *R, const skd_db *Q, bool self, co
     S.n_split = std::max(1u, std::min(want, B->dev.nb));
     S.cb_per_split = (B->dev.nb + S.n_split - 1) / S.n_split;
     S.n_split = (B->dev.nb + S.cb_per_split - 1) / S.cb_per_split;
-    const size_t part = (size_t)S.n_rb * TS * S.n_split * knn;
+    const size_t part = (size_t)S.n_rb * TS * S.n_split * cap;
     void *pk, *pa = nullptr;
     skd_status st = scratch_get(ctx, "knn_key", part * 8, &pk);
     if (st) return st;
@@ -410,7 +429,7 @@ skd_status run_knn(skd_ctx *ctx, const skd_db *R, const skd_db *Q, bool self, co
     st = timer_begin(ctx);
     if (st) return st;
     CU(ctx, launch_tiles(A->dev, B->dev, E, S, (uint64_t)S.n_rb * S.n_split, count32, smem, ctx->compute));
-    launch_knn_merge(S.part_key, S.part_aux, S.n_split, S.knn, row_begin - (uint64_t)S.rb0 * TS, n_rows, E.kind, didx,
+    launch_knn_merge(S.part_key, S.part_aux, S.n_split, S.knn, S.cap, row_begin - (uint64_t)S.rb0 * TS, n_rows, E.kind, didx,
                      dd0, dd1, ctx->compute);
     CU(ctx, cudaGetLastError());
     ctx->launches += 2;
@@ -582,6 +601,8 @@ skd_status skd_ctx_create(int device, skd_ctx **out) {
                     prop.major, prop.minor);
     }
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char *e = getenv("SKD_ZEROCOPY")) ctx->zero_copy = atoi(e) != 0;
+    if (const char *e = getenv("SKD_RESULT_CHUNK_MB")) kResultChunkBytes = (size_t)std::max(1, atoi(e)) << 20;
     for (int i = 0; i < 2; ++i) {
         cudaEventCreateWithFlags(&ctx->ev_a[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_b[i], cudaEventDisableTiming);
@@ -881,6 +902,7 @@ skd_status skd_match_counts_dense(skd_ctx *ctx, const skd_db *ref, const skd_db 
     E.nbins = (uint32_t)(64 * ref->W);
     E.k0 = 0;
     E.nk = (int)ref->kmers.size();
+    E.kp = counts_per_pair(E.nk, E.nbins >= 65536);
     ref_end = std::min(ref_end, ref->n);
     if (ref_begin >= ref_end || query->n == 0) return SKD_OK;
     if (!counts) return fail(ctx, SKD_ERR_INVALID, "null output");

@@ -103,6 +103,19 @@ __device__ __forceinline__ double ani_pois_dev(double j, double k) {
     return fmax(0.0, __dadd_rn(1.0, __dmul_rn(__ddiv_rn(1.0, k), log(q))));
 }
 
+// x / n for a small integer n, correctly rounded like IEEE division (so bit-identical to the reference's
+// f64 `/`), from the correctly rounded reciprocal: two FMA residual corrections (Markstein).  The first
+// makes the quotient faithful, the second rounds it correctly.  Inputs here are far from the
+// overflow/underflow ranges where the sequence would need a slow path (zero, inf and NaN pass through).
+__device__ __forceinline__ double div_by_n(double x, double dn, double rcp) {
+    double q = __dmul_rn(x, rcp);
+    q = __fma_rn(__fma_rn(-dn, q, x), rcp, q);
+    double r = __fma_rn(-dn, q, x);
+    double q2 = __fma_rn(r, rcp, q);
+    // tiny or non-finite x: fall back to the plain division (exact by definition)
+    return (fabs(x) > 1e-280 && fabs(x) < 1e280) ? q2 : __ddiv_rn(x, dn);
+}
+
 // simple_linear_regression (jaccard.rs:105-142) with the x statistics tabulated per n.
 __device__ __forceinline__ void regress(double ysum, double xysum, double ysq, int n, const EpiParams &E,
                                         float &core_out, float &acc_out) {
@@ -111,12 +124,12 @@ __device__ __forceinline__ void regress(double ysum, double xysum, double ysq, i
         acc_out = 1.0f;
         return;
     }
-    const double dn = (double)n;
+    const double dn = (double)n, rcp = E.rcp_n[n];
     const double xsum = E.xsum[n];
-    double ybar = __ddiv_rn(ysum, dn);
-    double y_diff = __dsub_rn(ysq, __ddiv_rn(__dmul_rn(ysum, ysum), dn));
-    double ystddev = __dsqrt_rn(__ddiv_rn(y_diff, dn));
-    double r = __ddiv_rn(__dsub_rn(xysum, __ddiv_rn(__dmul_rn(xsum, ysum), dn)),
+    double ybar = div_by_n(ysum, dn, rcp);
+    double y_diff = __dsub_rn(ysq, div_by_n(__dmul_rn(ysum, ysum), dn, rcp));
+    double ystddev = __dsqrt_rn(div_by_n(y_diff, dn, rcp));
+    double r = __ddiv_rn(__dsub_rn(xysum, div_by_n(__dmul_rn(xsum, ysum), dn, rcp)),
                          __dsqrt_rn(__dmul_rn(E.x_diff[n], y_diff)));
     double beta = __ddiv_rn(__dmul_rn(r, ystddev), E.xstddev[n]);
     double alpha = __dadd_rn(__dmul_rn(-beta, E.xbar[n]), ybar);
@@ -154,7 +167,8 @@ struct TileCoord {
 
 template <typename CountT>
 __device__ __forceinline__ void tile_counts(const DevDb &A, const DevDb &B, uint32_t rb, uint32_t cb, int k0, int nk,
-                                            uint32_t *stage_mem, uint64_t *full_bar, CountT *counts, uint32_t &git) {
+                                            uint32_t *stage_mem, uint64_t *full_bar, CountT *counts, int kp,
+                                            uint32_t &git) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int arow0 = 16 * (warp >> 1) + (lane >> 3);
     const int bcol0 = 32 * (warp & 1) + (lane & 7);
@@ -230,7 +244,7 @@ __device__ __forceinline__ void tile_counts(const DevDb &A, const DevDb &B, uint
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    counts[kk * (TS * TS) + (arow0 + 4 * i) * TS + bcol0 + 8 * j] = (CountT)(nbins - mism[i][j]);
+                    counts[((arow0 + 4 * i) * TS + bcol0 + 8 * j) * kp + kk] = (CountT)(nbins - mism[i][j]);
                     mism[i][j] = 0;
                 }
             w_in_k = 0;
@@ -241,34 +255,55 @@ __device__ __forceinline__ void tile_counts(const DevDb &A, const DevDb &B, uint
     __syncthreads();  // counts visible to all; all stages consumed
 }
 
-// One pair's distances from its counts in shared memory.  Returns key (first distance) and aux.
-template <typename CountT>
+// One pair's distances from its counts in shared memory ([pair][kp], read as 16-byte words).
+// Returns d0 (first distance or kNN key) and d1 (accessory distance).
+template <typename CountT, bool COMP>
 __device__ __forceinline__ void pair_epilogue(const CountT *counts, int pair, const EpiParams &E, uint64_t gi,
                                               uint64_t gj, bool for_knn, float &d0, float &d1) {
-    const bool comp = E.has_c != 0;
+    constexpr int PER = 16 / (int)sizeof(CountT);  // counts per 16-byte word
     double c1 = 0.0, c2 = 0.0;
-    if (comp) {
+    if (COMP) {
         c1 = E.a_comp[gi];
         c2 = E.b_comp[gj];
     }
+    const uint4 *words = reinterpret_cast<const uint4 *>(counts + (size_t)pair * E.kp);
     if (E.kind == KIND_CORE_ACC) {
         // core_acc_dist, jaccard.rs:73-100
         double ysum = 0.0, xysum = 0.0, ysq = 0.0;
         int n = 0;
-        for (int k = 0; k < E.nk; ++k) {
-            uint32_t c = counts[k * (TS * TS) + pair];
-            double y = comp ? log(corrected_jaccard(c, c1, c2, E)) : __ldg(&E.lny[c]);
-            if (y < E.tolerance) break;
-            ysum = __dadd_rn(ysum, y);
-            xysum = __dadd_rn(xysum, __dmul_rn(E.kf[k], y));
-            ysq = __dadd_rn(ysq, __dmul_rn(y, y));
-            ++n;
+        bool alive = true;
+        for (int kb = 0; kb < E.nk && alive; kb += PER) {
+            const uint4 v = words[kb / PER];
+            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+            // the ln J look-ups of this word are independent: issue them together
+            double y[PER];
+#pragma unroll
+            for (int t = 0; t < PER; ++t) {
+                const uint32_t c = sizeof(CountT) == 2 ? ((w4[t >> 1] >> (16 * (t & 1))) & 0xffffu) : w4[t];
+                if (COMP)
+                    y[t] = kb + t < E.nk ? log(corrected_jaccard(c, c1, c2, E)) : 0.0;
+                else
+                    y[t] = __ldg(&E.lny[c]);  // padding counts are 0 -> a valid table index
+            }
+#pragma unroll
+            for (int t = 0; t < PER; ++t) {
+                if (alive && kb + t < E.nk) {
+                    if (y[t] < E.tolerance) {
+                        alive = false;  // the reference breaks: later k are ignored (jaccard.rs:89-91)
+                    } else {
+                        ysum = __dadd_rn(ysum, y[t]);
+                        xysum = __dadd_rn(xysum, __dmul_rn(E.kf[kb + t], y[t]));
+                        ysq = __dadd_rn(ysq, __dmul_rn(y[t], y[t]));
+                        ++n;
+                    }
+                }
+            }
         }
         regress(ysum, xysum, ysq, n, E, d0, d1);
     } else {
-        uint32_t c = counts[pair];
+        const uint32_t c = sizeof(CountT) == 2 ? (words[0].x & 0xffffu) : words[0].x;
         d1 = 0.0f;
-        if (!comp) {
+        if (!COMP) {
             d0 = for_knn ? __ldg(&E.key_tab[c]) : __ldg(&E.val_tab[c]);
         } else {
             double j = corrected_jaccard(c, c1, c2, E);
@@ -314,7 +349,7 @@ __global__ void __launch_bounds__(THREADS, 2)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t *stage_mem = reinterpret_cast<uint32_t *>(smem_raw);
     CountT *counts = reinterpret_cast<CountT *>(smem_raw + NST * 2 * STAGE_BYTES);
-    size_t off = (size_t)NST * 2 * STAGE_BYTES + (size_t)E.nk * TS * TS * sizeof(CountT);
+    size_t off = (size_t)NST * 2 * STAGE_BYTES + (size_t)E.kp * TS * TS * sizeof(CountT);
     off = (off + 15) & ~(size_t)15;
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_raw + off);
     off += 64;
@@ -324,6 +359,9 @@ __global__ void __launch_bounds__(THREADS, 2)
         for (int s = 0; s < NST; ++s) mbar_init(&full_bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    // padding slots of the per-pair count words must hold a valid table index
+    if (E.kp != E.nk)
+        for (int e = tid; e < TS * TS * E.kp; e += THREADS) counts[e] = 0;
     __syncthreads();
     uint32_t git = 0;
 
@@ -343,7 +381,7 @@ __global__ void __launch_bounds__(THREADS, 2)
         const uint32_t cb = cb_first + (uint32_t)(local / rows_in_g);
         if (S.mode == MODE_DENSE_SELF && cb < rb) return;  // below the diagonal (only inside a diagonal group)
 
-        tile_counts<CountT>(A, B, rb, cb, E.k0, E.nk, stage_mem, full_bar, counts, git);
+        tile_counts<CountT>(A, B, rb, cb, E.k0, E.nk, stage_mem, full_bar, counts, E.kp, git);
 
         const uint64_t nA = A.n, nB = B.n;
         for (int m = 0; m < (TS * TS) / THREADS; ++m) {
@@ -352,7 +390,7 @@ __global__ void __launch_bounds__(THREADS, 2)
             if (gi < S.row_begin || gi >= S.row_end || gj >= nB) continue;
             if (S.mode == MODE_COUNTS) {
                 uint32_t *o = reinterpret_cast<uint32_t *>(S.out) + ((gi - S.row_begin) * nB + gj) * (uint64_t)E.nk;
-                for (int k = 0; k < E.nk; ++k) o[k] = counts[k * (TS * TS) + pair];
+                for (int k = 0; k < E.nk; ++k) o[k] = counts[pair * E.kp + k];
                 continue;
             }
             uint64_t idx;
@@ -363,21 +401,25 @@ __global__ void __launch_bounds__(THREADS, 2)
                 idx = (gi - S.row_begin) * nB + gj;  // ref-major
             }
             float d0, d1;
-            pair_epilogue<CountT>(counts, pair, E, gi, gj, false, d0, d1);
-            if (E.kind == KIND_CORE_ACC)
-                reinterpret_cast<float2 *>(S.out)[idx] = make_float2(d0, d1);
+            if (E.has_c)
+                pair_epilogue<CountT, true>(counts, pair, E, gi, gj, false, d0, d1);
             else
-                S.out[idx] = d0;
+                pair_epilogue<CountT, false>(counts, pair, E, gi, gj, false, d0, d1);
+            // results are written once and never re-read by the GPU: streaming stores keep the database in L2
+            if (E.kind == KIND_CORE_ACC)
+                __stcs(reinterpret_cast<float2 *>(S.out) + idx, make_float2(d0, d1));
+            else
+                __stcs(S.out + idx, d0);
         }
         return;
     }
 
-    // ---- kNN: this CTA owns row block rb and scans column blocks [cb_lo, cb_hi)
+    // ---- kNN: this CTA owns row block rb and scans column blocks [cb_lo, cb_hi).
+    // Per-row candidate lists live in global memory (L2 resident; appends are rare once the per-row
+    // threshold has tightened), so that shared memory stays small enough for two CTAs per SM.  Only the
+    // thresholds and fill counts are in shared memory; the pipeline stage buffers double as sort scratch
+    // between tiles, when no bulk copy is in flight.
     const bool with_aux = E.kind == KIND_CORE_ACC;
-    unsigned long long *cand_key = reinterpret_cast<unsigned long long *>(smem_raw + off);
-    off += (size_t)TS * S.cap * sizeof(unsigned long long);
-    float *cand_aux = reinterpret_cast<float *>(smem_raw + off);
-    if (with_aux) off += (size_t)TS * S.cap * sizeof(float);
     unsigned long long *thr = reinterpret_cast<unsigned long long *>(smem_raw + off);
     off += TS * sizeof(unsigned long long);
     uint32_t *cand_cnt = reinterpret_cast<uint32_t *>(smem_raw + off);
@@ -388,16 +430,39 @@ __global__ void __launch_bounds__(THREADS, 2)
     const uint32_t cb_hi = min(B.nb, cb_lo + S.cb_per_split);
     const int warp = tid >> 5, lane = tid & 31;
     const uint32_t cap = S.cap, knn = S.knn;
+    // this CTA's lists: [row][cap]
+    unsigned long long *cand_key = S.part_key + ((uint64_t)rbl * S.n_split + split) * TS * cap;
+    float *cand_aux = with_aux ? S.part_aux + ((uint64_t)rbl * S.n_split + split) * TS * cap : nullptr;
+    // sort scratch: one (cap keys + cap aux) region per sorting warp, carved from the stage buffers
+    const uint32_t scratch_bytes = cap * 12;
+    const int sorters = min(THREADS / 32, (int)((NST * 2 * STAGE_BYTES) / scratch_bytes));
+    unsigned long long *sc_key = reinterpret_cast<unsigned long long *>(smem_raw + (size_t)warp * scratch_bytes);
+    float *sc_aux = reinterpret_cast<float *>(sc_key + cap);
+
+    // Sort one row's list through shared memory; keeps the best `keep` entries (ascending) in place.
+    auto sort_row = [&](int row, uint32_t count, uint32_t keep) {
+        unsigned long long *gk = cand_key + (size_t)row * cap;
+        float *ga = with_aux ? cand_aux + (size_t)row * cap : nullptr;
+        for (uint32_t e = lane; e < cap; e += 32) {
+            sc_key[e] = e < count ? __ldcg(gk + e) : ~0ull;
+            if (with_aux) sc_aux[e] = e < count ? __ldcg(ga + e) : 0.0f;
+        }
+        warp_bitonic_sort(sc_key, with_aux ? sc_aux : nullptr, (int)cap, lane);
+        for (uint32_t e = lane; e < keep; e += 32) {
+            gk[e] = sc_key[e];
+            if (with_aux) ga[e] = sc_aux[e];
+        }
+        __syncwarp();
+    };
 
     for (int r = tid; r < TS; r += THREADS) {
         thr[r] = ~0ull;
         cand_cnt[r] = 0;
     }
-    for (uint32_t e = tid; e < TS * cap; e += THREADS) cand_key[e] = ~0ull;
     __syncthreads();
 
     for (uint32_t cb = cb_lo; cb < cb_hi; ++cb) {
-        tile_counts<CountT>(A, B, rb, cb, E.k0, E.nk, stage_mem, full_bar, counts, git);
+        tile_counts<CountT>(A, B, rb, cb, E.k0, E.nk, stage_mem, full_bar, counts, E.kp, git);
         for (int m = 0; m < (TS * TS) / THREADS; ++m) {
             const int pair = m * THREADS + tid;
             const int row = pair / TS;
@@ -405,51 +470,54 @@ __global__ void __launch_bounds__(THREADS, 2)
             if (gi < S.row_begin || gi >= S.row_end || gj >= B.n) continue;
             if (S.self_mode && gi == gj) continue;
             float d0, d1;
-            pair_epilogue<CountT>(counts, pair, E, gi, gj, true, d0, d1);
+            if (E.has_c)
+                pair_epilogue<CountT, true>(counts, pair, E, gi, gj, true, d0, d1);
+            else
+                pair_epilogue<CountT, false>(counts, pair, E, gi, gj, true, d0, d1);
             unsigned long long comp = ((unsigned long long)float_order_bits(d0) << 32) | (uint32_t)gj;
             if (comp < thr[row]) {
                 uint32_t slot = atomicAdd(&cand_cnt[row], 1u);
-                cand_key[row * cap + slot] = comp;
-                if (with_aux) cand_aux[row * cap + slot] = d1;
+                cand_key[(size_t)row * cap + slot] = comp;
+                if (with_aux) cand_aux[(size_t)row * cap + slot] = d1;
             }
         }
-        __syncthreads();
-        // compact rows that could overflow during the next tile
-        for (int row = warp; row < TS; row += THREADS / 32) {
-            uint32_t c = cand_cnt[row];
-            if (c + TS > cap) {
-                warp_bitonic_sort(cand_key + row * cap, with_aux ? cand_aux + row * cap : nullptr, (int)cap, lane);
-                for (uint32_t e = knn + lane; e < cap; e += 32) cand_key[row * cap + e] = ~0ull;
-                if (lane == 0) {
-                    cand_cnt[row] = knn;
-                    thr[row] = cand_key[row * cap + knn - 1];
+        __syncthreads();  // appends (global) visible CTA-wide; stage buffers idle until the next tile
+        // compact rows that could overflow during the next tile (a tile adds at most TS entries per row)
+        if (warp < sorters) {
+            for (int row = warp; row < TS; row += sorters) {
+                const uint32_t c = cand_cnt[row];
+                if (c + TS > cap) {
+                    sort_row(row, c, knn);
+                    if (lane == 0) {
+                        cand_cnt[row] = knn;
+                        thr[row] = sc_key[knn - 1];
+                    }
+                    __syncwarp();
                 }
             }
         }
+        // the scratch lives in the stage buffers the next tile's bulk copies (async proxy) will overwrite
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncthreads();
     }
-    // final sort and hand-off of this split's best knn per row
-    for (int row = warp; row < TS; row += THREADS / 32) {
-        warp_bitonic_sort(cand_key + row * cap, with_aux ? cand_aux + row * cap : nullptr, (int)cap, lane);
-        const uint64_t lrow = (uint64_t)rbl * TS + row;
-        unsigned long long *pk = S.part_key + (lrow * S.n_split + split) * knn;
-        float *pa = with_aux ? S.part_aux + (lrow * S.n_split + split) * knn : nullptr;
-        for (uint32_t e = lane; e < knn; e += 32) {
-            pk[e] = cand_key[row * cap + e];
-            if (with_aux) pa[e] = cand_aux[row * cap + e];
-        }
+    // final: each row's best knn of this split, ascending, padded with ~0
+    if (warp < sorters) {
+        for (int row = warp; row < TS; row += sorters) sort_row(row, cand_cnt[row], knn);
     }
 }
 
+int counts_per_pair(int nk, bool count32) {
+    const int per = count32 ? 4 : 8;
+    return (nk + per - 1) / per * per;
+}
+
 size_t tile_kernel_smem(int nk, bool count32, bool knn_mode, uint32_t cap, bool with_aux) {
-    size_t off = (size_t)NST * 2 * STAGE_BYTES + (size_t)nk * TS * TS * (count32 ? 4 : 2);
+    size_t off = (size_t)NST * 2 * STAGE_BYTES + (size_t)counts_per_pair(nk, count32) * TS * TS * (count32 ? 4 : 2);
     off = (off + 15) & ~(size_t)15;
     off += 64;
-    if (knn_mode) {
-        off += (size_t)TS * cap * 8;
-        if (with_aux) off += (size_t)TS * cap * 4;
-        off += TS * 8 + TS * 4;
-    }
+    (void)cap;
+    (void)with_aux;
+    if (knn_mode) off += TS * 8 + TS * 4;  // thresholds + fill counts; the lists themselves are in global memory
     return off;
 }
 
@@ -475,24 +543,27 @@ cudaError_t launch_tiles(const DevDb &A, const DevDb &B, const EpiParams &E, con
 // sparse row (neighbour index, first distance, second distance).  ANI keys are un-transformed as
 // 1.0f - key like the reference (src/distances/mod.rs:183-189).
 __global__ void knn_merge_kernel(const unsigned long long *__restrict__ part_key, const float *__restrict__ part_aux,
-                                 uint32_t n_split, uint32_t knn, uint64_t first_lrow, uint64_t n_rows, int kind,
+                                 uint32_t n_split, uint32_t knn, uint32_t cap, uint64_t first_lrow, uint64_t n_rows,
+                                 int kind,
                                  unsigned long long *__restrict__ idx_out, float *__restrict__ d0_out,
                                  float *__restrict__ d1_out) {
     const uint64_t row = (uint64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     const int lane = threadIdx.x & 31;
     if (row >= n_rows) return;
     const uint64_t lrow = first_lrow + row;
-    const unsigned long long *pk = part_key + lrow * n_split * knn;
-    const float *pa = part_aux ? part_aux + lrow * n_split * knn : nullptr;
+    // list of (row block rbl, split s, row r) starts at ((rbl * n_split + s) * TS + r) * cap
+    const uint64_t rbl = lrow / TS, r = lrow % TS;
+    auto list = [&](uint32_t s) { return ((rbl * n_split + s) * TS + r) * (uint64_t)cap; };
     const uint32_t total = n_split * knn;
     // rank of element e = number of elements smaller than it (composites are unique per row except padding)
     for (uint32_t e = lane; e < total; e += 32) {
-        unsigned long long v = pk[e];
+        const uint64_t src = list(e / knn) + e % knn;
+        unsigned long long v = part_key[src];
         if (v == ~0ull) continue;
         uint32_t rank = 0;
         for (uint32_t s = 0; s < n_split; ++s) {
             // binary search in list s for the number of entries < v
-            const unsigned long long *l = pk + s * knn;
+            const unsigned long long *l = part_key + list(s);
             uint32_t lo = 0, hi = knn;
             while (lo < hi) {
                 uint32_t mid = (lo + hi) >> 1;
@@ -504,18 +575,18 @@ __global__ void knn_merge_kernel(const unsigned long long *__restrict__ part_key
             float key = float_from_order_bits((uint32_t)(v >> 32));
             idx_out[row * knn + rank] = (unsigned long long)(uint32_t)v;
             d0_out[row * knn + rank] = kind == KIND_ANI ? 1.0f - key : key;
-            if (d1_out) d1_out[row * knn + rank] = pa ? pa[e] : 0.0f;
+            if (d1_out) d1_out[row * knn + rank] = part_aux ? part_aux[src] : 0.0f;
         }
     }
 }
 
 void launch_knn_merge(const unsigned long long *part_key, const float *part_aux, uint32_t n_split, uint32_t knn,
-                      uint64_t first_lrow, uint64_t n_rows, int kind, unsigned long long *idx_out, float *d0_out,
+                      uint32_t cap, uint64_t first_lrow, uint64_t n_rows, int kind, unsigned long long *idx_out, float *d0_out,
                       float *d1_out, cudaStream_t st) {
     if (n_rows == 0) return;
     const int warps = 8;
     knn_merge_kernel<<<(unsigned)((n_rows + warps - 1) / warps), warps * 32, 0, st>>>(
-        part_key, part_aux, n_split, knn, first_lrow, n_rows, kind, idx_out, d0_out, d1_out);
+        part_key, part_aux, n_split, knn, cap, first_lrow, n_rows, kind, idx_out, d0_out, d1_out);
 }
 
 // ------------------------------------------------------------------------------------------------

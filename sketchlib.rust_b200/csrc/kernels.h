@@ -12,13 +12,14 @@ namespace skd {
 void launch_repack(const uint64_t *raw, uint64_t raw_samples, uint64_t sample_stride, uint64_t kmer_stride,
                    uint32_t *tiled, const DevDb &db, uint32_t b0, uint32_t n_blocks, cudaStream_t st);
 
+int counts_per_pair(int nk, bool count32);
 size_t tile_kernel_smem(int nk, bool count32, bool knn_mode, uint32_t cap, bool with_aux);
 
 cudaError_t launch_tiles(const DevDb &A, const DevDb &B, const EpiParams &E, const SchedParams &S, uint64_t n_ctas,
                          bool count32, size_t smem, cudaStream_t st);
 
 void launch_knn_merge(const unsigned long long *part_key, const float *part_aux, uint32_t n_split, uint32_t knn,
-                      uint64_t first_lrow, uint64_t n_rows, int kind, unsigned long long *idx_out, float *d0_out,
+                      uint32_t cap, uint64_t first_lrow, uint64_t n_rows, int kind, unsigned long long *idx_out, float *d0_out,
                       float *d1_out, cudaStream_t st);
 
 void launch_pairs(const DevDb &A, const DevDb &B, const EpiParams &E, const uint64_t *pairs, uint64_t n_pairs,

@@ -40,6 +40,7 @@ struct EpiParams {
     int kind;
     int k0;          // first k index the tile loop visits
     int nk;          // number of k indices visited (K for core/acc, 1 for single-k modes)
+    int kp;          // nk rounded up so that one pair's counts fill whole 16-byte shared-memory words
     int has_c;       // completeness vectors supplied for both sides
     uint32_t nbins;  // 64 * W
     uint32_t expected; // expected_samebits = nbins >> 14
@@ -56,6 +57,7 @@ struct EpiParams {
     double xbar[MAXK + 1];
     double x_diff[MAXK + 1];
     double xstddev[MAXK + 1];
+    double rcp_n[MAXK + 1];   // correctly rounded 1/n, for the exact division-by-n sequence
 };
 
 enum : int { MODE_DENSE_SELF = 0, MODE_DENSE_CROSS = 1, MODE_COUNTS = 2, MODE_KNN = 3 };
@@ -76,8 +78,9 @@ struct SchedParams {
     uint32_t knn;
     uint32_t n_split;
     uint32_t cb_per_split;
-    uint32_t cap;         // candidate slots per row (>= knn + TS)
-    unsigned long long *part_key; // [n_rb * TS][n_split][knn] composite (key bits << 32 | idx), ascending
+    uint32_t cap;         // candidate slots per row: a power of two >= knn + TS
+    unsigned long long *part_key; // [n_rb][n_split][TS][cap] composite (key bits << 32 | idx); the first knn
+                                  // of each list are its best, ascending, when the kernel ends
     float *part_aux;              // same shape: accessory distance (core/acc only)
 };
 

@@ -1,0 +1,138 @@
+"""CPU-side tests: host logic of the package, the C-ABI library's exported symbols, the synthetic data
+generator, and the multi-rank sharding logic over gloo (world_size 2).  No GPU needed."""
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+
+import oracle
+from helpers import ROOT, synth_db
+
+
+def test_library_builds_loads_and_exports_every_declared_symbol():
+    import sketchlib.rust_b200 as sk
+    lib = sk.load_library()
+    header = open(os.path.join(ROOT, "include", "sketchdist.h")).read()
+    declared = set(re.findall(r"\b(skd_[a-z0-9_]+)\s*\(", header))
+    declared -= {"skd_status", "skd_loc", "skd_dist_kind", "skd_dist_type"}
+    assert len(declared) >= 28
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/sketchdist.h but not exported"
+    assert set(lib._signatures) == declared  # the ctypes layer binds exactly the declared ABI
+
+
+def test_no_cpu_fallback_without_gpu():
+    import sketchlib.rust_b200 as sk
+    try:
+        import torch
+        if torch.cuda.is_available():
+            pytest.skip("GPU present")
+    except ImportError:
+        pass
+    with pytest.raises(sk.SketchDistError, match="no CPU fallback"):
+        sk.Context(0)
+
+
+def test_pure_helpers_need_no_device():
+    import sketchlib.rust_b200 as sk
+    lib = sk.load_library()
+    for n in (2, 5, 64, 65, 1000, 10000):
+        assert lib.skd_self_pairs_in_rows(n, 0, n) == n * (n - 1) // 2
+        for r0, r1 in ((0, 1), (1, n), (n // 2, n // 2 + 1), (3, 2)):
+            want = sum(n - 1 - i for i in range(r0, min(r1, n)))
+            assert lib.skd_self_pairs_in_rows(n, r0, r1) == want
+        for world in (1, 2, 3, 4, 8):
+            tri = [sk.triangle_row_partition(n, r, world) for r in range(world)]
+            assert tri[0][0] == 0 and tri[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(tri, tri[1:]))
+            ev = [sk.row_partition(n, r, world) for r in range(world)]
+            assert ev[0][0] == 0 and ev[-1][1] == n and all(a[1] == b[0] for a, b in zip(ev, ev[1:]))
+            assert max(b - a for a, b in ev) - min(b - a for a, b in ev) <= 1
+    # equal pair counts to within one 64-row tile band
+    n, world = 100000, 8
+    counts = [lib.skd_self_pairs_in_rows(n, *sk.triangle_row_partition(n, r, world)) for r in range(world)]
+    assert max(counts) / min(counts) < 1.02
+
+
+def test_text_rendering_matches_rust_display():
+    import sketchlib.rust_b200 as sk
+    assert [sk.fmt_f32(x) for x in (1.0, 0.0, 0.008820182, 0.2137754, 0.35546875, 0.99009615, 1e-7)] == \
+        ["1", "0", "0.008820182", "0.2137754", "0.35546875", "0.99009615", "0.0000001"]
+    names = ["a", "b", "c"]
+    dm = sk.DistanceMatrix(names, None, sk.DistType(sk.CORE_ACC), np.array([0.5, 1, 0.25, 0, 1, 1], np.float32), (0, 3))
+    assert str(dm) == "a\tb\t0.5\t1\na\tc\t0.25\t0\nb\tc\t1\t1\n"
+    dmx = sk.DistanceMatrix(names, ["q"], sk.DistType(sk.JACCARD, 0, 21), np.array([0.5, 1, 0.25], np.float32), (0, 3))
+    assert str(dmx) == "a\tq\t0.5\nb\tq\t1\nc\tq\t0.25\n"
+    sp = sk.SparseDistanceMatrix(names, None, sk.DistType(sk.JACCARD, 0, 21), 2, np.array([[1, 0], [0, 2], [1, 2]], np.uint64),
+                                 np.array([[0.5, 1.0], [0.5, 0.75], [0.75, 1.0]], np.float32), None, (0, 3))
+    # padding entries (dist 1, self) are skipped: distance_matrix.rs:376-381
+    assert str(sp) == "a\tb\t0.5\nb\ta\t0.5\nb\tc\t0.75\nc\tb\t0.75\n"
+    assert str(sk.DistType(sk.CORE_ACC)) == "Distances: core/accessory regression"
+    assert str(sk.DistType(sk.ANI, 0, 21)) == "Distances: ANI at k=21"
+
+
+def test_synth_bit_slice_matches_fill_usigs():
+    import torch
+    from sketchlib.rust_b200 import synth
+    rng = np.random.default_rng(3)
+    bins = rng.integers(0, 1 << 14, size=(5, 3, 128), dtype=np.uint16)
+    got = synth.as_u64_numpy(synth.bit_slice(torch.from_numpy(bins.astype(np.int16))))
+    assert np.array_equal(got, oracle.fill_usigs(bins))
+    flat = synth.as_u64_numpy(synth.make_bins(130, 2, [17, 21, 25], seed=1, family_mean=10))
+    assert flat.size == 130 * 3 * 2 * 14
+    db = oracle.Db(flat, 130, [17, 21, 25], 2)
+    d = oracle.self_dists_all(db, k_idx=0)
+    assert (d < 0.9).any() and (d > 0.9).any()  # families are visible: both related and unrelated pairs
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _shard_worker(rank, world, port, tmp):
+    import torch.distributed as dist
+    import sketchlib.rust_b200 as sk
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    db = synth_db(150, 2, [17, 21, 25], seed=4, n_families=3)
+    lib = sk.load_library()
+    # dense: this rank's triangle row block, computed by the CPU oracle standing in for the device
+    r0, r1 = sk.triangle_row_partition(db.n, rank, world, align=16)
+    first = int(lib.skd_self_pairs_in_rows(db.n, 0, r0))
+    count = int(lib.skd_self_pairs_in_rows(db.n, r0, r1))
+    chunk0 = first - first % 1000
+    mine = oracle.self_dists_all(db, first=chunk0, count=count + first - chunk0)[2 * (first - chunk0):]
+    # kNN: even row split
+    k0, k1 = sk.row_partition(db.n, rank, world)
+    idx, d0, _ = oracle.self_dists_knn(db, 5, k_idx=1, rows=(k0, k1))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (r0, r1, mine, k0, k1, idx, d0))
+    if rank == 0:
+        np.save(os.path.join(tmp, "dense.npy"), np.concatenate([g[2] for g in gathered]))
+        np.save(os.path.join(tmp, "knn_idx.npy"), np.concatenate([g[5] for g in gathered]))
+        assert gathered[0][0] == 0 and gathered[-1][1] == db.n and gathered[0][3] == 0 and gathered[-1][4] == db.n
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_over_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_shard_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    db = synth_db(150, 2, [17, 21, 25], seed=4, n_families=3)
+    assert np.array_equal(np.load(tmp_path / "dense.npy"), oracle.self_dists_all(db))
+    assert np.array_equal(np.load(tmp_path / "knn_idx.npy"), oracle.self_dists_knn(db, 5, k_idx=1)[0])
+
+
+def test_bench_workload_sizes():
+    import bench
+    assert bench.n_for_gpus(1) == 10000 and bench.LOP3_PER_PAIR == 3584 and bench.POPC_PER_PAIR == 256
+    for g in (2, 4, 8):
+        n = bench.n_for_gpus(g)
+        assert n % 64 == 0 and abs(n * (n - 1) / 2 / g - 49995000) / 49995000 < 0.02
