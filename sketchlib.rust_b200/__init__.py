@@ -53,7 +53,7 @@ def load_library(build=True):
     if not os.path.exists(_build.LIB):
         raise SketchDistError(2, f"{_build.LIB} is missing: the CUDA extension has not been built "
                                  "(python sketchlib.rust_b200/build.py); there is no CPU fallback")
-    L = C.CDLL(_build.LIB)
+    L = C.CDLL(os.environ.get("SKD_LIB_OVERRIDE", _build.LIB))  # override: ablation builds (tools/)
     vp, u64, u32, i64, dbl, f32p = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int64, C.c_double, C.c_void_p
     sig = {
         "skd_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),

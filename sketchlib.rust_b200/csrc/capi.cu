@@ -251,6 +251,7 @@ skd_status launch_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, const Ep
                         uint64_t r1, float *dout, const std::vector<uint64_t> &off, const uint64_t *d_grp_off) {
     SchedParams S{};
     S.mode = mode;
+    S.one = 1;
     S.self_mode = mode == MODE_DENSE_SELF;
     S.rb0 = (uint32_t)(r0 / TS);
     S.n_rb = (uint32_t)((r1 + TS - 1) / TS) - S.rb0;
@@ -388,6 +389,7 @@ skd_status run_knn(skd_ctx *ctx, const skd_db *R, const skd_db *Q, bool self, co
                     (unsigned long long)knn, E.nk, smem, kMaxSmem);
     SchedParams S{};
     S.mode = MODE_KNN;
+    S.one = 1;
     S.self_mode = self;
     S.rb0 = (uint32_t)(row_begin / TS);
     S.n_rb = (uint32_t)((row_end + TS - 1) / TS) - S.rb0;

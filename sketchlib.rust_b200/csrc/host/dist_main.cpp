@@ -1,0 +1,425 @@
+// `sketchlib dist` -- drop-in front end for the B200 distance path (host-only C++17 above the C ABI).
+//
+// Mirrors the reference's Dist sub-command: flags of src/cli.rs:186-231 (+ the global -v/--verbose, --quiet
+// of src/cli.rs:88-104), control flow of src/lib.rs:303-453 (extension stripping, --subset via
+// read_sketch_data_block, completeness files, set_k, knn clamping :379-382 / :411-414), and the text
+// writers of src/distances/distance_matrix.rs:175-209 (dense) and :360-401 (sparse), byte for byte.
+// Only `dist` is implemented: the other sub-commands are not on the accelerated path.
+// Extra flag: --gpu <id> (default 0).  --threads is accepted for compatibility (the work runs on the GPU).
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../../include/sketchdist.h"
+#include "multisketch.hpp"
+
+using namespace skdhost;
+
+namespace {
+
+int g_level = 1;  // 0 = error (--quiet), 1 = warn (default), 2 = info (-v)
+void log_info(const std::string &m) {
+    if (g_level >= 2) fprintf(stderr, "INFO  [sketchlib] %s\n", m.c_str());
+}
+void log_warn(const std::string &m) {
+    if (g_level >= 1) fprintf(stderr, "WARN  [sketchlib] %s\n", m.c_str());
+}
+
+struct Panic : std::runtime_error {  // where the reference panics (exit code 101)
+    using std::runtime_error::runtime_error;
+};
+struct UsageError : std::runtime_error {  // clap errors (exit code 2)
+    using std::runtime_error::runtime_error;
+};
+
+struct DistArgs {
+    std::string ref_db;
+    std::string query_db;
+    bool has_query = false;
+    std::string output;
+    bool has_output = false;
+    long long knn = -1;
+    std::string subset;
+    long long kmer = -1;
+    bool ani = false;
+    long long threads = 1;
+    std::string ref_completeness_file, query_completeness_file;
+    double completeness_cutoff = 0.64;
+    int gpu = 0;
+    bool verbose = false, quiet = false;
+};
+
+const char *USAGE =
+    "Usage: sketchlib dist [OPTIONS] <REF_DB> [QUERY_DB]\n\n"
+    "Arguments:\n"
+    "  <REF_DB>    The .skm file used as the reference\n"
+    "  [QUERY_DB]  The .skm file used as the query (omit for ref v ref)\n\n"
+    "Options:\n"
+    "  -o <OUTPUT>                        Output filename (omit to output to stdout)\n"
+    "      --knn <KNN>                    Calculate sparse distances with k nearest-neighbours\n"
+    "      --subset <SUBSET>              Sample names to analyse\n"
+    "  -k <KMER>                          K-mer length (if provided only calculate Jaccard distance)\n"
+    "      --ani                          Calculate ANI rather than Jaccard dists, using Poisson model\n"
+    "      --threads <THREADS>            Number of CPU threads [default: 1] (unused: distances run on the GPU)\n"
+    "      --ref-completeness-file <F>    Reference completeness estimates (genome_id<tab>completeness)\n"
+    "      --query-completeness-file <F>  Query completeness estimates (cross-query mode only)\n"
+    "      --completeness-cutoff <X>      Minimum c1*c2 for the completeness correction [default: 0.64]\n"
+    "      --gpu <ID>                     CUDA device [default: 0]\n"
+    "  -v, --verbose                      Show progress messages\n"
+    "      --quiet                        Don't show any messages\n";
+
+long long parse_uint(const std::string &s, const char *what) {
+    if (s.empty() || s.find_first_not_of("0123456789") != std::string::npos)
+        throw UsageError(std::string("invalid value '") + s + "' for '" + what + "'");
+    return atoll(s.c_str());
+}
+
+DistArgs parse_args(int argc, char **argv) {
+    DistArgs a;
+    std::vector<std::string> pos;
+    bool saw_dist = false;
+    for (int i = 1; i < argc; ++i) {
+        std::string t = argv[i];
+        auto value = [&](const std::string &name) -> std::string {  // "--opt v", "--opt=v", "-ov", "-o v", "-o=v"
+            if (t.rfind("--", 0) == 0) {
+                size_t eq = t.find('=');
+                if (eq != std::string::npos) return t.substr(eq + 1);
+            } else if (t.size() > 2) {
+                return t[2] == '=' ? t.substr(3) : t.substr(2);
+            }
+            if (i + 1 >= argc) throw UsageError("a value is required for '" + name + "' but none was supplied");
+            return argv[++i];
+        };
+        auto is = [&](const char *name) { return t == name || t.rfind(std::string(name) + "=", 0) == 0; };
+        if (t == "-h" || t == "--help") {
+            fputs(USAGE, stdout);
+            exit(0);
+        } else if (t == "-v" || t == "--verbose") {
+            a.verbose = true;
+        } else if (t == "--quiet") {
+            a.quiet = true;
+        } else if (t == "--ani") {
+            a.ani = true;
+        } else if (is("--knn")) {
+            a.knn = parse_uint(value("--knn <KNN>"), "--knn <KNN>");
+        } else if (is("--subset")) {
+            a.subset = value("--subset <SUBSET>");
+        } else if (is("--threads")) {
+            a.threads = parse_uint(value("--threads <THREADS>"), "--threads <THREADS>");
+            if (a.threads < 1) throw UsageError("invalid value for '--threads <THREADS>': Threads must be one or higher");
+        } else if (is("--ref-completeness-file")) {
+            a.ref_completeness_file = value("--ref-completeness-file");
+        } else if (is("--query-completeness-file")) {
+            a.query_completeness_file = value("--query-completeness-file");
+        } else if (is("--completeness-cutoff")) {
+            std::string v = value("--completeness-cutoff");
+            char *end = nullptr;
+            a.completeness_cutoff = strtod(v.c_str(), &end);
+            if (v.empty() || end != v.c_str() + v.size())
+                throw UsageError("invalid value '" + v + "' for '--completeness-cutoff <COMPLETENESS_CUTOFF>'");
+        } else if (is("--gpu")) {
+            a.gpu = (int)parse_uint(value("--gpu <ID>"), "--gpu <ID>");
+        } else if (t.rfind("-o", 0) == 0 && t.rfind("--", 0) != 0) {
+            a.output = value("-o <OUTPUT>");
+            a.has_output = true;
+        } else if (t.rfind("-k", 0) == 0 && t.rfind("--", 0) != 0) {
+            a.kmer = parse_uint(value("-k <KMER>"), "-k <KMER>");
+        } else if (t.size() > 1 && t[0] == '-') {
+            throw UsageError("unexpected argument '" + t + "' found");
+        } else if (!saw_dist) {
+            if (t != "dist")
+                throw UsageError("unrecognized subcommand '" + t +
+                                 "': this build implements only `dist` (the B200-accelerated path)");
+            saw_dist = true;
+        } else {
+            pos.push_back(t);
+        }
+    }
+    if (!saw_dist) throw UsageError("a subcommand is required: sketchlib dist ...");
+    if (pos.empty()) throw UsageError("the following required arguments were not provided:\n  <REF_DB>");
+    if (pos.size() > 2) throw UsageError("unexpected argument '" + pos[2] + "' found");
+    a.ref_db = pos[0];
+    if (pos.size() == 2) {
+        a.query_db = pos[1];
+        a.has_query = true;
+    }
+    if (a.ani && a.kmer < 0)
+        throw UsageError("the following required arguments were not provided:\n  -k <KMER>");  // requires("kmer")
+    return a;
+}
+
+struct Gpu {
+    skd_ctx *ctx = nullptr;
+    ~Gpu() {
+        if (ctx) skd_ctx_destroy(ctx);
+    }
+    void check(skd_status st) const {
+        if (st == SKD_OK) return;
+        std::string msg = skd_last_error(ctx);
+        if (st == SKD_ERR_NEED_TWO_K || st == SKD_ERR_EMPTY_DB || st == SKD_ERR_IO) throw Panic(msg);
+        throw std::runtime_error(msg);
+    }
+};
+
+struct Loaded {
+    MultiSketch meta;
+    skd_db *db = nullptr;
+    ~Loaded() {
+        if (db) skd_db_free(db);
+    }
+};
+
+void load_db(const Gpu &gpu, Loaded &L, const std::string &prefix, const std::vector<uint64_t> *file_indices) {
+    const MultiSketch &m = L.meta;
+    const std::string skd = prefix + ".skd";
+    const uint64_t n = file_indices ? file_indices->size() : m.sketch_metadata.size();
+    gpu.check(skd_db_load_skd(gpu.ctx, skd.c_str(), file_indices ? file_indices->data() : nullptr, n, m.sample_stride,
+                              m.kmer_stride, m.sketchsize64, m.sketch_size, m.kmer_lengths.data(),
+                              (uint32_t)m.kmer_lengths.size(), &L.db));
+}
+
+struct Out {
+    FILE *f = stdout;
+    std::string buf;
+    explicit Out(const DistArgs &a) {
+        if (a.has_output) {
+            f = fopen(a.output.c_str(), "wb");
+            if (!f) throw Panic("could not create " + a.output);
+        }
+        buf.reserve(1 << 22);
+    }
+    ~Out() {
+        flush();
+        if (f != stdout) fclose(f);
+    }
+    void flush() {
+        if (!buf.empty() && fwrite(buf.data(), 1, buf.size(), f) != buf.size()) {
+            fprintf(stderr, "Error writing output distances\n");
+            exit(101);
+        }
+        buf.clear();
+    }
+    void line(const std::string &a, const std::string &b, float d0, const float *d1) {
+        buf += a;
+        buf += '\t';
+        buf += b;
+        buf += '\t';
+        buf += fmt_f32(d0);
+        if (d1) {
+            buf += '\t';
+            buf += fmt_f32(*d1);
+        }
+        buf += '\n';
+        if (buf.size() > (1 << 22) - 4096) flush();
+    }
+};
+
+struct Pinned {
+    skd_ctx *ctx;
+    void *p = nullptr;
+    Pinned(const Gpu &g, size_t bytes) : ctx(g.ctx) { g.check(skd_host_alloc(ctx, bytes, &p)); }
+    ~Pinned() { skd_host_free(ctx, p); }
+};
+
+int run(const DistArgs &a) {
+    g_level = a.quiet ? 0 : (a.verbose ? 2 : 1);
+    log_info("Using " + std::to_string(a.threads) + " threads (host); distances run on CUDA device " + std::to_string(a.gpu));
+    // ---- host phase: everything that can fail without the GPU (same messages as the reference)
+    const std::string ref_name = strip_sketch_extension(a.ref_db);
+    Loaded refs;
+    try {
+        refs.meta = MultiSketch::load_metadata(ref_name);
+    } catch (const std::exception &) {
+        throw Panic("Could not read sketch metadata from " + a.ref_db + ".skm");
+    }
+    std::vector<uint64_t> subset_idx;
+    if (!a.subset.empty()) {
+        try {
+            std::vector<std::string> names = read_subset_names(a.subset);
+            log_info("Read " + std::to_string(names.size()) + " names to subset");
+            subset_idx = refs.meta.select_subset(names);
+        } catch (const std::exception &e) {
+            throw Panic(e.what());
+        }
+    }
+    const uint64_t n = refs.meta.number_samples_loaded();
+    std::vector<std::string> warnings;
+    std::vector<double> ref_c, query_c;
+    const bool has_ref_c = !a.ref_completeness_file.empty();
+    if (has_ref_c) {
+        ref_c = read_completeness_file(a.ref_completeness_file, refs.meta, &warnings);
+        for (auto &w : warnings) log_warn(w);
+        warnings.clear();
+    }
+    if (a.kmer >= 0 && !refs.meta.get_k_idx((uint64_t)a.kmer))  // set_k: src/distances/mod.rs:25-37
+        throw Panic("Error setting k size: K-mer size " + std::to_string(a.kmer) + " not found in file");
+    Loaded queries;
+    std::string qname;
+    const bool has_query_c = a.has_query && !a.query_completeness_file.empty();
+    if (a.has_query) {
+        qname = strip_sketch_extension(a.query_db);
+        try {
+            queries.meta = MultiSketch::load_metadata(qname);
+        } catch (const std::exception &) {
+            throw Panic("Could not read sketch metadata from " + a.query_db + ".skm");
+        }
+        if (has_query_c) {
+            query_c = read_completeness_file(a.query_completeness_file, queries.meta, &warnings);
+            for (auto &w : warnings) log_warn(w);
+        }
+    }
+
+    // ---- device phase
+    Out out(a);
+    Gpu gpu;
+    if (skd_ctx_create(a.gpu, &gpu.ctx) != SKD_OK) throw std::runtime_error(skd_last_error(nullptr));
+    log_info("Loading sketch data from " + ref_name + ".skd");
+    load_db(gpu, refs, ref_name, a.subset.empty() ? nullptr : &subset_idx);
+    skd_dist_type dt;
+    {
+        skd_status st = skd_set_k(gpu.ctx, refs.db, a.kmer, a.ani ? 1 : 0, &dt);
+        if (st != SKD_OK) throw Panic(std::string("Error setting k size: ") + skd_last_error(gpu.ctx));
+        if (dt.kind == SKD_CORE_ACC)
+            log_info("Distances: core/accessory regression");
+        else
+            log_info(std::string(dt.kind == SKD_ANI ? "Distances: ANI at k=" : "Distances: Jaccard distances at k=") +
+                     std::to_string(a.kmer));
+    }
+    const int ncols = dt.kind == SKD_CORE_ACC ? 2 : 1;
+    if (a.has_query) {
+        log_info("Loading query sketch data from " + qname + ".skd");
+        load_db(gpu, queries, qname, nullptr);
+    }
+
+    const size_t kChunkBytes = (size_t)1 << 30;  // dense results are produced and written in row chunks
+    if (!a.has_query) {
+        if (a.knn < 0) {
+            log_info("Calculating all ref vs ref distances");
+            if (n >= 2) {
+                uint64_t rows_per = std::max<uint64_t>(64, kChunkBytes / std::max<uint64_t>(1, n * ncols * 4) / 64 * 64);
+                Pinned buf(gpu, std::min<size_t>(skd_self_pairs_in_rows(n, 0, n), (size_t)rows_per * n) * ncols * 4 + 16);
+                log_info("Writing out in long matrix form");
+                for (uint64_t r0 = 0; r0 < n - 1; r0 += rows_per) {
+                    uint64_t r1 = std::min(n, r0 + rows_per);
+                    gpu.check(skd_self_dists_all(gpu.ctx, refs.db, dt, has_ref_c ? ref_c.data() : nullptr,
+                                                 a.completeness_cutoff, r0, r1, (float *)buf.p, SKD_HOST));
+                    const float *d = (const float *)buf.p;
+                    for (uint64_t i = r0; i < r1; ++i) {
+                        const std::string &rn = refs.meta.sketch_name(i);
+                        for (uint64_t j = i + 1; j < n; ++j, d += ncols)
+                            out.line(rn, refs.meta.sketch_name(j), d[0], ncols == 2 ? d + 1 : nullptr);
+                    }
+                }
+            } else {
+                gpu.check(skd_self_dists_all(gpu.ctx, refs.db, dt, nullptr, a.completeness_cutoff, 0, n, nullptr, SKD_HOST));
+            }
+        } else {
+            if (n < 2) throw Panic("attempt to subtract with overflow: fewer than two samples loaded");
+            uint64_t nn = (uint64_t)a.knn;
+            if (nn >= n) {  // a genome cannot be its own neighbour: src/lib.rs:379-382
+                log_warn("knn=" + std::to_string(nn) + " is higher than number of samples=" + std::to_string(n));
+                nn = n - 1;
+            }
+            log_info("Calculating sparse ref vs ref distances with " + std::to_string(nn) + " nearest neighbours");
+            std::vector<uint64_t> idx(n * nn);
+            std::vector<float> d0(n * nn), d1(ncols == 2 ? n * nn : 0);
+            gpu.check(skd_self_dists_knn(gpu.ctx, refs.db, nn, dt, has_ref_c ? ref_c.data() : nullptr,
+                                         a.completeness_cutoff, 0, n, idx.data(), d0.data(),
+                                         ncols == 2 ? d1.data() : nullptr, SKD_HOST));
+            log_info("Writing out in sparse matrix form");
+            for (uint64_t r = 0; r < n; ++r) {
+                const std::string &rn = refs.meta.sketch_name(r);
+                for (uint64_t t = 0; t < nn; ++t) {
+                    const std::string &cn = refs.meta.sketch_name(idx[r * nn + t]);
+                    if (ncols == 2)
+                        out.line(rn, cn, d0[r * nn + t], &d1[r * nn + t]);
+                    else if (d0[r * nn + t] < 1.0f || cn != rn)  // padding rule: distance_matrix.rs:376-381
+                        out.line(rn, cn, d0[r * nn + t], nullptr);
+                }
+            }
+        }
+    } else {
+        const uint64_t nq = queries.meta.number_samples_loaded();
+        const double *rc = has_ref_c ? ref_c.data() : nullptr, *qc = has_query_c ? query_c.data() : nullptr;
+        if (a.knn >= 0) {
+            uint64_t nn = (uint64_t)a.knn;
+            if (nn > n) {  // src/lib.rs:411-414
+                log_warn("knn=" + std::to_string(nn) + " is higher than number of reference samples=" + std::to_string(n));
+                nn = n;
+            }
+            log_info("Calculating sparse ref vs query distances with " + std::to_string(nn) + " nearest neighbours");
+            uint64_t used = nn;
+            std::vector<uint64_t> idx(nq * std::max<uint64_t>(nn, 1));
+            std::vector<float> d0(idx.size()), d1(ncols == 2 ? idx.size() : 0);
+            gpu.check(skd_cross_dists_knn(gpu.ctx, refs.db, queries.db, nn, dt, rc, qc, a.completeness_cutoff, 0, nq,
+                                          idx.data(), d0.data(), ncols == 2 ? d1.data() : nullptr, SKD_HOST, &used));
+            log_info("Writing out in sparse matrix form");
+            for (uint64_t r = 0; r < nq; ++r) {
+                const std::string &rn = queries.meta.sketch_name(r);  // rows are queries: distance_matrix.rs:364
+                for (uint64_t t = 0; t < used; ++t) {
+                    const std::string &cn = refs.meta.sketch_name(idx[r * used + t]);
+                    if (ncols == 2)
+                        out.line(rn, cn, d0[r * used + t], &d1[r * used + t]);
+                    else if (d0[r * used + t] < 1.0f || cn != rn)
+                        out.line(rn, cn, d0[r * used + t], nullptr);
+                }
+            }
+        } else {
+            log_info("Calculating all ref vs query distances");
+            if (n > 0 && nq > 0) {
+                uint64_t rows_per = std::max<uint64_t>(64, kChunkBytes / std::max<uint64_t>(1, nq * ncols * 4) / 64 * 64);
+                Pinned buf(gpu, (size_t)std::min(rows_per, n) * nq * ncols * 4 + 16);
+                log_info("Writing out in long matrix form");
+                for (uint64_t r0 = 0; r0 < n; r0 += rows_per) {
+                    uint64_t r1 = std::min(n, r0 + rows_per);
+                    gpu.check(skd_cross_dists_all(gpu.ctx, refs.db, queries.db, dt, rc, qc, a.completeness_cutoff, r0, r1,
+                                                  (float *)buf.p, SKD_HOST));
+                    const float *d = (const float *)buf.p;
+                    for (uint64_t i = r0; i < r1; ++i) {
+                        const std::string &rn = refs.meta.sketch_name(i);
+                        for (uint64_t j = 0; j < nq; ++j, d += ncols)
+                            out.line(rn, queries.meta.sketch_name(j), d[0], ncols == 2 ? d + 1 : nullptr);
+                    }
+                }
+            } else {
+                gpu.check(skd_cross_dists_all(gpu.ctx, refs.db, queries.db, dt, rc, qc, a.completeness_cutoff, 0, n,
+                                              nullptr, SKD_HOST));
+            }
+        }
+    }
+    out.flush();
+    return 0;
+}
+
+}  // namespace
+
+int main(int argc, char **argv) {
+    auto start = std::chrono::steady_clock::now();
+    DistArgs a;
+    try {
+        a = parse_args(argc, argv);
+    } catch (const UsageError &e) {
+        fprintf(stderr, "error: %s\n\n%s", e.what(), USAGE);
+        return 2;
+    }
+    try {
+        run(a);
+    } catch (const Panic &e) {
+        fprintf(stderr, "thread 'main' panicked:\n%s\n", e.what());
+        return 101;
+    } catch (const std::exception &e) {
+        fprintf(stderr, "Error: %s\n", e.what());
+        return 1;
+    }
+    log_info("Complete");
+    if (!a.quiet) {
+        auto secs = std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - start).count();
+        fprintf(stderr, "\xF0\x9F\xA7\xAC\xF0\x9F\x96\x8B\xEF\xB8\x8F sketchlib done in %llds\n", (long long)secs);
+    }
+    return 0;
+}

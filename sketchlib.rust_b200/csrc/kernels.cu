@@ -26,6 +26,9 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     asm volatile(
         "{\n"
@@ -38,6 +41,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "}\n" ::"r"(smem_u32(bar)),
         "r"(parity)
         : "memory");
+}
+// Non-blocking phase probe: lets a warp learn early (mid-iteration) that the next stage has landed, so the
+// ~90-cycle latency of the phase check is off the critical path at the top of the next iteration.
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity));
+    return ok != 0;
 }
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -108,12 +125,12 @@ __device__ __forceinline__ double ani_pois_dev(double j, double k) {
 // makes the quotient faithful, the second rounds it correctly.  Inputs here are far from the
 // overflow/underflow ranges where the sequence would need a slow path (zero, inf and NaN pass through).
 __device__ __forceinline__ double div_by_n(double x, double dn, double rcp) {
+    // tiny or non-finite x (never seen in practice): the plain division is exact by definition
+    const int hi = __double2hiint(x) & 0x7fffffff;
+    if (__builtin_expect(hi < 0x05000000 || hi >= 0x7a000000, 0)) return __ddiv_rn(x, dn);
     double q = __dmul_rn(x, rcp);
     q = __fma_rn(__fma_rn(-dn, q, x), rcp, q);
-    double r = __fma_rn(-dn, q, x);
-    double q2 = __fma_rn(r, rcp, q);
-    // tiny or non-finite x: fall back to the plain division (exact by definition)
-    return (fabs(x) > 1e-280 && fabs(x) < 1e280) ? q2 : __ddiv_rn(x, dn);
+    return __fma_rn(__fma_rn(-dn, q, x), rcp, q);
 }
 
 // simple_linear_regression (jaccard.rs:105-142) with the x statistics tabulated per n.
@@ -168,7 +185,7 @@ struct TileCoord {
 template <typename CountT>
 __device__ __forceinline__ void tile_counts(const DevDb &A, const DevDb &B, uint32_t rb, uint32_t cb, int k0, int nk,
                                             uint32_t *stage_mem, uint64_t *full_bar, CountT *counts, int kp,
-                                            uint32_t &git) {
+                                            uint32_t one, uint32_t &git) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int arow0 = 16 * (warp >> 1) + (lane >> 3);
     const int bcol0 = 32 * (warp & 1) + (lane & 7);
@@ -185,9 +202,12 @@ __device__ __forceinline__ void tile_counts(const DevDb &A, const DevDb &B, uint
         bulk_g2s(dst + STAGE_U32, B.tiled + slab_index(B, k, w, cb) * STAGE_U32, STAGE_BYTES, bar);
     };
 
+    // One CTA barrier per pipeline iteration frees the stage consumed in the previous iteration; thread 0
+    // then refills it (two iterations ahead).  A variant with per-stage "empty" mbarriers and a rotating
+    // producer warp (no CTA barrier) measured 4 % slower on B200 and was dropped (profiles/README.md).
     if (tid == 0) {
         uint32_t pre = n_it < (uint32_t)(NST - 1) ? n_it : (uint32_t)(NST - 1);
-        for (uint32_t p = 0; p < pre; ++p) issue(p);
+        for (uint32_t p = 0; p < pre; ++p) issue(p);  // all stages are free at tile start (CTA barrier before)
     }
 
     uint32_t mism[4][4];
@@ -197,25 +217,37 @@ __device__ __forceinline__ void tile_counts(const DevDb &A, const DevDb &B, uint
         for (int j = 0; j < 4; ++j) mism[i][j] = 0;
 
     uint32_t w_in_k = 0, kk = 0;
+    bool ready = false;
     for (uint32_t it = 0; it < n_it; ++it) {
         if (it > 0) __syncthreads();  // every warp is done with iteration it-1: its stage may be refilled
         if (tid == 0 && it + NST - 1 < n_it) issue(it + NST - 1);
         const uint32_t g = git + it;
-        mbar_wait(&full_bar[g % NST], (g / NST) & 1u);
+        if (!ready) mbar_wait(&full_bar[g % NST], (g / NST) & 1u);
         const uint2 *sa = reinterpret_cast<const uint2 *>(stage_mem + (g % NST) * (2 * STAGE_U32));
         const uint2 *sb = sa + STAGE_U32 / 2;
 
-        uint32_t pc0[4][4];
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             uint32_t d[4][4];
 #pragma unroll
             for (int pp = 0; pp < PP; ++pp) {
                 uint2 av[4], bv[4];
+#ifdef SKD_ABLATE_LDS
+                if (pp == 0) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) av[i] = sa[(half * PP + pp) * TS + arow0 + 4 * i];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) bv[j] = sb[(half * PP + pp) * TS + bcol0 + 8 * j];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { av[i].x = av[i].x * 3 + pp; av[i].y += one; }
+                }
+#else
 #pragma unroll
                 for (int i = 0; i < 4; ++i) av[i] = sa[(half * PP + pp) * TS + arow0 + 4 * i];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) bv[j] = sb[(half * PP + pp) * TS + bcol0 + 8 * j];
+#endif
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -227,15 +259,12 @@ __device__ __forceinline__ void tile_counts(const DevDb &A, const DevDb &B, uint
                         d[i][j] |= av[i].y ^ bv[j].y;
                     }
             }
+            // accumulate on the FMA pipe (IMAD with a run-time 1) so the ALU pipe only sees the LOP3s
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    if (half == 0)
-                        pc0[i][j] = __popc(d[i][j]);
-                    else
-                        mism[i][j] += pc0[i][j] + __popc(d[i][j]);  // one 3-input add per 64 bins
-                }
+                for (int j = 0; j < 4; ++j) mism[i][j] = __popc(d[i][j]) * one + mism[i][j];
+            if (half == 0) ready = it + 1 < n_it && mbar_test(&full_bar[(g + 1) % NST], ((g + 1) / NST) & 1u);
         }
 
         if (++w_in_k == W) {  // finished this k: park the match counts in shared memory
@@ -381,7 +410,7 @@ __global__ void __launch_bounds__(THREADS, 2)
         const uint32_t cb = cb_first + (uint32_t)(local / rows_in_g);
         if (S.mode == MODE_DENSE_SELF && cb < rb) return;  // below the diagonal (only inside a diagonal group)
 
-        tile_counts<CountT>(A, B, rb, cb, E.k0, E.nk, stage_mem, full_bar, counts, E.kp, git);
+        tile_counts<CountT>(A, B, rb, cb, E.k0, E.nk, stage_mem, full_bar, counts, E.kp, S.one, git);
 
         const uint64_t nA = A.n, nB = B.n;
         for (int m = 0; m < (TS * TS) / THREADS; ++m) {
@@ -401,10 +430,15 @@ __global__ void __launch_bounds__(THREADS, 2)
                 idx = (gi - S.row_begin) * nB + gj;  // ref-major
             }
             float d0, d1;
+#ifdef SKD_ABLATE_EPI
+            d0 = (float)counts[pair * E.kp];
+            d1 = 0.f;
+#else
             if (E.has_c)
                 pair_epilogue<CountT, true>(counts, pair, E, gi, gj, false, d0, d1);
             else
                 pair_epilogue<CountT, false>(counts, pair, E, gi, gj, false, d0, d1);
+#endif
             // results are written once and never re-read by the GPU: streaming stores keep the database in L2
             if (E.kind == KIND_CORE_ACC)
                 __stcs(reinterpret_cast<float2 *>(S.out) + idx, make_float2(d0, d1));
@@ -462,7 +496,7 @@ __global__ void __launch_bounds__(THREADS, 2)
     __syncthreads();
 
     for (uint32_t cb = cb_lo; cb < cb_hi; ++cb) {
-        tile_counts<CountT>(A, B, rb, cb, E.k0, E.nk, stage_mem, full_bar, counts, E.kp, git);
+        tile_counts<CountT>(A, B, rb, cb, E.k0, E.nk, stage_mem, full_bar, counts, E.kp, S.one, git);
         for (int m = 0; m < (TS * TS) / THREADS; ++m) {
             const int pair = m * THREADS + tid;
             const int row = pair / TS;

@@ -74,6 +74,8 @@ struct SchedParams {
     uint64_t row_begin, row_end; // sample-level row range (clips the first/last block)
     uint64_t out_base;    // dense self: condensed index of (row_begin, row_begin+1)
     float *out;           // dense: distances; counts mode: reinterpret as uint32_t*
+    uint32_t one;         // always 1: a multiplier the compiler cannot fold, see tile_counts
+    uint32_t pad0_;
     // kNN: each CTA owns one row block and column blocks [split * cb_per_split, ...)
     uint32_t knn;
     uint32_t n_split;

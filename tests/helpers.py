@@ -76,3 +76,68 @@ def render_sparse(row_names, col_names, idx, d0, d1=None):
             else:
                 lines.append(f"{rn}\t{cn}\t{oracle.fmt_f32(d0[r, t])}\t{oracle.fmt_f32(d1[r, t])}\n")
     return "".join(lines)
+
+
+# ---------------------------------------------------------------- .skm writer (tests only)
+def _cbor(obj):
+    def head(major, val):
+        if val < 24:
+            return bytes([(major << 5) | val])
+        for info, nb in ((24, 1), (25, 2), (26, 4), (27, 8)):
+            if val < (1 << (8 * nb)):
+                return bytes([(major << 5) | info]) + val.to_bytes(nb, "big")
+        raise ValueError(val)
+    if isinstance(obj, bool):
+        return bytes([0xF5 if obj else 0xF4])
+    if isinstance(obj, int):
+        return head(0, obj) if obj >= 0 else head(1, -1 - obj)
+    if isinstance(obj, str):
+        b = obj.encode()
+        return head(3, len(b)) + b
+    if isinstance(obj, (list, tuple)):
+        return head(4, len(obj)) + b"".join(_cbor(x) for x in obj)
+    if isinstance(obj, dict):
+        return head(5, len(obj)) + b"".join(_cbor(k) + _cbor(v) for k, v in obj.items())
+    raise TypeError(type(obj))
+
+
+def _crc32c(data: bytes) -> int:
+    table = getattr(_crc32c, "table", None)
+    if table is None:
+        table = []
+        for i in range(256):
+            c = i
+            for _ in range(8):
+                c = (c >> 1) ^ 0x82F63B78 if c & 1 else c >> 1
+            table.append(c)
+        _crc32c.table = table
+    crc = 0xFFFFFFFF
+    for b in data:
+        crc = table[(crc ^ b) & 0xFF] ^ (crc >> 8)
+    return crc ^ 0xFFFFFFFF
+
+
+def write_skm_skd(prefix, db, version="0.3.0"):
+    """Writes <prefix>.skm/.skd for an oracle.Db in the reference's container format (snappy frame with
+    uncompressed chunks + CBOR map with the serde field names of MultiSketch / Sketch)."""
+    meta = {
+        "sketch_size": db.sketch_size, "sketchsize64": db.W, "kmer_lengths": [int(k) for k in db.kmers],
+        "sketch_metadata": [
+            {"name": nm, "index": i, "rc": True, "reads": False, "seq_length": 2000000, "densified": False,
+             "acgt": [1, 1, 1, 1], "non_acgt": 0} for i, nm in enumerate(db.names)],
+        "name_map": {nm: i for i, nm in enumerate(db.names)},
+        "bin_stride": 1, "kmer_stride": db.kmer_stride, "sample_stride": db.sample_stride,
+        "sketch_version": version, "hash_type": "DNA",
+    }
+    payload = _cbor(meta)
+    out = bytearray(b"\xff\x06\x00\x00sNaPpY")
+    for off in range(0, len(payload), 65536):
+        chunk = payload[off:off + 65536]
+        crc = _crc32c(chunk)
+        masked = (((crc >> 15) | (crc << 17)) + 0xA282EAD8) & 0xFFFFFFFF
+        body = masked.to_bytes(4, "little") + chunk
+        out += b"\x01" + len(body).to_bytes(3, "little") + body
+    with open(prefix + ".skm", "wb") as fh:
+        fh.write(bytes(out))
+    db.bins[: db.n * db.sample_stride].astype("<u8").tofile(prefix + ".skd")
+    return prefix

@@ -101,7 +101,8 @@ int main(int argc, char **argv) {
     double seconds = argc > 1 ? atof(argv[1]) : 1.0;
     cudaDeviceProp prop;
     cudaGetDeviceProperties(&prop, 0);
-    const int sms = prop.multiProcessorCount, cps = 4;  // 4 x 256 threads = 32 warps per SM
+    const int sms = prop.multiProcessorCount;
+    const int cps = argc > 2 ? atoi(argv[2]) : 4;  // CTAs of 256 threads per SM (4 => 32 warps per SM)
     uint32_t *out;
     unsigned long long *cyc;
     cudaMalloc(&out, (size_t)sms * cps * 256 * 4);
@@ -109,7 +110,7 @@ int main(int argc, char **argv) {
     Result l = run<M_LOP3>(sms, cps, seconds, out, cyc);
     Result p = run<M_POPC>(sms, cps, seconds, out, cyc);
     Result m = run<M_MIX>(sms, cps, seconds, out, cyc);
-    printf("{\"gpu\": \"%s\", \"sms\": %d, \"seconds_each\": %.2f,\n", prop.name, sms, seconds);
+    printf("{\"gpu\": \"%s\", \"sms\": %d, \"seconds_each\": %.2f, \"warps_per_sm\": %d,\n", prop.name, sms, seconds, cps * 8);
     printf(" \"lop3_per_s\": %.4e, \"lop3_per_clk_sm\": %.2f, \"lop3_sm_mhz\": %.0f,\n", l.ops_per_s, l.ops_per_clk_sm, l.sm_mhz);
     printf(" \"popc_per_s\": %.4e, \"popc_per_clk_sm\": %.2f, \"popc_sm_mhz\": %.0f,\n", p.ops_per_s, p.ops_per_clk_sm, p.sm_mhz);
     printf(" \"mix_lop3_per_s\": %.4e, \"mix_lop3_per_clk_sm\": %.2f, \"mix_sm_mhz\": %.0f,\n", m.ops_per_s, m.ops_per_clk_sm, m.sm_mhz);
