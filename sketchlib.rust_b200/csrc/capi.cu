@@ -489,14 +489,15 @@ skd_status db_build(skd_ctx *ctx, const ChunkSource &src, uint64_t n, uint64_t s
             return bail(fail(ctx, SKD_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
                              __LINE__));                                                                \
     } while (0)
-    if (db->tiled_bytes) CUB(cudaMalloc(&db->tiled, db->tiled_bytes));
+    if (db->tiled_bytes) CUB(cudaMallocAsync((void **)&db->tiled, db->tiled_bytes, ctx->compute));
     db->dev.tiled = db->tiled;
     {   // ln J by match count with the host libm (the reference calls f64::ln per pair, jaccard.rs:88)
         const uint32_t nbins = (uint32_t)(64 * W);
         std::vector<double> lny((size_t)nbins + 1);
         for (uint32_t c = 0; c <= nbins; ++c) lny[c] = std::log(host_jaccard(c, nbins));
-        CUB(cudaMalloc(&db->lny_dev, lny.size() * sizeof(double)));
-        CUB(cudaMemcpy(db->lny_dev, lny.data(), lny.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CUB(cudaMallocAsync((void **)&db->lny_dev, lny.size() * sizeof(double), ctx->compute));
+        CUB(cudaMemcpyAsync(db->lny_dev, lny.data(), lny.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->compute));
+        CUB(cudaStreamSynchronize(ctx->compute));  // lny is a local vector
     }
     if (n > 0) {
         if (src.direct && src.loc == SKD_DEVICE) {
@@ -603,6 +604,13 @@ skd_status skd_ctx_create(int device, skd_ctx **out) {
                     prop.major, prop.minor);
     }
     ctx->sm_count = prop.multiProcessorCount;
+    {   // keep freed database buffers in the device's default pool instead of returning them to the driver
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    }
     if (const char *e = getenv("SKD_ZEROCOPY")) ctx->zero_copy = atoi(e) != 0;
     if (const char *e = getenv("SKD_RESULT_CHUNK_MB")) kResultChunkBytes = (size_t)std::max(1, atoi(e)) << 20;
     for (int i = 0; i < 2; ++i) {
@@ -720,8 +728,9 @@ skd_status skd_db_load_skd(skd_ctx *ctx, const char *skd_path, const uint64_t *s
 void skd_db_free(skd_db *db) {
     if (!db) return;
     if (db->ctx) cudaSetDevice(db->ctx->device);
-    if (db->tiled) cudaFree(db->tiled);
-    if (db->lny_dev) cudaFree(db->lny_dev);
+    cudaStream_t st = db->ctx ? db->ctx->compute : nullptr;
+    if (db->tiled) cudaFreeAsync(db->tiled, st);  // back to the device pool: the next upload reuses it
+    if (db->lny_dev) cudaFreeAsync(db->lny_dev, st);
     delete db;
 }
 uint64_t skd_db_n_samples(const skd_db *db) { return db ? db->n : 0; }

@@ -229,6 +229,7 @@ struct Pinned {
 int run(const DistArgs &a) {
     g_level = a.quiet ? 0 : (a.verbose ? 2 : 1);
     log_info("Using " + std::to_string(a.threads) + " threads (host); distances run on CUDA device " + std::to_string(a.gpu));
+    Gpu gpu;  // declared first: destroyed after the databases that belong to its context
     // ---- host phase: everything that can fail without the GPU (same messages as the reference)
     const std::string ref_name = strip_sketch_extension(a.ref_db);
     Loaded refs;
@@ -276,7 +277,6 @@ int run(const DistArgs &a) {
 
     // ---- device phase
     Out out(a);
-    Gpu gpu;
     if (skd_ctx_create(a.gpu, &gpu.ctx) != SKD_OK) throw std::runtime_error(skd_last_error(nullptr));
     log_info("Loading sketch data from " + ref_name + ".skd");
     load_db(gpu, refs, ref_name, a.subset.empty() ? nullptr : &subset_idx);

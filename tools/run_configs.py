@@ -1,0 +1,202 @@
+"""Runs BASELINE.json configs[2..4] (and reduced variants) on the visible GPU(s) and prints one JSON line each.
+
+    python tools/run_configs.py [--scale 1.0] [--configs 3,4,5] [--out profiles/r1_configs.jsonl]
+    torchrun --nproc-per-node N tools/run_configs.py ...      (rows / queries / refs sharded over ranks)
+
+config 3: n=100k genomes, 1024 bins, K=8, self kNN 50 core/accessory (rows split evenly over ranks)
+config 4: 10k queries vs 1M refs, 1024 bins, K=8: cross kNN 50 (queries split) and dense (ref row blocks,
+          results left in HBM chunk by chunk: 80 GB of f32 pairs do not fit one host buffer)
+config 5: n=200k, 10 240 bins (W=160), k=21: dense Jaccard (triangle row blocks, chunked in HBM) and self kNN 50
+--scale shrinks n (not the sketch shape) for quick runs.  Kernel time = CUDA events on the library's stream.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+import sketchlib.rust_b200 as sk  # noqa: E402
+from sketchlib.rust_b200 import synth  # noqa: E402
+
+KMERS8 = list(range(15, 31, 2))
+
+
+def make_db(ctx, n, W, kmers, seed, dev):
+    parts, chunk = [], 100_000
+    t = time.time()
+    bins = torch.empty(n * len(kmers) * W * 14, dtype=torch.int64, device=dev)
+    per = len(kmers) * W * 14
+    for s0 in range(0, n, chunk):
+        s1 = min(n, s0 + chunk)
+        bins[s0 * per:s1 * per] = synth.make_bins(s1 - s0, W, kmers, seed=seed + s0, device=dev)
+    torch.cuda.synchronize()
+    gen_s = time.time() - t
+    t = time.time()
+    g = sk.SketchDb.upload(ctx, bins.data_ptr(), n, kmers, W, bins_loc=sk.SKD_DEVICE)
+    up_s = time.time() - t
+    del bins, parts
+    torch.cuda.empty_cache()
+    return g, gen_s, up_s
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--configs", default="3,4,5")
+    ap.add_argument("--out", default="")
+    ap.add_argument("--reps", type=int, default=2)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def maxr(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ctx = sk.Context(local)
+    want = [int(c) for c in args.configs.split(",")]
+    lines = []
+
+    def emit(d):
+        d.update({"n_gpus": world, "scale": args.scale})
+        if rank == 0:
+            print(json.dumps(d), flush=True)
+            lines.append(d)
+
+    def timed(fn):
+        best = None
+        for _ in range(args.reps):
+            barrier()
+            fn()
+            ms = maxr(ctx.last_kernel_ms_total)
+            best = ms if best is None else min(best, ms)
+        return best
+
+    # accumulate kernel ms over several library calls
+    class Acc:
+        total = 0.0
+    ctx.last_kernel_ms_total = 0.0
+
+    if 3 in want:
+        n = int(100_000 * args.scale)
+        g, gen_s, up_s = make_db(ctx, n, 16, KMERS8, 3, dev)
+        r0, r1 = sk.row_partition(n, rank, world)
+
+        def run():
+            sk.self_dists_knn(g, knn=50, dist_type=sk.set_k(g), rows=(r0, r1))
+            ctx.last_kernel_ms_total = ctx.last_kernel_ms
+        ms = timed(run)
+        emit({"config": 3, "what": "self kNN 50 core/acc, 1024 bins, K=8", "n": n, "kernel_ms": ms,
+              "ordered_pairs_per_s": n * (n - 1) / (ms * 1e-3), "unique_pairs_per_s": n * (n - 1) / 2 / (ms * 1e-3),
+              "lop3_T_per_s": n * (n - 1) * 3584 / (ms * 1e-3) / 1e12, "db_hbm_bytes": g.hbm_bytes,
+              "note": "like the reference, every ordered pair (i, j != i) is evaluated; rows split evenly over ranks"})
+        g.free()
+
+    if 4 in want:
+        n_ref, n_q = int(1_000_000 * args.scale), int(10_000 * max(args.scale, 0.1))
+        gr, _, _ = make_db(ctx, n_ref, 16, KMERS8, 4, dev)
+        gq, _, _ = make_db(ctx, n_q, 16, KMERS8, 5, dev)
+        q0, q1 = sk.row_partition(n_q, rank, world)
+
+        def run_knn():
+            sk.cross_dists_knn(gr, gq, knn=50, dist_type=sk.set_k(gr), rows=(q0, q1))
+            ctx.last_kernel_ms_total = ctx.last_kernel_ms
+        ms = timed(run_knn)
+        emit({"config": 4, "what": "cross kNN 50 core/acc (queries x refs), 1024 bins, K=8", "n_ref": n_ref, "n_query": n_q,
+              "kernel_ms": ms, "pairs_per_s": n_ref * n_q / (ms * 1e-3), "lop3_T_per_s": n_ref * n_q * 3584 / (ms * 1e-3) / 1e12,
+              "ref_db_hbm_bytes": gr.hbm_bytes, "note": "queries split over ranks, reference database replicated"})
+        # dense: this rank's ref rows, in chunks whose results stay in HBM (4 GB buffer)
+        a0, a1 = sk.row_partition(n_ref, rank, world)
+        rows_per = max(64, (4 << 30) // (n_q * 8) // 64 * 64)
+        dbuf = ctx.device_alloc(rows_per * n_q * 8)
+        dt = sk.set_k(gr)
+
+        def run_dense():
+            tot = 0.0
+            for s in range(a0, a1, rows_per):
+                e = min(a1, s + rows_per)
+                ctx._check(ctx.lib.skd_cross_dists_all(ctx.handle, gr.handle, gq.handle, dt.c, None, None, 0.64, s, e, dbuf,
+                                                       sk.SKD_DEVICE))
+                tot += ctx.last_kernel_ms
+            ctx.last_kernel_ms_total = tot
+        ms = timed(run_dense)
+        emit({"config": 4, "what": "cross dense core/acc (ref-major), results left in HBM per 4 GB chunk", "n_ref": n_ref,
+              "n_query": n_q, "kernel_ms": ms, "pairs_per_s": n_ref * n_q / (ms * 1e-3),
+              "lop3_T_per_s": n_ref * n_q * 3584 / (ms * 1e-3) / 1e12,
+              "ref_stream_GBps": gr.hbm_bytes / world / (ms * 1e-3) / 1e9,
+              "note": "refs split over ranks; ref_stream_GBps = each ref slab counted once (INT-bound at 10k queries per ref)"})
+        ctx.device_free(dbuf)
+        gr.free()
+        gq.free()
+
+    if 5 in want:
+        n = int(200_000 * args.scale)
+        g, _, _ = make_db(ctx, n, 160, [21], 6, dev)
+        r0, r1 = sk.triangle_row_partition(n, rank, world)
+        dt = sk.set_k(g, 21)
+        lop3_pair = 160 * 28
+        # chunk rows so that each chunk's results fit a 4 GB device buffer
+        chunks, s = [], r0
+        while s < r1:
+            e = s + 64
+            while e < r1 and int(ctx.lib.skd_self_pairs_in_rows(n, s, min(r1, e + 64))) * 4 <= (4 << 30):
+                e += 64
+            chunks.append((s, min(e, r1)))
+            s = min(e, r1)
+        dbuf = ctx.device_alloc(max(int(ctx.lib.skd_self_pairs_in_rows(n, a, b)) for a, b in chunks) * 4 + 16)
+
+        def run_dense():
+            tot = 0.0
+            for a, b in chunks:
+                ctx._check(ctx.lib.skd_self_dists_all(ctx.handle, g.handle, dt.c, None, 0.64, a, b, dbuf, sk.SKD_DEVICE))
+                tot += ctx.last_kernel_ms
+            ctx.last_kernel_ms_total = tot
+        ms = timed(run_dense)
+        pairs = n * (n - 1) // 2
+        emit({"config": 5, "what": "dense Jaccard k=21, 10240 bins (W=160), results left in HBM per <=4 GB chunk", "n": n,
+              "kernel_ms": ms, "pairs_per_s": pairs / (ms * 1e-3), "lop3_T_per_s": pairs * lop3_pair / (ms * 1e-3) / 1e12,
+              "db_hbm_bytes": g.hbm_bytes, "note": "equal-pair triangle row blocks over ranks"})
+        ctx.device_free(dbuf)
+        k0, k1 = sk.row_partition(n, rank, world)
+        dta = sk.set_k(g, 21, ani=True)
+
+        def run_knn():
+            sk.self_dists_knn(g, knn=50, dist_type=dta, rows=(k0, k1))
+            ctx.last_kernel_ms_total = ctx.last_kernel_ms
+        ms = timed(run_knn)
+        emit({"config": 5, "what": "self kNN 50 ANI k=21, 10240 bins", "n": n, "kernel_ms": ms,
+              "ordered_pairs_per_s": n * (n - 1) / (ms * 1e-3), "lop3_T_per_s": n * (n - 1) * lop3_pair / (ms * 1e-3) / 1e12})
+        g.free()
+
+    if rank == 0 and args.out:
+        with open(os.path.join(ROOT, args.out), "a") as fh:
+            for d in lines:
+                fh.write(json.dumps(d) + "\n")
+    barrier()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
