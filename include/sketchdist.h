@@ -148,6 +148,30 @@ skd_status skd_cross_dists_knn(skd_ctx *ctx, const skd_db *ref, const skd_db *qu
                                uint64_t query_begin, uint64_t query_end, uint64_t *idx_out, float *d0_out,
                                float *d1_out, skd_loc out_loc, uint64_t *knn_used);
 
+/* ---- partial kNN lists for multi-GPU runs that split the COLUMNS of the problem -----------------------------
+ * A partial list is, per row, `knn` opaque 64-bit composites (distance key and neighbour index) in ascending
+ * order, padded with UINT64_MAX, plus (core/accessory only) the accessory distance of each entry.  Ranks exchange
+ * them (one NCCL all-gather / gather: rows x knn x 12 bytes per rank) and skd_knn_merge turns `n_parts` of them
+ * into the reference's sparse rows.  Each candidate must appear in exactly one partial.
+ *
+ * skd_self_knn_partial: symmetric self mode -- evaluates every unordered pair (i, j > i) with i in
+ *   [row_begin, row_end) ONCE and credits it to both rows, so the lists cover ALL n rows (n x knn entries); the
+ *   union over a partition of the rows (row_begin a multiple of 64; use equal-pair triangle blocks) is the
+ *   result of self_dists_knn (src/distances/mod.rs:133-224) at half its pair evaluations.  knn <= 64.
+ * skd_cross_knn_partial: cross mode with the REFERENCES sharded -- the best knn of this shard for every query
+ *   (n_query x knn entries); neighbour indices are shifted by ref_index_offset (the shard's first reference). */
+skd_status skd_self_knn_partial(skd_ctx *ctx, const skd_db *db, uint64_t knn, skd_dist_type dist,
+                                const double *completeness, double completeness_cutoff, uint64_t row_begin,
+                                uint64_t row_end, uint64_t *keys_out, float *aux_out, skd_loc out_loc);
+skd_status skd_cross_knn_partial(skd_ctx *ctx, const skd_db *ref_shard, const skd_db *query, uint64_t knn,
+                                 skd_dist_type dist, const double *ref_completeness, const double *query_completeness,
+                                 double completeness_cutoff, uint64_t ref_index_offset, uint64_t *keys_out,
+                                 float *aux_out, skd_loc out_loc);
+/* keys: [n_parts][n_rows][knn] (aux likewise; NULL unless core/accessory).  Outputs as skd_self_dists_knn. */
+skd_status skd_knn_merge(skd_ctx *ctx, const uint64_t *keys, const float *aux, uint32_t n_parts, uint64_t n_rows,
+                         uint64_t knn, skd_dist_type dist, skd_loc in_loc, uint64_t *idx_out, float *d0_out,
+                         float *d1_out, skd_loc out_loc);
+
 /* Distances for an explicit list of (ref_idx, query_idx) pairs (the per-pair calls inside
  * self_dists_knn_precluster, src/distances/mod.rs:399-553).  out: 1 or 2 floats per pair. */
 skd_status skd_pair_dists(skd_ctx *ctx, const skd_db *ref, const skd_db *query, skd_dist_type dist,

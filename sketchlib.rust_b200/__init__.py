@@ -18,6 +18,7 @@ from . import build as _build
 __all__ = [
     "Context", "SketchDb", "DistType", "DistanceMatrix", "SparseDistanceMatrix", "SketchDistError", "set_k",
     "self_dists_all", "self_dists_knn", "cross_dists_all", "cross_dists_knn", "pair_dists", "match_counts",
+    "self_knn_partial", "cross_knn_partial", "knn_merge",
     "row_partition", "triangle_row_partition", "load_library", "library_path",
 ]
 
@@ -84,6 +85,9 @@ def load_library(build=True):
         "skd_self_dists_knn": (C.c_int, [vp, vp, u64, _DistType, vp, dbl, u64, u64, vp, vp, vp, C.c_int]),
         "skd_cross_dists_knn": (C.c_int, [vp, vp, vp, u64, _DistType, vp, vp, dbl, u64, u64, vp, vp, vp, C.c_int,
                                           C.POINTER(u64)]),
+        "skd_self_knn_partial": (C.c_int, [vp, vp, u64, _DistType, vp, dbl, u64, u64, vp, vp, C.c_int]),
+        "skd_cross_knn_partial": (C.c_int, [vp, vp, vp, u64, _DistType, vp, vp, dbl, u64, vp, vp, C.c_int]),
+        "skd_knn_merge": (C.c_int, [vp, vp, vp, u32, u64, u64, _DistType, C.c_int, vp, vp, vp, C.c_int]),
         "skd_pair_dists": (C.c_int, [vp, vp, vp, _DistType, vp, vp, dbl, vp, u64, vp]),
         "skd_match_counts": (C.c_int, [vp, vp, vp, vp, u64, vp]),
         "skd_match_counts_dense": (C.c_int, [vp, vp, vp, u64, u64, vp]),
@@ -439,6 +443,51 @@ def cross_dists_knn(ref_sketches, query_sketches, n=None, n_query=None, knn=50, 
                                            _ptr(idx), _ptr(d0), _ptr(d1), SKD_HOST, C.byref(used)))
     return SparseDistanceMatrix(ref_sketches.names, query_sketches.names, dist_type, int(used.value), idx, d0, d1,
                                 (r0, r1))
+
+
+def self_knn_partial(sketches, knn=50, dist_type=None, rows=None, completeness_vec=None, completeness_cutoff=0.64):
+    """Symmetric self kNN over triangle rows `rows` (skd_self_knn_partial): partial lists for ALL n rows as
+    (keys uint64 [n, knn], aux float32 [n, knn] or None).  Merge the shards' lists with knn_merge."""
+    ctx = sketches.ctx
+    n = sketches.number_samples_loaded()
+    dist_type = dist_type or DistType(CORE_ACC)
+    r0, r1 = (0, n) if rows is None else rows
+    keys = np.zeros((n, knn), dtype=np.uint64)
+    aux = np.zeros((n, knn), dtype=np.float32) if dist_type.kind == CORE_ACC else None
+    ctx._check(ctx.lib.skd_self_knn_partial(ctx.handle, sketches.handle, int(knn), dist_type.c,
+                                            _ptr(_f64(completeness_vec)), float(completeness_cutoff), r0, r1, _ptr(keys),
+                                            _ptr(aux), SKD_HOST))
+    return keys, aux
+
+
+def cross_knn_partial(ref_shard, query_sketches, knn=50, dist_type=None, ref_index_offset=0, ref_completeness_vec=None,
+                      query_completeness_vec=None, completeness_cutoff=0.64):
+    """Best knn of one reference shard for every query (skd_cross_knn_partial): (keys [n_query, knn], aux)."""
+    ctx = ref_shard.ctx
+    nq = query_sketches.number_samples_loaded()
+    dist_type = dist_type or DistType(CORE_ACC)
+    keys = np.zeros((nq, knn), dtype=np.uint64)
+    aux = np.zeros((nq, knn), dtype=np.float32) if dist_type.kind == CORE_ACC else None
+    ctx._check(ctx.lib.skd_cross_knn_partial(ctx.handle, ref_shard.handle, query_sketches.handle, int(knn), dist_type.c,
+                                             _ptr(_f64(ref_completeness_vec)), _ptr(_f64(query_completeness_vec)),
+                                             float(completeness_cutoff), int(ref_index_offset), _ptr(keys), _ptr(aux),
+                                             SKD_HOST))
+    return keys, aux
+
+
+def knn_merge(ctx, keys_parts, aux_parts, dist_type, ref_names, query_names=None):
+    """Merge partial lists (one per rank / shard) into the reference's sparse rows (skd_knn_merge)."""
+    keys = np.ascontiguousarray(np.stack(keys_parts), dtype=np.uint64)
+    n_parts, n_rows, knn = keys.shape
+    aux = None
+    if dist_type.kind == CORE_ACC:
+        aux = np.ascontiguousarray(np.stack(aux_parts), dtype=np.float32)
+    idx = np.zeros((n_rows, knn), dtype=np.uint64)
+    d0 = np.zeros((n_rows, knn), dtype=np.float32)
+    d1 = np.zeros((n_rows, knn), dtype=np.float32) if dist_type.kind == CORE_ACC else None
+    ctx._check(ctx.lib.skd_knn_merge(ctx.handle, _ptr(keys), _ptr(aux), n_parts, n_rows, knn, dist_type.c, SKD_HOST,
+                                     _ptr(idx), _ptr(d0), _ptr(d1), SKD_HOST))
+    return SparseDistanceMatrix(ref_names, query_names, dist_type, knn, idx, d0, d1, (0, n_rows))
 
 
 def pair_dists(ref_sketches, query_sketches, pairs, dist_type=None, ref_completeness_vec=None,

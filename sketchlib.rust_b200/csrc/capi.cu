@@ -29,6 +29,8 @@ constexpr size_t kMaxSmem = 232448;           // 227 KB opt-in dynamic shared me
 constexpr size_t kUploadChunkBytes = 64ull << 20;
 size_t kResultChunkBytes = 64ull << 20;       // SKD_RESULT_CHUNK_MB overrides
 constexpr uint32_t kGroup = 8;                // row blocks per L2 group
+constexpr uint32_t kSymKnnMax = 64;           // symmetric self-kNN keeps 128-slot lists: knn + 64 candidates per step
+size_t g_sym_chunk_bytes = 2ull << 30;        // HBM buffer of one symmetric-kNN row group (SKD_SYM_CHUNK_MB)
 }  // namespace
 
 struct skd_ctx {
@@ -44,6 +46,7 @@ struct skd_ctx {
     void *pinned[2] = {nullptr, nullptr};
     size_t pinned_bytes = 0;
     int sm_count = 148;
+    bool knn_symmetric = true;  // SKD_KNN_SYMMETRIC=0: whole-matrix self kNN evaluates both (i,j) and (j,i)
     bool zero_copy = true;   // dense kernels store straight into pinned host results (SKD_ZEROCOPY=0 disables)
 };
 
@@ -366,15 +369,19 @@ skd_status run_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, bool self, 
     return timers_collect(ctx);
 }
 
+// Row-owned kNN: the tile kernel scans every column for rows [row_begin, row_end).  Output is either the final
+// sparse rows (idx/d0/d1) or, when key_out is set, one sorted composite list per row (a partial result for a
+// merge across column shards; idx_offset is added to the stored neighbour indices).
 skd_status run_knn(skd_ctx *ctx, const skd_db *R, const skd_db *Q, bool self, const EpiParams &E, uint64_t knn,
                    uint64_t row_begin, uint64_t row_end, uint64_t *idx_out, float *d0_out, float *d1_out,
-                   skd_loc out_loc) {
+                   skd_loc out_loc, uint64_t *key_out = nullptr, float *aux_out = nullptr, uint64_t idx_offset = 0) {
     // Rows are the A side of the tile kernel (self: the database; cross: queries), columns the refs.
     const skd_db *A = self ? R : Q, *B = R;
     const uint64_t n_rows = row_end - row_begin;
     timers_reset(ctx);
     if (n_rows == 0) return SKD_OK;
     const bool with_aux = E.kind == KIND_CORE_ACC;
+    const bool partial = key_out != nullptr;
     uint32_t cap = 128;
     while (cap < knn + TS) cap <<= 1;
     if ((size_t)cap * 12 > (size_t)NST * 2 * STAGE_BYTES)
@@ -397,11 +404,11 @@ skd_status run_knn(skd_ctx *ctx, const skd_db *R, const skd_db *Q, bool self, co
     S.row_end = row_end;
     S.knn = (uint32_t)knn;
     S.cap = cap;
+    S.idx_offset = idx_offset;
     uint32_t want = (uint32_t)((8ull * ctx->sm_count + S.n_rb - 1) / S.n_rb);  // aim for >= 8 waves of CTAs
-    // every split must be able to fill knn slots or be merged with padding; keep splits coarse
-    S.n_split = std::max(1u, std::min(want, B->dev.nb));
-    S.cb_per_split = (B->dev.nb + S.n_split - 1) / S.n_split;
-    S.n_split = (B->dev.nb + S.cb_per_split - 1) / S.cb_per_split;
+    S.n_split = std::max(1u, std::min(want, std::max(1u, B->dev.nb)));
+    S.cb_per_split = (std::max(1u, B->dev.nb) + S.n_split - 1) / S.n_split;
+    S.n_split = (std::max(1u, B->dev.nb) + S.cb_per_split - 1) / S.cb_per_split;
     const size_t part = (size_t)S.n_rb * TS * S.n_split * cap;
     void *pk, *pa = nullptr;
     skd_status st = scratch_get(ctx, "knn_key", part * 8, &pk);
@@ -412,8 +419,56 @@ skd_status run_knn(skd_ctx *ctx, const skd_db *R, const skd_db *Q, bool self, co
     }
     S.part_key = (unsigned long long *)pk;
     S.part_aux = (float *)pa;
+    // device-side destinations
+    unsigned long long *didx = (unsigned long long *)idx_out, *dkey = (unsigned long long *)key_out;
+    float *dd0 = d0_out, *dd1 = d1_out, *daux = aux_out;
+    if (out_loc == SKD_HOST) {
+        void *p;
+        st = scratch_get(ctx, "knn_idx", n_rows * knn * 8, &p);
+        if (st) return st;
+        didx = dkey = (unsigned long long *)p;
+        st = scratch_get(ctx, "knn_d0", n_rows * knn * 4, &p);
+        if (st) return st;
+        dd0 = daux = (float *)p;
+        if (d1_out) {
+            st = scratch_get(ctx, "knn_d1", n_rows * knn * 4, &p);
+            if (st) return st;
+            dd1 = (float *)p;
+        }
+    }
+    st = timer_begin(ctx);
+    if (st) return st;
+    if (partial) launch_fill_u64(dkey, n_rows * knn, ~0ull, ctx->compute);
+    CU(ctx, launch_tiles(A->dev, B->dev, E, S, (uint64_t)S.n_rb * S.n_split, count32, smem, ctx->compute));
+    launch_knn_merge(S.part_key, S.part_aux, S.n_split, S.knn, S.cap, row_begin - (uint64_t)S.rb0 * TS, n_rows, E.kind,
+                     partial ? nullptr : didx, partial ? nullptr : dd0, partial ? nullptr : dd1, partial ? dkey : nullptr,
+                     partial && with_aux ? daux : nullptr, ctx->compute);
+    CU(ctx, cudaGetLastError());
+    ctx->launches += 2;
+    st = timer_end(ctx);
+    if (st) return st;
+    if (out_loc == SKD_HOST) {
+        if (partial) {
+            CU(ctx, cudaMemcpyAsync(key_out, dkey, n_rows * knn * 8, cudaMemcpyDeviceToHost, ctx->compute));
+            if (aux_out && with_aux)
+                CU(ctx, cudaMemcpyAsync(aux_out, daux, n_rows * knn * 4, cudaMemcpyDeviceToHost, ctx->compute));
+        } else {
+            CU(ctx, cudaMemcpyAsync(idx_out, didx, n_rows * knn * 8, cudaMemcpyDeviceToHost, ctx->compute));
+            CU(ctx, cudaMemcpyAsync(d0_out, dd0, n_rows * knn * 4, cudaMemcpyDeviceToHost, ctx->compute));
+            if (d1_out) CU(ctx, cudaMemcpyAsync(d1_out, dd1, n_rows * knn * 4, cudaMemcpyDeviceToHost, ctx->compute));
+        }
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->compute));
+    return timers_collect(ctx);
+}
+
+// Final sparse rows from n_parts device-resident partial lists (keys[part][n_rows][knn]).
+skd_status finalize_lists(skd_ctx *ctx, const unsigned long long *dkeys, const float *daux, uint32_t n_parts,
+                          uint64_t part_stride, uint64_t n_rows, uint64_t knn, int kind, uint64_t *idx_out, float *d0_out,
+                          float *d1_out, skd_loc out_loc) {
     unsigned long long *didx = (unsigned long long *)idx_out;
     float *dd0 = d0_out, *dd1 = d1_out;
+    skd_status st;
     if (out_loc == SKD_HOST) {
         void *p;
         st = scratch_get(ctx, "knn_idx", n_rows * knn * 8, &p);
@@ -430,11 +485,10 @@ skd_status run_knn(skd_ctx *ctx, const skd_db *R, const skd_db *Q, bool self, co
     }
     st = timer_begin(ctx);
     if (st) return st;
-    CU(ctx, launch_tiles(A->dev, B->dev, E, S, (uint64_t)S.n_rb * S.n_split, count32, smem, ctx->compute));
-    launch_knn_merge(S.part_key, S.part_aux, S.n_split, S.knn, S.cap, row_begin - (uint64_t)S.rb0 * TS, n_rows, E.kind, didx,
-                     dd0, dd1, ctx->compute);
+    launch_knn_finalize(dkeys, daux, n_parts, part_stride, 0, n_rows, (uint32_t)knn, kind, didx, dd0, dd1, nullptr, nullptr,
+                        ctx->compute);
     CU(ctx, cudaGetLastError());
-    ctx->launches += 2;
+    ctx->launches++;
     st = timer_end(ctx);
     if (st) return st;
     if (out_loc == SKD_HOST) {
@@ -443,7 +497,73 @@ skd_status run_knn(skd_ctx *ctx, const skd_db *R, const skd_db *Q, bool self, co
         if (d1_out) CU(ctx, cudaMemcpyAsync(d1_out, dd1, n_rows * knn * 4, cudaMemcpyDeviceToHost, ctx->compute));
     }
     CU(ctx, cudaStreamSynchronize(ctx->compute));
-    return timers_collect(ctx);
+    return SKD_OK;
+}
+
+// Symmetric self-kNN: every unordered pair is evaluated once.  Row groups of the upper triangle are computed
+// by the tile kernel into a row-major key matrix in HBM (rect mode) and folded into per-row lists twice by
+// select_kernel: along rows (candidates j for row i) and along columns (candidates i for row j).
+// Lists: dkey[n][knn] (+ daux), device memory, covering ALL n rows; only triangle rows [row_begin, row_end)
+// are evaluated, so ranks that split the triangle produce partial lists to be merged (skd_knn_merge).
+
+skd_status run_knn_symmetric(skd_ctx *ctx, const skd_db *db, const EpiParams &E, uint64_t knn, uint64_t row_begin,
+                             uint64_t row_end, unsigned long long *dkey, float *daux) {
+    const uint64_t n = db->n;
+    const bool with_aux = E.kind == KIND_CORE_ACC;
+    const uint64_t elt = with_aux ? 8 : 4;
+    launch_fill_u64(dkey, n * knn, ~0ull, ctx->compute);
+    ctx->launches++;
+    row_begin = row_begin / TS * TS;  // groups are block aligned; callers pass block-aligned shards
+    for (uint64_t g0 = row_begin; g0 < row_end && g0 + 1 < n;) {
+        const uint64_t C = n - g0;                     // columns g0 .. n-1
+        const uint64_t ld = (C + 3) / 4 * 4;
+        uint64_t R = std::max<uint64_t>(TS, g_sym_chunk_bytes / (ld * elt) / TS * TS);
+        R = std::min<uint64_t>(R, (row_end - g0 + TS - 1) / TS * TS);
+        const uint64_t g1 = std::min<uint64_t>({g0 + R, row_end, n});
+        void *D;
+        skd_status st = scratch_get(ctx, "knn_rect", R * ld * elt, &D);
+        if (st) return st;
+        // tile kernel, rect mode, rows [g0, g1)
+        SchedParams S{};
+        S.mode = MODE_DENSE_SELF;
+        S.one = 1;
+        S.self_mode = 1;
+        S.rb0 = (uint32_t)(g0 / TS);
+        S.n_rb = (uint32_t)((g1 + TS - 1) / TS) - S.rb0;
+        S.group = kGroup;
+        std::vector<uint64_t> off;
+        build_groups(true, S.rb0, S.n_rb, db->dev.nb, &off);
+        S.n_groups = (uint32_t)off.size() - 1;
+        void *doff;
+        st = scratch_get(ctx, "grp_off", off.size() * sizeof(uint64_t), &doff);
+        if (st) return st;
+        CU(ctx, cudaMemcpyAsync(doff, off.data(), off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->compute));
+        CU(ctx, cudaStreamSynchronize(ctx->compute));  // off is a local vector (also fences reuse of grp_off / knn_rect)
+        S.grp_off = (const uint64_t *)doff;
+        S.row_begin = g0;
+        S.row_end = g1;
+        S.out = (float *)D;
+        S.rect_ld = ld;
+        S.rect_c0 = g0;
+        const bool count32 = E.nbins >= 65536;
+        const size_t smem = tile_kernel_smem(E.nk, count32, false, 0, false);
+        if (smem > kMaxSmem)
+            return fail(ctx, SKD_ERR_UNSUPPORTED, "%d k-mer lengths at %u bins need %zu B of shared memory per tile", E.nk,
+                        E.nbins, smem);
+        st = timer_begin(ctx);
+        if (st) return st;
+        CU(ctx, launch_tiles(db->dev, db->dev, E, S, off.back(), count32, smem, ctx->compute));
+        // rows of the group: candidates to their right; columns right of g0: candidates from the group's rows
+        CU(ctx, launch_select(false, with_aux, (const float *)D, ld, g0, (uint32_t)(g1 - g0), g0, n, g0, g1, dkey, daux,
+                              (uint32_t)knn, ctx->compute));
+        CU(ctx, launch_select(true, with_aux, (const float *)D, ld, g0, (uint32_t)(g1 - g0), g0, n, g0, n, dkey, daux,
+                              (uint32_t)knn, ctx->compute));
+        ctx->launches += 3;
+        st = timer_end(ctx);
+        if (st) return st;
+        g0 = g1;
+    }
+    return SKD_OK;
 }
 
 // Shared by skd_db_upload (host or device array) and skd_db_load_skd (file): `fill` stages samples
@@ -612,6 +732,8 @@ skd_status skd_ctx_create(int device, skd_ctx **out) {
         }
     }
     if (const char *e = getenv("SKD_ZEROCOPY")) ctx->zero_copy = atoi(e) != 0;
+    if (const char *e = getenv("SKD_KNN_SYMMETRIC")) ctx->knn_symmetric = atoi(e) != 0;
+    if (const char *e = getenv("SKD_SYM_CHUNK_MB")) g_sym_chunk_bytes = (size_t)std::max(1, atoi(e)) << 20;
     if (const char *e = getenv("SKD_RESULT_CHUNK_MB")) kResultChunkBytes = (size_t)std::max(1, atoi(e)) << 20;
     for (int i = 0; i < 2; ++i) {
         cudaEventCreateWithFlags(&ctx->ev_a[i], cudaEventDisableTiming);
@@ -818,6 +940,24 @@ skd_status skd_self_dists_knn(skd_ctx *ctx, const skd_db *db, uint64_t knn, skd_
     row_end = std::min(row_end, db->n);
     if (row_begin > row_end) row_begin = row_end;
     if (!idx_out || !d0_out) return fail(ctx, SKD_ERR_INVALID, "null output");
+    if (ctx->knn_symmetric && row_begin == 0 && row_end == db->n && knn <= kSymKnnMax) {
+        // whole matrix on one GPU: evaluate each unordered pair once (the reference evaluates both orders)
+        const uint64_t n = db->n;
+        void *lk, *la = nullptr;
+        st = scratch_get(ctx, "sym_key", n * knn * 8, &lk);
+        if (st) return st;
+        if (E.kind == KIND_CORE_ACC) {
+            st = scratch_get(ctx, "sym_aux", n * knn * 4, &la);
+            if (st) return st;
+        }
+        timers_reset(ctx);
+        st = run_knn_symmetric(ctx, db, E, knn, 0, n, (unsigned long long *)lk, (float *)la);
+        if (st) return st;
+        st = finalize_lists(ctx, (const unsigned long long *)lk, (const float *)la, 1, 0, n, knn, E.kind, idx_out, d0_out,
+                            d1_out, out_loc);
+        if (st) return st;
+        return timers_collect(ctx);
+    }
     return run_knn(ctx, db, db, true, E, knn, row_begin, row_end, idx_out, d0_out, d1_out, out_loc);
 }
 
@@ -841,6 +981,107 @@ skd_status skd_cross_dists_knn(skd_ctx *ctx, const skd_db *ref, const skd_db *qu
     if (query_begin > query_end) query_begin = query_end;
     if (!idx_out || !d0_out) return fail(ctx, SKD_ERR_INVALID, "null output");
     return run_knn(ctx, ref, query, false, E, knn, query_begin, query_end, idx_out, d0_out, d1_out, out_loc);
+}
+
+skd_status skd_self_knn_partial(skd_ctx *ctx, const skd_db *db, uint64_t knn, skd_dist_type dist,
+                                const double *completeness, double cutoff, uint64_t row_begin, uint64_t row_end,
+                                uint64_t *keys_out, float *aux_out, skd_loc out_loc) {
+    skd_status st = check_pair(ctx, db, db);
+    if (st) return st;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (db->n < 2 || knn == 0 || knn > db->n - 1)
+        return fail(ctx, SKD_ERR_INVALID, "knn must be in [1, n-1] (n = %llu, knn = %llu)", (unsigned long long)db->n,
+                    (unsigned long long)knn);
+    if (knn > kSymKnnMax)
+        return fail(ctx, SKD_ERR_UNSUPPORTED, "symmetric self kNN supports knn <= %u", kSymKnnMax);
+    if (row_begin % TS != 0) return fail(ctx, SKD_ERR_INVALID, "row_begin must be a multiple of %d", TS);
+    EpiParams E;
+    st = build_epi(ctx, db, db, dist, completeness, completeness, cutoff, &E);
+    if (st) return st;
+    row_end = std::min(row_end, db->n);
+    if (!keys_out) return fail(ctx, SKD_ERR_INVALID, "null output");
+    const uint64_t n = db->n;
+    const bool with_aux = E.kind == KIND_CORE_ACC;
+    unsigned long long *dk = (unsigned long long *)keys_out;
+    float *da = aux_out;
+    if (out_loc == SKD_HOST) {
+        void *p;
+        st = scratch_get(ctx, "sym_key", n * knn * 8, &p);
+        if (st) return st;
+        dk = (unsigned long long *)p;
+        st = scratch_get(ctx, "sym_aux", n * knn * 4, &p);
+        if (st) return st;
+        da = (float *)p;
+    } else if (with_aux && !aux_out) {
+        return fail(ctx, SKD_ERR_INVALID, "aux_out is required for core/accessory");
+    }
+    timers_reset(ctx);
+    st = run_knn_symmetric(ctx, db, E, knn, row_begin, std::max(row_begin, row_end), dk, da);
+    if (st) return st;
+    if (out_loc == SKD_HOST) {
+        CU(ctx, cudaMemcpyAsync(keys_out, dk, n * knn * 8, cudaMemcpyDeviceToHost, ctx->compute));
+        if (aux_out && with_aux) CU(ctx, cudaMemcpyAsync(aux_out, da, n * knn * 4, cudaMemcpyDeviceToHost, ctx->compute));
+    }
+    CU(ctx, cudaStreamSynchronize(ctx->compute));
+    return timers_collect(ctx);
+}
+
+skd_status skd_cross_knn_partial(skd_ctx *ctx, const skd_db *ref_shard, const skd_db *query, uint64_t knn,
+                                 skd_dist_type dist, const double *ref_c, const double *query_c, double cutoff,
+                                 uint64_t ref_index_offset, uint64_t *keys_out, float *aux_out, skd_loc out_loc) {
+    skd_status st = check_pair(ctx, ref_shard, query);
+    if (st) return st;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (query->n == 0) return fail(ctx, SKD_ERR_EMPTY_DB, "Query database has no loaded samples");
+    if (knn == 0) return fail(ctx, SKD_ERR_INVALID, "knn must be at least 1");
+    if (ref_index_offset + ref_shard->n > 0xffffffffull) return fail(ctx, SKD_ERR_UNSUPPORTED, "more than 2^32 references");
+    if (!keys_out) return fail(ctx, SKD_ERR_INVALID, "null output");
+    EpiParams E;
+    st = build_epi(ctx, query, ref_shard, dist, query_c, ref_c, cutoff, &E);
+    if (st) return st;
+    if (E.kind == KIND_CORE_ACC && out_loc == SKD_DEVICE && !aux_out)
+        return fail(ctx, SKD_ERR_INVALID, "aux_out is required for core/accessory");
+    if (ref_shard->n == 0) {  // an empty shard contributes only padding
+        if (out_loc == SKD_HOST) {
+            for (uint64_t i = 0; i < query->n * knn; ++i) keys_out[i] = ~0ull;
+        } else {
+            launch_fill_u64((unsigned long long *)keys_out, query->n * knn, ~0ull, ctx->compute);
+            CU(ctx, cudaStreamSynchronize(ctx->compute));
+        }
+        return SKD_OK;
+    }
+    return run_knn(ctx, ref_shard, query, false, E, knn, 0, query->n, nullptr, nullptr, nullptr, out_loc, keys_out, aux_out,
+                   ref_index_offset);
+}
+
+skd_status skd_knn_merge(skd_ctx *ctx, const uint64_t *keys, const float *aux, uint32_t n_parts, uint64_t n_rows,
+                         uint64_t knn, skd_dist_type dist, skd_loc in_loc, uint64_t *idx_out, float *d0_out, float *d1_out,
+                         skd_loc out_loc) {
+    if (!ctx) return SKD_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (!keys || !idx_out || !d0_out || n_parts == 0 || knn == 0) return fail(ctx, SKD_ERR_INVALID, "bad argument");
+    if (dist.kind == SKD_CORE_ACC && (!aux || !d1_out)) return fail(ctx, SKD_ERR_INVALID, "core/accessory needs aux and d1_out");
+    const size_t total = (size_t)n_parts * n_rows * knn;
+    const unsigned long long *dk = (const unsigned long long *)keys;
+    const float *da = aux;
+    timers_reset(ctx);
+    if (in_loc == SKD_HOST) {
+        void *p;
+        skd_status st = scratch_get(ctx, "merge_key", total * 8, &p);
+        if (st) return st;
+        CU(ctx, cudaMemcpyAsync(p, keys, total * 8, cudaMemcpyHostToDevice, ctx->compute));
+        dk = (const unsigned long long *)p;
+        if (aux) {
+            st = scratch_get(ctx, "merge_aux", total * 4, &p);
+            if (st) return st;
+            CU(ctx, cudaMemcpyAsync(p, aux, total * 4, cudaMemcpyHostToDevice, ctx->compute));
+            da = (const float *)p;
+        }
+    }
+    skd_status st = finalize_lists(ctx, dk, dist.kind == SKD_CORE_ACC ? da : nullptr, n_parts, n_rows * knn, n_rows, knn,
+                                   dist.kind, idx_out, d0_out, d1_out, out_loc);
+    if (st) return st;
+    return timers_collect(ctx);
 }
 
 static skd_status pairs_common(skd_ctx *ctx, const skd_db *ref, const skd_db *query, const EpiParams &E,

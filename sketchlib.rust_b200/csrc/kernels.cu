@@ -9,6 +9,7 @@
 // Arithmetic restated from the reference: src/distances/jaccard.rs (whole file).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdint>
 
 #include "kernels.h"
@@ -423,9 +424,13 @@ __global__ void __launch_bounds__(THREADS, 2)
                 continue;
             }
             uint64_t idx;
+            const bool rect = S.rect_ld != 0;
             if (S.mode == MODE_DENSE_SELF) {
                 if (gj <= gi) continue;
-                idx = nA * gi - ((gi * (gi + 1)) >> 1) + gj - 1 - gi - S.out_base;  // square_to_condensed
+                if (rect)
+                    idx = (gi - S.row_begin) * S.rect_ld + (gj - S.rect_c0);
+                else
+                    idx = nA * gi - ((gi * (gi + 1)) >> 1) + gj - 1 - gi - S.out_base;  // square_to_condensed
             } else {
                 idx = (gi - S.row_begin) * nB + gj;  // ref-major
             }
@@ -435,10 +440,17 @@ __global__ void __launch_bounds__(THREADS, 2)
             d1 = 0.f;
 #else
             if (E.has_c)
-                pair_epilogue<CountT, true>(counts, pair, E, gi, gj, false, d0, d1);
+                pair_epilogue<CountT, true>(counts, pair, E, gi, gj, rect, d0, d1);
             else
-                pair_epilogue<CountT, false>(counts, pair, E, gi, gj, false, d0, d1);
+                pair_epilogue<CountT, false>(counts, pair, E, gi, gj, rect, d0, d1);
 #endif
+            if (rect) {  // read back soon by select_kernel: normal (L2-resident) stores
+                if (E.kind == KIND_CORE_ACC)
+                    reinterpret_cast<float2 *>(S.out)[idx] = make_float2(d0, d1);
+                else
+                    S.out[idx] = d0;
+                continue;
+            }
             // results are written once and never re-read by the GPU: streaming stores keep the database in L2
             if (E.kind == KIND_CORE_ACC)
                 __stcs(reinterpret_cast<float2 *>(S.out) + idx, make_float2(d0, d1));
@@ -508,7 +520,7 @@ __global__ void __launch_bounds__(THREADS, 2)
                 pair_epilogue<CountT, true>(counts, pair, E, gi, gj, true, d0, d1);
             else
                 pair_epilogue<CountT, false>(counts, pair, E, gi, gj, true, d0, d1);
-            unsigned long long comp = ((unsigned long long)float_order_bits(d0) << 32) | (uint32_t)gj;
+            unsigned long long comp = ((unsigned long long)float_order_bits(d0) << 32) | (uint32_t)(gj + S.idx_offset);
             if (comp < thr[row]) {
                 uint32_t slot = atomicAdd(&cand_cnt[row], 1u);
                 cand_key[(size_t)row * cap + slot] = comp;
@@ -580,7 +592,8 @@ __global__ void knn_merge_kernel(const unsigned long long *__restrict__ part_key
                                  uint32_t n_split, uint32_t knn, uint32_t cap, uint64_t first_lrow, uint64_t n_rows,
                                  int kind,
                                  unsigned long long *__restrict__ idx_out, float *__restrict__ d0_out,
-                                 float *__restrict__ d1_out) {
+                                 float *__restrict__ d1_out, unsigned long long *__restrict__ key_out,
+                                 float *__restrict__ aux_out) {
     const uint64_t row = (uint64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
     const int lane = threadIdx.x & 31;
     if (row >= n_rows) return;
@@ -606,21 +619,225 @@ __global__ void knn_merge_kernel(const unsigned long long *__restrict__ part_key
             rank += lo;
         }
         if (rank < knn) {
-            float key = float_from_order_bits((uint32_t)(v >> 32));
-            idx_out[row * knn + rank] = (unsigned long long)(uint32_t)v;
-            d0_out[row * knn + rank] = kind == KIND_ANI ? 1.0f - key : key;
-            if (d1_out) d1_out[row * knn + rank] = part_aux ? part_aux[src] : 0.0f;
+            if (key_out) {  // partial result for a later cross-rank merge: keep the composite
+                key_out[row * knn + rank] = v;
+                if (aux_out) aux_out[row * knn + rank] = part_aux ? part_aux[src] : 0.0f;
+            } else {
+                float key = float_from_order_bits((uint32_t)(v >> 32));
+                idx_out[row * knn + rank] = (unsigned long long)(uint32_t)v;
+                d0_out[row * knn + rank] = kind == KIND_ANI ? 1.0f - key : key;
+                if (d1_out) d1_out[row * knn + rank] = part_aux ? part_aux[src] : 0.0f;
+            }
         }
     }
 }
 
 void launch_knn_merge(const unsigned long long *part_key, const float *part_aux, uint32_t n_split, uint32_t knn,
                       uint32_t cap, uint64_t first_lrow, uint64_t n_rows, int kind, unsigned long long *idx_out, float *d0_out,
-                      float *d1_out, cudaStream_t st) {
+                      float *d1_out, unsigned long long *key_out, float *aux_out, cudaStream_t st) {
     if (n_rows == 0) return;
     const int warps = 8;
     knn_merge_kernel<<<(unsigned)((n_rows + warps - 1) / warps), warps * 32, 0, st>>>(
-        part_key, part_aux, n_split, knn, cap, first_lrow, n_rows, kind, idx_out, d0_out, d1_out);
+        part_key, part_aux, n_split, knn, cap, first_lrow, n_rows, kind, idx_out, d0_out, d1_out, key_out, aux_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Symmetric self-kNN, second stage.  The tile kernel (rect mode) has written the kNN keys of the pairs
+// (i, j > i) of a row group as a row-major matrix D in HBM; every such value is a candidate for row i
+// (read along rows) and for row j (read along columns), so each unordered pair is computed once.
+// One CTA owns 64 targets (rows or columns of D), streams 64x64 sub-tiles of D through shared memory and
+// keeps, per target, the running list L[target][knn] (sorted composites) topped up through a 128-slot
+// buffer with threshold rejection, exactly like the tile kernel's kNN epilogue.
+template <bool COLS, bool AUX>
+__global__ void __launch_bounds__(256) select_kernel(const float *__restrict__ D, uint64_t ld, uint64_t g0, uint32_t R,
+                                                     uint64_t c0, uint64_t n, uint64_t t0, uint64_t t1,
+                                                     unsigned long long *__restrict__ Lkey, float *__restrict__ Laux,
+                                                     uint32_t knn) {
+    constexpr int CAP = 128;
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    unsigned long long *buf = reinterpret_cast<unsigned long long *>(sm_raw);           // [64][CAP]
+    float *baux = reinterpret_cast<float *>(buf + TS * CAP);                              // [64][CAP]
+    float *tkey = baux + (AUX ? TS * CAP : 0);                                            // [64][65]
+    float *taux = tkey + TS * (TS + 1);                                                   // [64][65]
+    unsigned long long *thr = reinterpret_cast<unsigned long long *>(taux + (AUX ? TS * (TS + 1) : 0));
+    uint32_t *cnt = reinterpret_cast<uint32_t *>(thr + TS);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint64_t tbase = t0 + (uint64_t)blockIdx.x * TS;  // first target (global sample index) of this CTA
+
+    // start from the lists accumulated so far
+    for (int e = tid; e < TS * CAP; e += 256) {
+        const int t = e / CAP, s = e % CAP;
+        const uint64_t tg = tbase + t;
+        unsigned long long v = ~0ull;
+        float a = 0.f;
+        if (tg < t1 && s < (int)knn) {
+            v = Lkey[tg * knn + s];
+            if (AUX) a = Laux[tg * knn + s];
+        }
+        buf[e] = v;
+        if (AUX) baux[e] = a;
+    }
+    __syncthreads();
+    for (int t = tid; t < TS; t += 256) {
+        uint32_t c = 0;
+        while (c < knn && buf[t * CAP + c] != ~0ull) ++c;  // lists are sorted: padding is at the end
+        cnt[t] = c;
+        thr[t] = c == knn ? buf[t * CAP + knn - 1] : ~0ull;
+    }
+    __syncthreads();
+
+    // candidate range along the streamed dimension
+    // ROWS: targets are rows i in [tbase, +64), candidates are columns j in (i, n)
+    // COLS: targets are columns j, candidates are rows i in [g0, min(j, g0 + R))
+    const uint64_t s_begin = COLS ? g0 : (tbase + 1 > c0 ? tbase + 1 : c0);
+    const uint64_t s_end = COLS ? (g0 + R < tbase + TS ? g0 + R : tbase + TS) : n;
+    for (uint64_t sb = s_begin / TS * TS; sb < s_end; sb += TS) {
+        // load D sub-tile: ROWS: rows = targets, cols = sb..sb+63 ; COLS: rows = sb.., cols = targets
+        for (int e = tid; e < TS * TS; e += 256) {
+            const int r = e / TS, c = e % TS;
+            const uint64_t gi = COLS ? sb + r : tbase + r, gj = COLS ? tbase + c : sb + c;
+            float k = 0.f, a = 0.f;
+            if (gi >= g0 && gi < g0 + R && gj < n && gj > gi && gj >= c0) {
+                const uint64_t off = (gi - g0) * ld + (gj - c0);
+                if (AUX) {
+                    float2 v = __ldcs(reinterpret_cast<const float2 *>(D) + off);
+                    k = v.x;
+                    a = v.y;
+                } else {
+                    k = __ldcs(D + off);
+                }
+            }
+            tkey[r * (TS + 1) + c] = k;
+            if (AUX) taux[r * (TS + 1) + c] = a;
+        }
+        __syncthreads();
+        for (int t = warp; t < TS; t += 8) {
+            const uint64_t tg = tbase + t;
+            if (tg >= t1) continue;
+            const unsigned long long th = thr[t];
+            uint32_t c = cnt[t];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int s = lane + 32 * h;
+                const uint64_t cand = sb + s;  // global index of the candidate sample
+                const uint64_t gi = COLS ? cand : tg, gj = COLS ? tg : cand;
+                bool ok = gi >= g0 && gi < g0 + R && gj < n && gj > gi && gj >= c0;
+                const int r = COLS ? s : t, cc = COLS ? t : s;
+                unsigned long long comp = 0;
+                if (ok) {
+                    comp = ((unsigned long long)float_order_bits(tkey[r * (TS + 1) + cc]) << 32) | (uint32_t)cand;
+                    ok = comp < th;
+                }
+                const unsigned m = __ballot_sync(0xffffffffu, ok);
+                if (ok) {
+                    const uint32_t slot = c + __popc(m & ((1u << lane) - 1u));
+                    buf[t * CAP + slot] = comp;
+                    if (AUX) baux[t * CAP + slot] = taux[r * (TS + 1) + cc];
+                }
+                c += __popc(m);
+            }
+            __syncwarp();
+            if (c + TS > CAP) {
+                warp_bitonic_sort(buf + t * CAP, AUX ? baux + t * CAP : nullptr, CAP, lane);
+                for (int e = knn + lane; e < CAP; e += 32) buf[t * CAP + e] = ~0ull;
+                __syncwarp();
+                c = knn;
+                if (lane == 0) thr[t] = buf[t * CAP + knn - 1];
+            }
+            if (lane == 0) cnt[t] = c;
+        }
+        __syncthreads();
+    }
+    for (int t = warp; t < TS; t += 8) {
+        const uint64_t tg = tbase + t;
+        if (tg >= t1) continue;
+        warp_bitonic_sort(buf + t * CAP, AUX ? baux + t * CAP : nullptr, CAP, lane);
+        for (uint32_t e = lane; e < knn; e += 32) {
+            Lkey[tg * knn + e] = buf[t * CAP + e];
+            if (AUX) Laux[tg * knn + e] = baux[t * CAP + e];
+        }
+    }
+}
+
+cudaError_t launch_select(bool cols, bool aux, const float *D, uint64_t ld, uint64_t g0, uint32_t R, uint64_t c0,
+                          uint64_t n, uint64_t t0, uint64_t t1, unsigned long long *Lkey, float *Laux, uint32_t knn,
+                          cudaStream_t st) {
+    if (t1 <= t0) return cudaSuccess;
+    const unsigned grid = (unsigned)((t1 - t0 + TS - 1) / TS);
+    size_t smem = (size_t)TS * 128 * 8 + (aux ? (size_t)TS * 128 * 4 : 0) + (size_t)TS * (TS + 1) * 4 * (aux ? 2 : 1) +
+                  TS * 8 + TS * 4;
+    cudaError_t err;
+#define SKD_SEL(C, A)                                                                                            \
+    do {                                                                                                         \
+        err = cudaFuncSetAttribute(select_kernel<C, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (err != cudaSuccess) return err;                                                                      \
+        select_kernel<C, A><<<grid, 256, smem, st>>>(D, ld, g0, R, c0, n, t0, t1, Lkey, Laux, knn);               \
+    } while (0)
+    if (cols && aux) SKD_SEL(true, true);
+    else if (cols) SKD_SEL(true, false);
+    else if (aux) SKD_SEL(false, true);
+    else SKD_SEL(false, false);
+#undef SKD_SEL
+    return cudaGetLastError();
+}
+
+// Merges n_parts sorted partial lists per row (keys[part][row][knn], ~0 padded) and either writes the final
+// sparse rows (idx, d0, d1; ANI un-transformed as 1.0f - key like the reference, mod.rs:183-189) or, when
+// key_out is given, one merged composite list per row.
+__global__ void knn_finalize_kernel(const unsigned long long *__restrict__ keys, const float *__restrict__ aux,
+                                    uint32_t n_parts, uint64_t part_stride, uint64_t row0, uint64_t n_rows, uint32_t knn,
+                                    int kind, unsigned long long *__restrict__ idx_out, float *__restrict__ d0_out,
+                                    float *__restrict__ d1_out, unsigned long long *__restrict__ key_out,
+                                    float *__restrict__ aux_out) {
+    const uint64_t row = (uint64_t)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32;
+    const int lane = threadIdx.x & 31;
+    if (row >= n_rows) return;
+    const uint32_t total = n_parts * knn;
+    for (uint32_t e = lane; e < total; e += 32) {
+        const uint64_t src = (uint64_t)(e / knn) * part_stride + (row0 + row) * knn + e % knn;
+        const unsigned long long v = keys[src];
+        uint32_t rank = 0;
+        if (v != ~0ull) {
+            for (uint32_t s = 0; s < n_parts; ++s) {
+                const unsigned long long *l = keys + (uint64_t)s * part_stride + (row0 + row) * knn;
+                uint32_t lo = 0, hi = knn;
+                while (lo < hi) {
+                    uint32_t mid = (lo + hi) >> 1;
+                    if (l[mid] < v) lo = mid + 1; else hi = mid;
+                }
+                rank += lo;
+            }
+        } else {
+            rank = knn;  // padding never ranks
+        }
+        if (rank < knn) {
+            if (key_out) {
+                key_out[row * knn + rank] = v;
+                if (aux_out) aux_out[row * knn + rank] = aux ? aux[src] : 0.0f;
+            } else {
+                const float key = float_from_order_bits((uint32_t)(v >> 32));
+                idx_out[row * knn + rank] = (unsigned long long)(uint32_t)v;
+                d0_out[row * knn + rank] = kind == KIND_ANI ? 1.0f - key : key;
+                if (d1_out) d1_out[row * knn + rank] = aux ? aux[src] : 0.0f;
+            }
+        }
+    }
+}
+
+void launch_knn_finalize(const unsigned long long *keys, const float *aux, uint32_t n_parts, uint64_t part_stride,
+                         uint64_t row0, uint64_t n_rows, uint32_t knn, int kind, unsigned long long *idx_out,
+                         float *d0_out, float *d1_out, unsigned long long *key_out, float *aux_out, cudaStream_t st) {
+    if (n_rows == 0) return;
+    const int warps = 8;
+    knn_finalize_kernel<<<(unsigned)((n_rows + warps - 1) / warps), warps * 32, 0, st>>>(
+        keys, aux, n_parts, part_stride, row0, n_rows, knn, kind, idx_out, d0_out, d1_out, key_out, aux_out);
+}
+
+__global__ void fill_u64_kernel(unsigned long long *p, uint64_t n, unsigned long long v) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+void launch_fill_u64(unsigned long long *p, uint64_t n, unsigned long long v, cudaStream_t st) {
+    if (n) fill_u64_kernel<<<(unsigned)std::min<uint64_t>(4096, (n + 255) / 256), 256, 0, st>>>(p, n, v);
 }
 
 // ------------------------------------------------------------------------------------------------

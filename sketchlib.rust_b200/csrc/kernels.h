@@ -20,7 +20,17 @@ cudaError_t launch_tiles(const DevDb &A, const DevDb &B, const EpiParams &E, con
 
 void launch_knn_merge(const unsigned long long *part_key, const float *part_aux, uint32_t n_split, uint32_t knn,
                       uint32_t cap, uint64_t first_lrow, uint64_t n_rows, int kind, unsigned long long *idx_out, float *d0_out,
-                      float *d1_out, cudaStream_t st);
+                      float *d1_out, unsigned long long *key_out, float *aux_out, cudaStream_t st);
+
+cudaError_t launch_select(bool cols, bool aux, const float *D, uint64_t ld, uint64_t g0, uint32_t R, uint64_t c0,
+                          uint64_t n, uint64_t t0, uint64_t t1, unsigned long long *Lkey, float *Laux, uint32_t knn,
+                          cudaStream_t st);
+
+void launch_knn_finalize(const unsigned long long *keys, const float *aux, uint32_t n_parts, uint64_t part_stride,
+                         uint64_t row0, uint64_t n_rows, uint32_t knn, int kind, unsigned long long *idx_out,
+                         float *d0_out, float *d1_out, unsigned long long *key_out, float *aux_out, cudaStream_t st);
+
+void launch_fill_u64(unsigned long long *p, uint64_t n, unsigned long long v, cudaStream_t st);
 
 void launch_pairs(const DevDb &A, const DevDb &B, const EpiParams &E, const uint64_t *pairs, uint64_t n_pairs,
                   uint32_t *counts_out, float *dist_out, cudaStream_t st);

@@ -73,6 +73,9 @@ struct SchedParams {
     const uint64_t *grp_off; // [n_groups + 1] first linear tile of each group
     uint64_t row_begin, row_end; // sample-level row range (clips the first/last block)
     uint64_t out_base;    // dense self: condensed index of (row_begin, row_begin+1)
+    uint64_t rect_ld;     // dense self, if non-zero: write kNN keys row-major at [(i - row_begin) * rect_ld + (j - rect_c0)]
+    uint64_t rect_c0;     //   (only j > i is written): the symmetric self-kNN path reads them back by row and by column
+    uint64_t idx_offset;  // kNN: added to the neighbour index stored in the composite (column shards of a bigger database)
     float *out;           // dense: distances; counts mode: reinterpret as uint32_t*
     uint32_t one;         // always 1: a multiplier the compiler cannot fold, see tile_counts
     uint32_t pad0_;

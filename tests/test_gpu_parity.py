@@ -386,3 +386,76 @@ def test_scale_properties(sk, ctx):
     full[iu] = d[:, 0]
     full.T[iu] = d[:, 0]
     assert np.array_equal(np.sort(full, axis=1)[:, :50], knn.d0)
+
+
+# ------------------------------------------------------------------ symmetric self kNN, partial lists, merges
+def fresh_ctx(sk, **env):
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update({k: str(v) for k, v in env.items()})
+    try:
+        return sk.Context(0)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+@pytest.mark.parametrize("kind", ["ca", "jaccard", "ani"])
+def test_symmetric_knn_equals_row_owned_knn(sk, ctx, kind):
+    db = synth_db(700, 16, [15, 19, 23, 27], seed=70, n_families=9, unrelated_frac=0.05)
+    plain = fresh_ctx(sk, SKD_KNN_SYMMETRIC=0)
+    tiny = fresh_ctx(sk, SKD_SYM_CHUNK_MB=1)  # many row groups: exercises the list carry-over between groups
+    try:
+        outs = []
+        for c in (ctx, plain, tiny):
+            g = up(sk, c, db)
+            dt = sk.set_k(g) if kind == "ca" else sk.set_k(g, 23, ani=(kind == "ani"))
+            outs.append(sk.self_dists_knn(g, knn=20, dist_type=dt))
+        for o in outs[1:]:  # same deterministic tie-break (neighbour index): identical, not just equivalent
+            assert np.array_equal(o.idx, outs[0].idx) and np.array_equal(o.d0, outs[0].d0)
+            if kind == "ca":
+                assert np.array_equal(o.d1, outs[0].d1)
+        oidx, od0, od1 = oracle.self_dists_knn(db, 20, k_idx=-1 if kind == "ca" else 2, ani=(kind == "ani"), threads=8)
+        assert_knn_matches(outs[0].idx, outs[0].d0, outs[0].d1, oidx, od0, od1, kind != "ca")
+    finally:
+        os.environ.pop("SKD_SYM_CHUNK_MB", None)
+        fresh_ctx(sk, SKD_SYM_CHUNK_MB=2048).close()  # restore the library-wide chunk size
+        plain.close()
+        tiny.close()
+
+
+def test_self_knn_partials_merge_like_ranks(sk, ctx):
+    db = synth_db(650, 16, [17, 21, 25, 29], seed=71, n_families=7)
+    g = up(sk, ctx, db)
+    for dt in (sk.set_k(g), sk.set_k(g, 21)):
+        whole = sk.self_dists_knn(g, knn=30, dist_type=dt)
+        for world in (2, 3):
+            shards = [sk.triangle_row_partition(650, r, world) for r in range(world)]
+            parts = [sk.self_knn_partial(g, knn=30, dist_type=dt, rows=s) for s in shards]
+            merged = sk.knn_merge(ctx, [p[0] for p in parts], [p[1] for p in parts], dt, db.names)
+            assert np.array_equal(merged.idx, whole.idx) and np.array_equal(merged.d0, whole.d0)
+            if dt.kind == sk.CORE_ACC:
+                assert np.array_equal(merged.d1, whole.d1)
+    with pytest.raises(sk.SketchDistError, match="knn <= 64"):
+        sk.self_knn_partial(g, knn=65, dist_type=sk.set_k(g, 21))
+
+
+def test_cross_knn_ref_shards_merge(sk, ctx):
+    ref = synth_db(500, 16, [17, 21, 25, 29], seed=72, n_families=6)
+    qry = synth_db(130, 16, [17, 21, 25, 29], seed=72, n_families=6)
+    gq = up(sk, ctx, qry)
+    whole_ref = up(sk, ctx, ref)
+    bounds = [0, 100, 101, 320, 500]  # ragged shards, one with a single reference
+    for kidx in (-1, 1):
+        dt = sk.set_k(whole_ref) if kidx < 0 else sk.set_k(whole_ref, 21)
+        want = sk.cross_dists_knn(whole_ref, gq, knn=12, dist_type=dt)
+        parts = []
+        for a, b in zip(bounds, bounds[1:]):
+            shard = oracle.Db(ref.bins[a * ref.sample_stride:b * ref.sample_stride], b - a, ref.kmers, ref.W)
+            parts.append(sk.cross_knn_partial(up(sk, ctx, shard), gq, knn=12, dist_type=dt, ref_index_offset=a))
+        merged = sk.knn_merge(ctx, [p[0] for p in parts], [p[1] for p in parts], dt, ref.names, qry.names)
+        assert np.array_equal(merged.idx, want.idx) and np.array_equal(merged.d0, want.d0)
+        if kidx < 0:
+            assert np.array_equal(merged.d1, want.d1)
