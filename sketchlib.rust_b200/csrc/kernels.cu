@@ -79,14 +79,23 @@ __global__ void __launch_bounds__(256) repack_kernel(const uint64_t *__restrict_
         sh[s][p] = v;
     }
     __syncthreads();
-    uint2 *dst = reinterpret_cast<uint2 *>(tiled + slab_index(db, k, w, b) * STAGE_U32);
-    for (int e = threadIdx.x; e < 2 * PP * TS; e += blockDim.x) {
-        int half = e / (PP * TS), pp = (e / TS) % PP, s = e % TS;
-        uint64_t lo = sh[s][2 * pp], hi = sh[s][2 * pp + 1];
-        uint2 v;
-        v.x = (uint32_t)(lo >> (32 * half));
-        v.y = (uint32_t)(hi >> (32 * half));
-        dst[e] = v;
+    uint32_t *dst = tiled + slab_index(db, k, w, b) * STAGE_U32;
+    for (int v = threadIdx.x; v < 2 * 4 * TS; v += blockDim.x) {
+        const int half = v / (4 * TS), r = v % (4 * TS), q = r / TS, s = r % TS;
+        const int shift = 32 * half;
+        if (q < 3) {
+            uint4 o;
+            o.x = (uint32_t)(sh[s][4 * q + 0] >> shift);
+            o.y = (uint32_t)(sh[s][4 * q + 1] >> shift);
+            o.z = (uint32_t)(sh[s][4 * q + 2] >> shift);
+            o.w = (uint32_t)(sh[s][4 * q + 3] >> shift);
+            *reinterpret_cast<uint4 *>(dst + half * HALF_U32 + q * QUAD_U32 + s * 4) = o;
+        } else {
+            uint2 o;
+            o.x = (uint32_t)(sh[s][12] >> shift);
+            o.y = (uint32_t)(sh[s][13] >> shift);
+            *reinterpret_cast<uint2 *>(dst + half * HALF_U32 + TAIL_U32 + s * 2) = o;
+        }
     }
 }
 
@@ -224,39 +233,47 @@ __device__ __forceinline__ void tile_counts(const DevDb &A, const DevDb &B, uint
         if (tid == 0 && it + NST - 1 < n_it) issue(it + NST - 1);
         const uint32_t g = git + it;
         if (!ready) mbar_wait(&full_bar[g % NST], (g / NST) & 1u);
-        const uint2 *sa = reinterpret_cast<const uint2 *>(stage_mem + (g % NST) * (2 * STAGE_U32));
-        const uint2 *sb = sa + STAGE_U32 / 2;
+        const uint32_t *sa = stage_mem + (g % NST) * (2 * STAGE_U32);
+        const uint32_t *sb = sa + STAGE_U32;
 
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
             uint32_t d[4][4];
+            const uint4 *a4 = reinterpret_cast<const uint4 *>(sa + half * HALF_U32);
+            const uint4 *b4 = reinterpret_cast<const uint4 *>(sb + half * HALF_U32);
 #pragma unroll
-            for (int pp = 0; pp < PP; ++pp) {
-                uint2 av[4], bv[4];
-#ifdef SKD_ABLATE_LDS
-                if (pp == 0) {
+            for (int q = 0; q < 3; ++q) {  // planes 4q .. 4q+3: one LDS.128 per sample
+                uint4 av[4], bv[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) av[i] = sa[(half * PP + pp) * TS + arow0 + 4 * i];
+                for (int i = 0; i < 4; ++i) av[i] = a4[q * TS + arow0 + 4 * i];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) bv[j] = sb[(half * PP + pp) * TS + bcol0 + 8 * j];
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) { av[i].x = av[i].x * 3 + pp; av[i].y += one; }
-                }
-#else
-#pragma unroll
-                for (int i = 0; i < 4; ++i) av[i] = sa[(half * PP + pp) * TS + arow0 + 4 * i];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) bv[j] = sb[(half * PP + pp) * TS + bcol0 + 8 * j];
-#endif
+                for (int j = 0; j < 4; ++j) bv[j] = b4[q * TS + bcol0 + 8 * j];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        if (pp == 0)
+                        if (q == 0)
                             d[i][j] = av[i].x ^ bv[j].x;
                         else
                             d[i][j] |= av[i].x ^ bv[j].x;
+                        d[i][j] |= av[i].y ^ bv[j].y;
+                        d[i][j] |= av[i].z ^ bv[j].z;
+                        d[i][j] |= av[i].w ^ bv[j].w;
+                    }
+            }
+            {  // planes 12, 13: one LDS.64 per sample
+                const uint2 *a2 = reinterpret_cast<const uint2 *>(sa + half * HALF_U32 + TAIL_U32);
+                const uint2 *b2 = reinterpret_cast<const uint2 *>(sb + half * HALF_U32 + TAIL_U32);
+                uint2 av[4], bv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) av[i] = a2[arow0 + 4 * i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bv[j] = b2[bcol0 + 8 * j];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        d[i][j] |= av[i].x ^ bv[j].x;
                         d[i][j] |= av[i].y ^ bv[j].y;
                     }
             }
@@ -865,14 +882,18 @@ __global__ void pair_kernel(const __grid_constant__ DevDb A, const __grid_consta
     for (int k = k_lo; k < k_hi; ++k) {
         uint32_t mism = 0;
         for (uint32_t wc = lane; wc < 2 * A.W; wc += 32) {
-            const uint2 *pa = reinterpret_cast<const uint2 *>(A.tiled + slab_index(A, k, wc >> 1, ba) * STAGE_U32 +
-                                                               (wc & 1) * HALF_U32);
-            const uint2 *pb = reinterpret_cast<const uint2 *>(B.tiled + slab_index(B, k, wc >> 1, bb) * STAGE_U32 +
-                                                               (wc & 1) * HALF_U32);
+            const uint32_t *pa = A.tiled + slab_index(A, k, wc >> 1, ba) * STAGE_U32 + (wc & 1) * HALF_U32;
+            const uint32_t *pb = B.tiled + slab_index(B, k, wc >> 1, bb) * STAGE_U32 + (wc & 1) * HALF_U32;
             uint32_t d = 0;
 #pragma unroll
-            for (int pp = 0; pp < PP; ++pp) {
-                uint2 a = pa[pp * TS + sa], b = pb[pp * TS + sb];
+            for (int q = 0; q < 3; ++q) {
+                const uint4 a = reinterpret_cast<const uint4 *>(pa + q * QUAD_U32)[sa];
+                const uint4 b = reinterpret_cast<const uint4 *>(pb + q * QUAD_U32)[sb];
+                d |= (a.x ^ b.x) | (a.y ^ b.y) | (a.z ^ b.z) | (a.w ^ b.w);
+            }
+            {
+                const uint2 a = reinterpret_cast<const uint2 *>(pa + TAIL_U32)[sa];
+                const uint2 b = reinterpret_cast<const uint2 *>(pb + TAIL_U32)[sb];
                 d |= (a.x ^ b.x) | (a.y ^ b.y);
             }
             mism += __popc(d);

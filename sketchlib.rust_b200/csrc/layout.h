@@ -5,7 +5,7 @@
 namespace skd {
 
 constexpr int BBITS = 14;                  // bit planes per bin (reference src/sketch/mod.rs:34)
-constexpr int PP = BBITS / 2;              // plane pairs (one 64-bit shared-memory load each)
+constexpr int PP = BBITS / 2;              // plane pairs
 constexpr int TS = 64;                     // samples per block = tile edge
 constexpr int HALF_U32 = PP * TS * 2;      // u32 per (32-bin word column, sample block) = 896 (3584 B)
 constexpr int STAGE_U32 = 2 * HALF_U32;    // u32 per (64-bin word, sample block): one pipeline stage operand
@@ -14,12 +14,16 @@ constexpr int NST = 3;                     // pipeline stages
 constexpr int THREADS = 256;               // 8 warps, warp tile 16x32, thread tile 4x4
 constexpr int MAXK = 32;                   // k-mer lengths supported by the fused core/accessory epilogue
 
-// Tiled layout ("k-major, 64-bin-word, sample-block"):
-//   u32 index = (((k * W + w) * nb + b) * 2 + half) * HALF_U32 + (pp * TS + s) * 2 + h
-// holds bits [32*half, 32*half+32) of bit plane 2*pp+h of 64-bin word w of sample b*TS+s at k-mer k.
-// One (k, w, b) slab is a contiguous 7168 B: exactly what one bulk (TMA) copy moves into shared memory,
-// and inside it the 64 samples of a plane pair are adjacent 8-byte items, so a warp's 64-bit
-// shared-memory loads are conflict free.  Samples past n in the last block are zero.
+// Tiled layout ("k-major, 64-bin-word, sample-block"): one (k, w, b) slab = 64 samples x 14 planes x 64 bins =
+// STAGE_U32 u32 = 7168 contiguous bytes, exactly what one bulk (TMA) copy moves into shared memory.  Inside a
+// slab, for each 32-bin half h (HALF_U32 u32 each):
+//   planes 4q..4q+3 (q = 0, 1, 2):  u32 [h*896 + q*256 + s*4 + (p - 4q)]     one 16-byte item per sample
+//   planes 12, 13:                  u32 [h*896 + 768   + s*2 + (p - 12)]      one  8-byte item per sample
+// so a thread fetches the 14 planes of a sample with three LDS.128 and one LDS.64, and the 64 samples of a
+// plane group are adjacent items: a warp's operand loads are conflict free (row operands broadcast).
+// Slab order in HBM: index ((k * W + w) * nb + b).  Samples past n in the last block are zero.
+constexpr int QUAD_U32 = TS * 4;           // u32 per plane quad of one half (256)
+constexpr int TAIL_U32 = 3 * QUAD_U32;     // offset of the plane 12/13 pair inside a half (768)
 struct DevDb {
     const uint32_t *tiled;
     uint64_t n;   // samples
