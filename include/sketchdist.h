@@ -172,6 +172,18 @@ skd_status skd_knn_merge(skd_ctx *ctx, const uint64_t *keys, const float *aux, u
                          uint64_t knn, skd_dist_type dist, skd_loc in_loc, uint64_t *idx_out, float *d0_out,
                          float *d1_out, skd_loc out_loc);
 
+/* The distance half of self_dists_knn_precluster (src/distances/mod.rs:399-553): per row i the candidates
+ * cand_idx[cand_offsets[i] .. cand_offsets[i+1]) (.skd sample indices; what Inverted::any_shared_bins returned,
+ * src/inverted.rs:259-268; the row itself may be listed and is skipped) are compared with row i and the knn
+ * nearest kept, ascending; short rows are padded with (i, 1.0) (:537-544).  retain_unmatched: 0 = none,
+ * 1 = singleton (a row without any neighbour becomes (i, 0.0), (i, 1.0), ...; :491-499), 2 = brute force (the
+ * caller lists all samples for such rows).  Single-k distance types only (the reference's CoreAcc arm is
+ * unimplemented!, :548-550).  All buffers are host memory; outputs are n x knn. */
+skd_status skd_self_dists_knn_candidates(skd_ctx *ctx, const skd_db *db, uint64_t knn, skd_dist_type dist,
+                                         const double *completeness, double completeness_cutoff,
+                                         const uint64_t *cand_offsets, const uint64_t *cand_idx, int retain_unmatched,
+                                         uint64_t *idx_out, float *d0_out);
+
 /* Distances for an explicit list of (ref_idx, query_idx) pairs (the per-pair calls inside
  * self_dists_knn_precluster, src/distances/mod.rs:399-553).  out: 1 or 2 floats per pair. */
 skd_status skd_pair_dists(skd_ctx *ctx, const skd_db *ref, const skd_db *query, skd_dist_type dist,

@@ -220,3 +220,38 @@ def fill_usigs(bins16) -> np.ndarray:
 def fmt_f32(x) -> str:
     """Rust `{}` for f32: shortest round-trip digits, positional, `1.0` -> `1`."""
     return np.format_float_positional(np.float32(x), unique=True, trim="-")
+
+
+# ---------------------------------------------------------------- precluster (candidate-list kNN)
+def any_shared_bins_csr(skq_bins, ski_to_skd=None):
+    """skq_bins: uint16 [n_ski, stride] (untransposed bins, .skq layout, src/inverted.rs:92-100).  For each
+    sample (in .skd order) the ascending-.ski-index list of samples sharing at least one (position, value) bin
+    with it -- what Inverted::any_shared_bins returns (src/inverted.rs:259-268) -- mapped to .skd indices.
+    Pure-Python/numpy, O(n^2 * stride / 8): test sizes only."""
+    skq = np.ascontiguousarray(skq_bins, dtype=np.uint16)
+    n = skq.shape[0]
+    ski_to_skd = np.arange(n) if ski_to_skd is None else np.asarray(ski_to_skd)
+    skd_to_ski = np.empty(n, dtype=np.int64)
+    skd_to_ski[ski_to_skd] = np.arange(n)
+    off, idx = [0], []
+    for skd_i in range(n):
+        row = skq[skd_to_ski[skd_i]]
+        hits = np.nonzero((skq == row[None, :]).any(axis=1))[0]  # ascending ski index, includes itself
+        idx.extend(int(ski_to_skd[h]) for h in hits)
+        off.append(len(idx))
+    return np.array(off, dtype=np.uint64), np.array(idx, dtype=np.uint64)
+
+
+def self_dists_knn_precluster(db: Db, cand_off, cand_idx, knn, k_idx, ani=False, completeness=None, cutoff=0.64,
+                              retain=0):
+    cand_off = np.ascontiguousarray(cand_off, dtype=np.uint64)
+    cand_idx = np.ascontiguousarray(cand_idx, dtype=np.uint64)
+    idx = np.zeros((db.n, knn), dtype=np.uint64)
+    d0 = np.zeros((db.n, knn), dtype=np.float32)
+    cv = _c_or_none(completeness)
+    rc = lib().oracle_self_dists_knn_precluster(C.byref(db.c), _p(cand_off), _p(cand_idx), C.c_uint64(knn),
+                                                C.c_int64(k_idx), C.c_int(ani), _p(cv), C.c_double(cutoff),
+                                                C.c_int(retain), _p(idx), _p(d0))
+    if rc != 0:
+        raise RuntimeError("Prefilter only available for single k-mer distances")
+    return idx, d0

@@ -460,3 +460,59 @@ void oracle_match_counts(const oracle_db *ref, const oracle_db *query, const uin
             counts[p * ref->n_k + k] =
                 oracle_samebits(slice(ref, pairs[2 * p], k), slice(query, pairs[2 * p + 1], k), ref->sketchsize64);
 }
+
+/* self_dists_knn_precluster: src/distances/mod.rs:399-553 (single-k modes only; CoreAcc is unimplemented!
+ * there, :548-550).  The inverted index is represented by its effect on this function: for row i the
+ * candidates cand_idx[cand_off[i] .. cand_off[i+1]) are the samples `any_shared_bins` returns
+ * (src/inverted.rs:259-268), already mapped to .skd indices and in the reference's iteration order (ascending
+ * .ski index); the row itself may be listed and is skipped (:459-461).
+ * retain: 0 = None, 1 = Singleton, 2 = Bruteforce (src/cli.rs RetainUnmatched; mod.rs:489-527). */
+int oracle_self_dists_knn_precluster(const oracle_db *db, const uint64_t *cand_off, const uint64_t *cand_idx,
+                                     uint64_t knn, int64_t k_idx, int ani, const double *completeness, double cutoff,
+                                     int retain, uint64_t *idx_out, float *d0_out) {
+    if (k_idx < 0) return -4;
+    uint64_t n = db->n_samples;
+    double kf = (double)db->kmers[k_idx];
+    hitem *heap = (hitem *)malloc(sizeof(hitem) * (knn + 1));
+    for (uint64_t i = 0; i < n; ++i) {
+        size_t len = 0;
+        const uint64_t *i_sketch = slice(db, i, (uint64_t)k_idx);
+        for (int pass = 0; pass < 2; ++pass) {
+            if (pass == 1 && !(len == 0 && retain == 2)) break; /* bruteforce only when nothing matched */
+            uint64_t lo = pass == 0 ? cand_off[i] : 0, hi = pass == 0 ? cand_off[i + 1] : n;
+            for (uint64_t c = lo; c < hi; ++c) {
+                uint64_t j = pass == 0 ? cand_idx[c] : c;
+                if (j == i) continue;
+                int has_c = completeness != NULL;
+                double jac = oracle_jaccard_index(i_sketch, slice(db, j, (uint64_t)k_idx), db->sketchsize64, has_c,
+                                                  has_c ? completeness[i] : 0.0, has_c ? completeness[j] : 0.0, cutoff);
+                hitem it;
+                it.idx = j;
+                it.aux = 0.0f;
+                it.key = ani ? (float)(1.0 - oracle_ani_pois(jac, kf)) : (float)(1.0 - jac);
+                heap_push_bounded(heap, &len, it, (size_t)knn);
+            }
+        }
+        uint64_t *ri = idx_out + i * knn;
+        float *rd = d0_out + i * knn;
+        if (len == 0 && retain == 1) { /* Singleton: (i, 0.0) then (i, 1.0) padding, no ANI transform */
+            for (uint64_t t = 0; t < knn; ++t) {
+                ri[t] = i;
+                rd[t] = t == 0 ? 0.0f : 1.0f;
+            }
+            continue;
+        }
+        heap_into_sorted(heap, len);
+        for (uint64_t t = 0; t < knn; ++t) {
+            if (t < len) {
+                ri[t] = heap[t].idx;
+                rd[t] = ani ? 1.0f - heap[t].key : heap[t].key;
+            } else { /* null values at the end: (i, 1.0) */
+                ri[t] = i;
+                rd[t] = 1.0f;
+            }
+        }
+    }
+    free(heap);
+    return 0;
+}

@@ -18,7 +18,7 @@ from . import build as _build
 __all__ = [
     "Context", "SketchDb", "DistType", "DistanceMatrix", "SparseDistanceMatrix", "SketchDistError", "set_k",
     "self_dists_all", "self_dists_knn", "cross_dists_all", "cross_dists_knn", "pair_dists", "match_counts",
-    "self_knn_partial", "cross_knn_partial", "knn_merge",
+    "self_knn_partial", "cross_knn_partial", "knn_merge", "self_dists_knn_precluster",
     "row_partition", "triangle_row_partition", "load_library", "library_path",
 ]
 
@@ -88,6 +88,7 @@ def load_library(build=True):
         "skd_self_knn_partial": (C.c_int, [vp, vp, u64, _DistType, vp, dbl, u64, u64, vp, vp, C.c_int]),
         "skd_cross_knn_partial": (C.c_int, [vp, vp, vp, u64, _DistType, vp, vp, dbl, u64, vp, vp, C.c_int]),
         "skd_knn_merge": (C.c_int, [vp, vp, vp, u32, u64, u64, _DistType, C.c_int, vp, vp, vp, C.c_int]),
+        "skd_self_dists_knn_candidates": (C.c_int, [vp, vp, u64, _DistType, vp, dbl, vp, vp, C.c_int, vp, vp]),
         "skd_pair_dists": (C.c_int, [vp, vp, vp, _DistType, vp, vp, dbl, vp, u64, vp]),
         "skd_match_counts": (C.c_int, [vp, vp, vp, vp, u64, vp]),
         "skd_match_counts_dense": (C.c_int, [vp, vp, vp, u64, u64, vp]),
@@ -488,6 +489,15 @@ def knn_merge(ctx, keys_parts, aux_parts, dist_type, ref_names, query_names=None
     ctx._check(ctx.lib.skd_knn_merge(ctx.handle, _ptr(keys), _ptr(aux), n_parts, n_rows, knn, dist_type.c, SKD_HOST,
                                      _ptr(idx), _ptr(d0), _ptr(d1), SKD_HOST))
     return SparseDistanceMatrix(ref_names, query_names, dist_type, knn, idx, d0, d1, (0, n_rows))
+
+
+def self_dists_knn_precluster(sketches, skq_bins, skq_names, knn, dist_type, retain_unmatched=None,
+                              completeness_vec=None, completeness_cutoff=0.64):
+    """self_dists_knn_precluster: src/distances/mod.rs:399-553 (see precluster.py)."""
+    import sys
+    from . import precluster
+    return precluster.self_dists_knn_precluster(sys.modules[__name__], sketches, skq_bins, skq_names, knn, dist_type,
+                                                retain_unmatched, completeness_vec, completeness_cutoff)
 
 
 def pair_dists(ref_sketches, query_sketches, pairs, dist_type=None, ref_completeness_vec=None,

@@ -1084,6 +1084,54 @@ skd_status skd_knn_merge(skd_ctx *ctx, const uint64_t *keys, const float *aux, u
     return timers_collect(ctx);
 }
 
+skd_status skd_self_dists_knn_candidates(skd_ctx *ctx, const skd_db *db, uint64_t knn, skd_dist_type dist,
+                                         const double *completeness, double cutoff, const uint64_t *cand_offsets,
+                                         const uint64_t *cand_idx, int retain_unmatched, uint64_t *idx_out,
+                                         float *d0_out) {
+    skd_status st = check_pair(ctx, db, db);
+    if (st) return st;
+    CU(ctx, cudaSetDevice(ctx->device));
+    if (dist.kind == SKD_CORE_ACC)
+        return fail(ctx, SKD_ERR_UNSUPPORTED, "Prefilter only available for single k-mer distances");  // mod.rs:548-550
+    if (knn == 0 || knn > 2048) return fail(ctx, SKD_ERR_UNSUPPORTED, "knn must be in [1, 2048] for candidate lists");
+    if (!cand_offsets || !idx_out || !d0_out) return fail(ctx, SKD_ERR_INVALID, "null argument");
+    EpiParams E;
+    st = build_epi(ctx, db, db, dist, completeness, completeness, cutoff, &E);
+    if (st) return st;
+    const uint64_t n = db->n;
+    timers_reset(ctx);
+    if (n == 0) return SKD_OK;
+    const uint64_t total = cand_offsets[n];
+    for (uint64_t i = 0; i < n; ++i)
+        if (cand_offsets[i] > cand_offsets[i + 1]) return fail(ctx, SKD_ERR_INVALID, "candidate offsets must not decrease");
+    for (uint64_t c = 0; c < total; ++c)
+        if (cand_idx[c] >= n) return fail(ctx, SKD_ERR_INVALID, "candidate index %llu out of range", (unsigned long long)cand_idx[c]);
+    uint32_t cap = 128;
+    while (cap < knn + 64) cap <<= 1;
+    void *doff, *didx, *oi, *od;
+    st = scratch_get(ctx, "cand_off", (n + 1) * 8, &doff);
+    if (st) return st;
+    st = scratch_get(ctx, "cand_idx", std::max<uint64_t>(1, total) * 8, &didx);
+    if (st) return st;
+    st = scratch_get(ctx, "knn_idx", n * knn * 8, &oi);
+    if (st) return st;
+    st = scratch_get(ctx, "knn_d0", n * knn * 4, &od);
+    if (st) return st;
+    CU(ctx, cudaMemcpyAsync(doff, cand_offsets, (n + 1) * 8, cudaMemcpyHostToDevice, ctx->compute));
+    if (total) CU(ctx, cudaMemcpyAsync(didx, cand_idx, total * 8, cudaMemcpyHostToDevice, ctx->compute));
+    st = timer_begin(ctx);
+    if (st) return st;
+    CU(ctx, launch_knn_candidates(db->dev, E, (const uint64_t *)doff, (const uint64_t *)didx, n, (uint32_t)knn, cap,
+                                  retain_unmatched, (unsigned long long *)oi, (float *)od, ctx->compute));
+    ctx->launches++;
+    st = timer_end(ctx);
+    if (st) return st;
+    CU(ctx, cudaMemcpyAsync(idx_out, oi, n * knn * 8, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(ctx, cudaMemcpyAsync(d0_out, od, n * knn * 4, cudaMemcpyDeviceToHost, ctx->compute));
+    CU(ctx, cudaStreamSynchronize(ctx->compute));
+    return timers_collect(ctx);
+}
+
 static skd_status pairs_common(skd_ctx *ctx, const skd_db *ref, const skd_db *query, const EpiParams &E,
                                const uint64_t *pairs, uint64_t n_pairs, uint32_t *counts, float *dists, int ncols) {
     timers_reset(ctx);

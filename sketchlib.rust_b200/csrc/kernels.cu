@@ -857,6 +857,121 @@ void launch_fill_u64(unsigned long long *p, uint64_t n, unsigned long long v, cu
     if (n) fill_u64_kernel<<<(unsigned)std::min<uint64_t>(4096, (n + 255) / 256), 256, 0, st>>>(p, n, v);
 }
 
+// Mismatching bins of one (sample of A, sample of B) pair at k-mer index k, computed by a whole warp straight
+// from the tiled layout in global memory (lanes stride over the 32-bin halves).  Every lane gets the total.
+__device__ __forceinline__ uint32_t warp_pair_mismatches(const DevDb &A, const DevDb &B, uint32_t k, uint32_t ba,
+                                                         uint32_t sa, uint32_t bb, uint32_t sb, int lane) {
+    uint32_t mism = 0;
+    for (uint32_t wc = lane; wc < 2 * A.W; wc += 32) {
+        const uint32_t *pa = A.tiled + slab_index(A, k, wc >> 1, ba) * STAGE_U32 + (wc & 1) * HALF_U32;
+        const uint32_t *pb = B.tiled + slab_index(B, k, wc >> 1, bb) * STAGE_U32 + (wc & 1) * HALF_U32;
+        uint32_t d = 0;
+#pragma unroll
+        for (int q = 0; q < 3; ++q) {
+            const uint4 a = reinterpret_cast<const uint4 *>(pa + q * QUAD_U32)[sa];
+            const uint4 b = reinterpret_cast<const uint4 *>(pb + q * QUAD_U32)[sb];
+            d |= (a.x ^ b.x) | (a.y ^ b.y) | (a.z ^ b.z) | (a.w ^ b.w);
+        }
+        {
+            const uint2 a = reinterpret_cast<const uint2 *>(pa + TAIL_U32)[sa];
+            const uint2 b = reinterpret_cast<const uint2 *>(pb + TAIL_U32)[sb];
+            d |= (a.x ^ b.x) | (a.y ^ b.y);
+        }
+        mism += __popc(d);
+    }
+    for (int o = 16; o > 0; o >>= 1) mism += __shfl_xor_sync(0xffffffffu, mism, o);
+    return mism;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Candidate-list kNN (the distance half of self_dists_knn_precluster, reference src/distances/mod.rs:399-553):
+// one CTA per row walks the row's candidate list (CSR, .skd indices, the row itself is skipped), one pair per
+// warp at a time, and keeps the knn best through a threshold + sort-in-rounds buffer in shared memory.
+// Rows with fewer than knn neighbours are padded with (row, 1.0); retain == 1 (Singleton) turns a row without
+// any neighbour into (row, 0.0), (row, 1.0)...  Single-k modes only, like the reference.
+__global__ void __launch_bounds__(128) knn_candidates_kernel(const __grid_constant__ DevDb A,
+                                                             const __grid_constant__ EpiParams E,
+                                                             const uint64_t *__restrict__ cand_off,
+                                                             const uint64_t *__restrict__ cand_idx, uint32_t knn,
+                                                             uint32_t cap, int retain,
+                                                             unsigned long long *__restrict__ idx_out,
+                                                             float *__restrict__ d0_out) {
+    extern __shared__ __align__(16) unsigned long long cbuf[];  // [cap]
+    __shared__ uint32_t cnt;
+    __shared__ unsigned long long thr;
+    const uint64_t row = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (uint32_t e = tid; e < cap; e += 128) cbuf[e] = ~0ull;
+    if (tid == 0) {
+        cnt = 0;
+        thr = ~0ull;
+    }
+    __syncthreads();
+    const uint64_t lo = cand_off[row], hi = cand_off[row + 1];
+    const uint32_t ba = (uint32_t)(row / TS), sa = (uint32_t)(row % TS);
+    const bool comp = E.has_c != 0;
+    const double c1 = comp ? E.a_comp[row] : 0.0;
+    const uint32_t round = cap - knn;  // new entries a round may add on top of the knn kept
+    for (uint64_t base = lo; base < hi; base += round) {
+        const uint64_t end = hi < base + round ? hi : base + round;
+        const unsigned long long th = thr;
+        for (uint64_t c = base + warp; c < end; c += 4) {
+            const uint64_t j = cand_idx[c];
+            if (j == row || j >= A.n) continue;
+            const uint32_t mism = warp_pair_mismatches(A, A, (uint32_t)E.k0, ba, sa, (uint32_t)(j / TS), (uint32_t)(j % TS), lane);
+            if (lane == 0) {
+                const uint32_t count = E.nbins - mism;
+                float key;
+                if (!comp) {
+                    key = E.key_tab[count];
+                } else {
+                    const double jac = corrected_jaccard(count, c1, E.b_comp[j], E);
+                    key = E.kind == KIND_ANI ? (float)__dsub_rn(1.0, ani_pois_dev(jac, E.k_single)) : (float)__dsub_rn(1.0, jac);
+                }
+                const unsigned long long v = ((unsigned long long)float_order_bits(key) << 32) | (uint32_t)j;
+                if (v < th) cbuf[atomicAdd(&cnt, 1u)] = v;
+            }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            warp_bitonic_sort(cbuf, nullptr, (int)cap, lane);
+            for (uint32_t e = knn + lane; e < cap; e += 32) cbuf[e] = ~0ull;
+            __syncwarp();
+            if (lane == 0) {
+                cnt = cnt < knn ? cnt : knn;
+                thr = cnt == knn ? cbuf[knn - 1] : ~0ull;
+            }
+        }
+        __syncthreads();
+    }
+    const uint32_t have = cnt;
+    for (uint32_t t = tid; t < knn; t += 128) {
+        unsigned long long oi = row;
+        float od = 1.0f;  // padding: (row, 1.0), mod.rs:537-544
+        if (t < have) {
+            const unsigned long long v = cbuf[t];
+            const float key = float_from_order_bits((uint32_t)(v >> 32));
+            oi = (uint32_t)v;
+            od = E.kind == KIND_ANI ? 1.0f - key : key;
+        } else if (have == 0 && retain == 1 && t == 0) {
+            od = 0.0f;  // Singleton, mod.rs:491-499
+        }
+        idx_out[row * knn + t] = oi;
+        d0_out[row * knn + t] = od;
+    }
+}
+
+cudaError_t launch_knn_candidates(const DevDb &A, const EpiParams &E, const uint64_t *cand_off, const uint64_t *cand_idx,
+                                  uint64_t n_rows, uint32_t knn, uint32_t cap, int retain, unsigned long long *idx_out,
+                                  float *d0_out, cudaStream_t st) {
+    if (n_rows == 0) return cudaSuccess;
+    const size_t smem = (size_t)cap * 8;
+    cudaError_t err = cudaFuncSetAttribute(knn_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (err != cudaSuccess) return err;
+    knn_candidates_kernel<<<(unsigned)n_rows, 128, smem, st>>>(A, E, cand_off, cand_idx, knn, cap, retain, idx_out, d0_out);
+    return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------
 // Explicit pair list: one warp per pair.  counts_out (nullable): [pair][K]; dist_out (nullable): 1 or 2 floats.
 __global__ void pair_kernel(const __grid_constant__ DevDb A, const __grid_constant__ DevDb B,
@@ -880,25 +995,7 @@ __global__ void pair_kernel(const __grid_constant__ DevDb A, const __grid_consta
     }
     float d0 = 0.0f, d1 = 0.0f;
     for (int k = k_lo; k < k_hi; ++k) {
-        uint32_t mism = 0;
-        for (uint32_t wc = lane; wc < 2 * A.W; wc += 32) {
-            const uint32_t *pa = A.tiled + slab_index(A, k, wc >> 1, ba) * STAGE_U32 + (wc & 1) * HALF_U32;
-            const uint32_t *pb = B.tiled + slab_index(B, k, wc >> 1, bb) * STAGE_U32 + (wc & 1) * HALF_U32;
-            uint32_t d = 0;
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                const uint4 a = reinterpret_cast<const uint4 *>(pa + q * QUAD_U32)[sa];
-                const uint4 b = reinterpret_cast<const uint4 *>(pb + q * QUAD_U32)[sb];
-                d |= (a.x ^ b.x) | (a.y ^ b.y) | (a.z ^ b.z) | (a.w ^ b.w);
-            }
-            {
-                const uint2 a = reinterpret_cast<const uint2 *>(pa + TAIL_U32)[sa];
-                const uint2 b = reinterpret_cast<const uint2 *>(pb + TAIL_U32)[sb];
-                d |= (a.x ^ b.x) | (a.y ^ b.y);
-            }
-            mism += __popc(d);
-        }
-        for (int o = 16; o > 0; o >>= 1) mism += __shfl_xor_sync(0xffffffffu, mism, o);
+        const uint32_t mism = warp_pair_mismatches(A, B, (uint32_t)k, ba, sa, bb, sb, lane);
         const uint32_t c = E.nbins - mism;
         if (counts_out && lane == 0) counts_out[p * A.K + k] = c;
         if (!dist_out) continue;

@@ -32,6 +32,10 @@ void launch_knn_finalize(const unsigned long long *keys, const float *aux, uint3
 
 void launch_fill_u64(unsigned long long *p, uint64_t n, unsigned long long v, cudaStream_t st);
 
+cudaError_t launch_knn_candidates(const DevDb &A, const EpiParams &E, const uint64_t *cand_off, const uint64_t *cand_idx,
+                                  uint64_t n_rows, uint32_t knn, uint32_t cap, int retain, unsigned long long *idx_out,
+                                  float *d0_out, cudaStream_t st);
+
 void launch_pairs(const DevDb &A, const DevDb &B, const EpiParams &E, const uint64_t *pairs, uint64_t n_pairs,
                   uint32_t *counts_out, float *dist_out, cudaStream_t st);
 

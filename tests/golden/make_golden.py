@@ -36,6 +36,7 @@ def main():
     for f in ("dists_knn_ca", "dists_knn_jaccard", "dists_knn_ani", "dists_subset", "inverted_precluster",
               "inverted_precluster_ani"):
         shutil.copyfile(os.path.join(OUT, f + ".stdout"), os.path.join(fx, f + ".stdout"))
+    shutil.copyfile(os.path.join(OUT, "inverted.skq"), os.path.join(fx, "inverted.skq"))  # 4 samples x 10 u16 bins
 
     names = [l.split()[0] for l in open(os.path.join(IN, "rfile.txt"))]
     recs = {n: oracle.read_fasta_records(os.path.join(IN, n)) for n in names}

@@ -459,3 +459,54 @@ def test_cross_knn_ref_shards_merge(sk, ctx):
         assert np.array_equal(merged.idx, want.idx) and np.array_equal(merged.d0, want.d0)
         if kidx < 0:
             assert np.array_equal(merged.d1, want.d1)
+
+
+# ------------------------------------------------------------------ precluster (candidate-list kNN)
+def test_precluster_goldens_and_modes(sk, ctx):
+    db = fixture_db("sketches3")
+    g = up(sk, ctx, db)
+    skq = np.fromfile(os.path.join(FIXTURES, "inverted.skq"), dtype="<u2").reshape(4, 10)
+    for knn in (1, 50):  # tests/inverted.rs:244-347: knn 50 prints the same rows (padding is skipped)
+        got = sk.self_dists_knn_precluster(g, skq, db.names, knn, sk.set_k(g, 21))
+        assert str(got) == golden("inverted_precluster")
+        got = sk.self_dists_knn_precluster(g, skq, db.names, knn, sk.set_k(g, 21, ani=True))
+        assert str(got) == golden("inverted_precluster_ani")
+    # .ski order differs from .skd order: names drive the index remap (mod.rs:412-438)
+    perm = [2, 0, 3, 1]
+    got = sk.self_dists_knn_precluster(g, skq[perm], [db.names[i] for i in perm], 1, sk.set_k(g, 21))
+    assert str(got) == golden("inverted_precluster")
+    with pytest.raises(sk.SketchDistError, match="could not be found in the .ski"):
+        sk.self_dists_knn_precluster(g, skq[:3], db.names[:3], 1, sk.set_k(g, 21))
+    leg = up(sk, ctx, fixture_db("legacy_db"))
+    with pytest.raises(sk.SketchDistError, match="Prefilter only available for single k-mer distances"):
+        sk.self_dists_knn_precluster(leg, skq[:2], ["R6.fa.gz", "TIGR4.fa.gz"], 1, sk.set_k(leg))
+
+
+@pytest.mark.parametrize("retain", [None, "singleton", "bruteforce"])
+def test_precluster_vs_oracle(sk, ctx, retain):
+    db = synth_db(300, 16, [17, 21, 25], seed=80, n_families=25, unrelated_frac=0.2)
+    g = up(sk, ctx, db)
+    rng = np.random.default_rng(5)
+    # a coarse 8-bin "inverted" sketch per sample: family members share bins, loners share none
+    fam = rng.integers(0, 40, size=300)
+    skq = (fam[:, None] * 131 + np.arange(8)[None, :] * 7).astype(np.uint16)
+    lone = rng.random(300) < 0.15
+    skq[lone] = rng.integers(0, 1 << 16, size=(int(lone.sum()), 8), dtype=np.uint16)
+    mut = rng.random((300, 8)) < 0.3
+    skq[mut] = rng.integers(0, 1 << 16, size=int(mut.sum()), dtype=np.uint16)
+    off, idx = oracle.any_shared_bins_csr(skq)
+    for ani in (False, True):
+        dt = sk.set_k(g, 21, ani=ani)
+        got = sk.self_dists_knn_precluster(g, skq, db.names, 10, dt, retain_unmatched=retain)
+        oidx, od0 = oracle.self_dists_knn_precluster(db, off, idx, 10, 1, ani=ani,
+                                                      retain={None: 0, "singleton": 1, "bruteforce": 2}[retain])
+        assert np.array_equal(got.d0, od0)
+        pad = od0 == 1.0  # padding rows point at the row itself in both
+        assert np.array_equal(got.idx[pad & (oidx == np.arange(300)[:, None])], oidx[pad & (oidx == np.arange(300)[:, None])])
+        for r in range(300):
+            strict = od0[r] != od0[r, -1]
+            assert set(got.idx[r][strict].tolist()) == set(oidx[r][strict].tolist())
+    cv = rng.uniform(0.7, 1.0, size=300)
+    got = sk.self_dists_knn_precluster(g, skq, db.names, 5, sk.set_k(g, 21), completeness_vec=cv)
+    oidx, od0 = oracle.self_dists_knn_precluster(db, off, idx, 5, 1, completeness=cv)
+    assert np.abs(got.d0.astype(np.float64) - od0).max() <= TOL

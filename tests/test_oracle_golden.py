@@ -110,3 +110,28 @@ def test_degenerate_cases():
     # expected_samebits > 0 needs >= 16384 bins (W = 256 -> expected = 1)
     assert j(1, 256, 0, 0, 0, 0.64) == 0.0
     assert j(16384, 256, 0, 0, 0, 0.64) == 1.0
+
+
+def test_precluster_driver_goldens():
+    # tests/inverted.rs:244-347: index built with -k 21 -s 10 (inverted.skq), distances from the standard
+    # k=21 / 1024-bin database (= the shipped sketches3), knn 1 and knn 50 print the same rows (padding skipped)
+    db = fixture_db("sketches3")
+    skq = np.fromfile(os.path.join(FIXTURES, "inverted.skq"), dtype="<u2").reshape(4, 10)
+    off, idx = oracle.any_shared_bins_csr(skq)
+    cand = [idx[off[i]:off[i + 1]].tolist() for i in range(4)]
+    assert cand == [[0, 1], [0, 1], [2, 3], [2, 3]]  # "Identified 2 prefilter pairs from a max of 6"
+    for knn in (1, 3):
+        nidx, d0 = oracle.self_dists_knn_precluster(db, off, idx, knn, 0)
+        assert render_sparse(db.names, db.names, nidx, d0) == golden("inverted_precluster")
+        nidx, d0 = oracle.self_dists_knn_precluster(db, off, idx, knn, 0, ani=True)
+        assert render_sparse(db.names, db.names, nidx, d0) == golden("inverted_precluster_ani")
+    # no candidates: padded with (i, 1.0) and not printed; singleton keeps (i, 0); bruteforce = plain kNN
+    none_off, none_idx = np.arange(5, dtype=np.uint64), np.arange(4, dtype=np.uint64)  # only itself
+    nidx, d0 = oracle.self_dists_knn_precluster(db, none_off, none_idx, 2, 0)
+    assert (nidx == np.arange(4)[:, None]).all() and (d0 == 1.0).all()
+    assert render_sparse(db.names, db.names, nidx, d0) == ""
+    nidx, d0 = oracle.self_dists_knn_precluster(db, none_off, none_idx, 2, 0, retain=1)
+    assert d0.tolist() == [[0.0, 1.0]] * 4 and (nidx == np.arange(4)[:, None]).all()
+    nidx, d0 = oracle.self_dists_knn_precluster(db, none_off, none_idx, 2, 0, retain=2)
+    kidx, kd0, _ = oracle.self_dists_knn(db, 2, k_idx=0)
+    assert np.array_equal(nidx, kidx) and np.array_equal(d0, kd0)
