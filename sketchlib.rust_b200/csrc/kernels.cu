@@ -197,8 +197,8 @@ __device__ __forceinline__ void tile_counts(const DevDb &A, const DevDb &B, uint
                                             uint32_t *stage_mem, uint64_t *full_bar, CountT *counts, int kp,
                                             uint32_t one, uint32_t &git) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int arow0 = 16 * (warp >> 1) + (lane >> 3);
-    const int bcol0 = 32 * (warp & 1) + (lane & 7);
+    const int arow0 = (TJ == 4 ? 16 * (warp >> 1) : 16 * warp) + (lane >> 3);
+    const int bcol0 = (TJ == 4 ? 32 * (warp & 1) : 0) + (lane & 7);
     const uint32_t W = A.W;
     const uint32_t n_it = (uint32_t)nk * W;
 
@@ -220,11 +220,11 @@ __device__ __forceinline__ void tile_counts(const DevDb &A, const DevDb &B, uint
         for (uint32_t p = 0; p < pre; ++p) issue(p);  // all stages are free at tile start (CTA barrier before)
     }
 
-    uint32_t mism[4][4];
+    uint32_t mism[4][TJ];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) mism[i][j] = 0;
+        for (int j = 0; j < TJ; ++j) mism[i][j] = 0;
 
     uint32_t w_in_k = 0, kk = 0;
     bool ready = false;
@@ -238,20 +238,20 @@ __device__ __forceinline__ void tile_counts(const DevDb &A, const DevDb &B, uint
 
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-            uint32_t d[4][4];
+            uint32_t d[4][TJ];
             const uint4 *a4 = reinterpret_cast<const uint4 *>(sa + half * HALF_U32);
             const uint4 *b4 = reinterpret_cast<const uint4 *>(sb + half * HALF_U32);
 #pragma unroll
             for (int q = 0; q < 3; ++q) {  // planes 4q .. 4q+3: one LDS.128 per sample
-                uint4 av[4], bv[4];
+                uint4 av[4], bv[TJ];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) av[i] = a4[q * TS + arow0 + 4 * i];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) bv[j] = b4[q * TS + bcol0 + 8 * j];
+                for (int j = 0; j < TJ; ++j) bv[j] = b4[q * TS + bcol0 + 8 * j];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < TJ; ++j) {
                         if (q == 0)
                             d[i][j] = av[i].x ^ bv[j].x;
                         else
@@ -264,15 +264,15 @@ __device__ __forceinline__ void tile_counts(const DevDb &A, const DevDb &B, uint
             {  // planes 12, 13: one LDS.64 per sample
                 const uint2 *a2 = reinterpret_cast<const uint2 *>(sa + half * HALF_U32 + TAIL_U32);
                 const uint2 *b2 = reinterpret_cast<const uint2 *>(sb + half * HALF_U32 + TAIL_U32);
-                uint2 av[4], bv[4];
+                uint2 av[4], bv[TJ];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) av[i] = a2[arow0 + 4 * i];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) bv[j] = b2[bcol0 + 8 * j];
+                for (int j = 0; j < TJ; ++j) bv[j] = b2[bcol0 + 8 * j];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
+                    for (int j = 0; j < TJ; ++j) {
                         d[i][j] |= av[i].x ^ bv[j].x;
                         d[i][j] |= av[i].y ^ bv[j].y;
                     }
@@ -281,7 +281,7 @@ __device__ __forceinline__ void tile_counts(const DevDb &A, const DevDb &B, uint
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) mism[i][j] = __popc(d[i][j]) * one + mism[i][j];
+                for (int j = 0; j < TJ; ++j) mism[i][j] = __popc(d[i][j]) * one + mism[i][j];
             if (half == 0) ready = it + 1 < n_it && mbar_test(&full_bar[(g + 1) % NST], ((g + 1) / NST) & 1u);
         }
 
@@ -290,7 +290,7 @@ __device__ __forceinline__ void tile_counts(const DevDb &A, const DevDb &B, uint
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < TJ; ++j) {
                     counts[((arow0 + 4 * i) * TS + bcol0 + 8 * j) * kp + kk] = (CountT)(nbins - mism[i][j]);
                     mism[i][j] = 0;
                 }

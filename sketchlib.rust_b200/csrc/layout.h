@@ -11,7 +11,11 @@ constexpr int HALF_U32 = PP * TS * 2;      // u32 per (32-bin word column, sampl
 constexpr int STAGE_U32 = 2 * HALF_U32;    // u32 per (64-bin word, sample block): one pipeline stage operand
 constexpr int STAGE_BYTES = STAGE_U32 * 4; // 7168 B
 constexpr int NST = 3;                     // pipeline stages
-constexpr int THREADS = 256;               // 8 warps, warp tile 16x32, thread tile 4x4
+#ifndef SKD_TJ
+#define SKD_TJ 4
+#endif
+constexpr int TJ = SKD_TJ;                 // columns per thread: 4 (8 warps, warp tile 16x32) or 8 (4 warps, 16x64)
+constexpr int THREADS = TJ == 4 ? 256 : 128;  // thread tile 4 x TJ pairs
 constexpr int MAXK = 32;                   // k-mer lengths supported by the fused core/accessory epilogue
 
 // Tiled layout ("k-major, 64-bin-word, sample-block"): one (k, w, b) slab = 64 samples x 14 planes x 64 bins =
