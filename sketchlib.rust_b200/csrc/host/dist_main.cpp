@@ -7,12 +7,15 @@
 // Only `dist` is implemented: the other sub-commands are not on the accelerated path.
 // Extra flag: --gpu <id> (default 0).  --threads is accepted for compatibility (the work runs on the GPU).
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
+#include <functional>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/sketchdist.h"
@@ -65,7 +68,7 @@ const char *USAGE =
     "      --subset <SUBSET>              Sample names to analyse\n"
     "  -k <KMER>                          K-mer length (if provided only calculate Jaccard distance)\n"
     "      --ani                          Calculate ANI rather than Jaccard dists, using Poisson model\n"
-    "      --threads <THREADS>            Number of CPU threads [default: 1] (unused: distances run on the GPU)\n"
+    "      --threads <THREADS>            Number of CPU threads [default: 1] (formats the dense text output; distances run on the GPU)\n"
     "      --ref-completeness-file <F>    Reference completeness estimates (genome_id<tab>completeness)\n"
     "      --query-completeness-file <F>  Query completeness estimates (cross-query mode only)\n"
     "      --completeness-cutoff <X>      Minimum c1*c2 for the completeness correction [default: 0.64]\n"
@@ -219,6 +222,50 @@ struct Out {
     }
 };
 
+// Formats rows [r0, r1) of a dense result on `threads` host threads (row_fn appends the text of one row) and
+// writes the blocks in row order.  The reference's Display is serial; --threads is reused for this tail.
+void write_rows(Out &out, uint64_t r0, uint64_t r1, int threads, const std::function<void(uint64_t, std::string &)> &row_fn) {
+    if (threads <= 1 || r1 - r0 < 64) {
+        for (uint64_t i = r0; i < r1; ++i) {
+            row_fn(i, out.buf);
+            if (out.buf.size() > (1 << 22)) out.flush();
+        }
+        return;
+    }
+    const uint64_t block = 32;
+    const uint64_t n_blocks = (r1 - r0 + block - 1) / block;
+    std::vector<std::string> text(n_blocks);
+    std::atomic<uint64_t> next{0};
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; ++t)
+        pool.emplace_back([&] {
+            for (;;) {
+                uint64_t b = next.fetch_add(1);
+                if (b >= n_blocks) break;
+                for (uint64_t i = r0 + b * block; i < std::min(r1, r0 + (b + 1) * block); ++i) row_fn(i, text[b]);
+            }
+        });
+    for (auto &th : pool) th.join();
+    out.flush();
+    for (auto &t : text) {
+        out.buf.swap(t);
+        out.flush();
+    }
+}
+
+inline void append_line(std::string &buf, const std::string &a, const std::string &b, float d0, const float *d1) {
+    buf += a;
+    buf += '\t';
+    buf += b;
+    buf += '\t';
+    buf += fmt_f32(d0);
+    if (d1) {
+        buf += '\t';
+        buf += fmt_f32(*d1);
+    }
+    buf += '\n';
+}
+
 struct Pinned {
     skd_ctx *ctx;
     void *p = nullptr;
@@ -296,7 +343,7 @@ int run(const DistArgs &a) {
         load_db(gpu, queries, qname, nullptr);
     }
 
-    const size_t kChunkBytes = (size_t)1 << 30;  // dense results are produced and written in row chunks
+    const size_t kChunkBytes = (size_t)128 << 20;  // dense results are produced and written in row chunks
     if (!a.has_query) {
         if (a.knn < 0) {
             log_info("Calculating all ref vs ref distances");
@@ -308,12 +355,13 @@ int run(const DistArgs &a) {
                     uint64_t r1 = std::min(n, r0 + rows_per);
                     gpu.check(skd_self_dists_all(gpu.ctx, refs.db, dt, has_ref_c ? ref_c.data() : nullptr,
                                                  a.completeness_cutoff, r0, r1, (float *)buf.p, SKD_HOST));
-                    const float *d = (const float *)buf.p;
-                    for (uint64_t i = r0; i < r1; ++i) {
+                    const float *base = (const float *)buf.p;
+                    write_rows(out, r0, std::min(r1, n - 1), (int)a.threads, [&](uint64_t i, std::string &txt) {
+                        const float *d = base + skd_self_pairs_in_rows(n, r0, i) * ncols;
                         const std::string &rn = refs.meta.sketch_name(i);
                         for (uint64_t j = i + 1; j < n; ++j, d += ncols)
-                            out.line(rn, refs.meta.sketch_name(j), d[0], ncols == 2 ? d + 1 : nullptr);
-                    }
+                            append_line(txt, rn, refs.meta.sketch_name(j), d[0], ncols == 2 ? d + 1 : nullptr);
+                    });
                 }
             } else {
                 gpu.check(skd_self_dists_all(gpu.ctx, refs.db, dt, nullptr, a.completeness_cutoff, 0, n, nullptr, SKD_HOST));
@@ -379,12 +427,13 @@ int run(const DistArgs &a) {
                     uint64_t r1 = std::min(n, r0 + rows_per);
                     gpu.check(skd_cross_dists_all(gpu.ctx, refs.db, queries.db, dt, rc, qc, a.completeness_cutoff, r0, r1,
                                                   (float *)buf.p, SKD_HOST));
-                    const float *d = (const float *)buf.p;
-                    for (uint64_t i = r0; i < r1; ++i) {
+                    const float *base = (const float *)buf.p;
+                    write_rows(out, r0, r1, (int)a.threads, [&](uint64_t i, std::string &txt) {
+                        const float *d = base + (i - r0) * nq * ncols;
                         const std::string &rn = refs.meta.sketch_name(i);
                         for (uint64_t j = 0; j < nq; ++j, d += ncols)
-                            out.line(rn, queries.meta.sketch_name(j), d[0], ncols == 2 ? d + 1 : nullptr);
-                    }
+                            append_line(txt, rn, queries.meta.sketch_name(j), d[0], ncols == 2 ? d + 1 : nullptr);
+                    });
                 }
             } else {
                 gpu.check(skd_cross_dists_all(gpu.ctx, refs.db, queries.db, dt, rc, qc, a.completeness_cutoff, 0, n,
