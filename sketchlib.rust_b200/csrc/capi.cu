@@ -251,7 +251,8 @@ void build_groups(bool self, uint32_t rb0, uint32_t n_rb, uint32_t nbB, std::vec
 // Launch the tile kernel for rows [r0, r1) writing to device memory `dout`.  `d_grp_off` is the device copy
 // of `off` (group offsets built by build_groups for exactly this row range).
 skd_status launch_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, const EpiParams &E, int mode, uint64_t r0,
-                        uint64_t r1, float *dout, const std::vector<uint64_t> &off, const uint64_t *d_grp_off) {
+                        uint64_t r1, float *dout, const std::vector<uint64_t> &off, const uint64_t *d_grp_off,
+                        uint64_t rect_ld = 0) {
     SchedParams S{};
     S.mode = mode;
     S.one = 1;
@@ -265,6 +266,7 @@ skd_status launch_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, const Ep
     S.row_end = r1;
     S.out_base = S.self_mode ? condensed(r0, r0 + 1, A->n) : 0;
     S.out = dout;
+    S.rect_ld = rect_ld;
     const bool count32 = E.nbins >= 65536;
     size_t smem = tile_kernel_smem(E.nk, count32, false, 0, false);
     if (smem > kMaxSmem)
@@ -369,6 +371,96 @@ skd_status run_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, bool self, 
     return timers_collect(ctx);
 }
 
+// Cross kNN with few queries: the row-owned kernel would have only a few row blocks (queries are its rows), so
+// instead the dense cross kernel (references as rows; narrow-column variant when <= 32 queries) writes the kNN
+// keys ref-major into HBM and select_kernel folds each query's column into per-slice lists, merged at the end.
+// E is oriented for the row-owned call (a = queries, b = refs).
+constexpr uint64_t kFewQueries = 512;
+skd_status finalize_lists(skd_ctx *ctx, const unsigned long long *dkeys, const float *daux, uint32_t n_parts,
+                          uint64_t part_stride, uint64_t n_rows, uint64_t knn, int kind, uint64_t *idx_out, float *d0_out,
+                          float *d1_out, skd_loc out_loc);
+
+skd_status run_knn_few_queries(skd_ctx *ctx, const skd_db *R, const skd_db *Q, const EpiParams &E, uint64_t knn,
+                               uint64_t *idx_out, float *d0_out, float *d1_out, skd_loc out_loc, uint64_t *key_out,
+                               float *aux_out, uint64_t idx_offset) {
+    const uint64_t nq = Q->n, n_ref = R->n;
+    const bool with_aux = E.kind == KIND_CORE_ACC, partial = key_out != nullptr;
+    const uint64_t elt = with_aux ? 8 : 4;
+    EpiParams Ed = E;  // dense launch: rows = refs, columns = queries
+    std::swap(Ed.a_comp, Ed.b_comp);
+    uint64_t rows_chunk = std::max<uint64_t>(TS, g_sym_chunk_bytes / (nq * elt) / TS * TS);
+    rows_chunk = std::min<uint64_t>(rows_chunk, (n_ref + TS - 1) / TS * TS);
+    const uint32_t n_chunks = (uint32_t)((n_ref + rows_chunk - 1) / rows_chunk);
+    const uint32_t tgt_groups = (uint32_t)((nq + TS - 1) / TS);
+    uint32_t n_splits = (uint32_t)std::max<uint64_t>(1, (4ull * ctx->sm_count) / ((uint64_t)tgt_groups * n_chunks));
+    n_splits = std::min<uint32_t>({n_splits, 64u, (uint32_t)(rows_chunk / TS)});
+    n_splits = std::max(1u, n_splits);
+    const uint32_t rows_per_split = (uint32_t)(((rows_chunk + n_splits - 1) / n_splits + TS - 1) / TS * TS);
+    const uint32_t parts = n_chunks * n_splits;
+    const uint64_t part_stride = nq * knn;
+    void *D, *pk, *pa = nullptr;
+    skd_status st = scratch_get(ctx, "knn_rect", rows_chunk * nq * elt, &D);
+    if (st) return st;
+    st = scratch_get(ctx, "few_key", (size_t)parts * part_stride * 8, &pk);
+    if (st) return st;
+    if (with_aux) {
+        st = scratch_get(ctx, "few_aux", (size_t)parts * part_stride * 4, &pa);
+        if (st) return st;
+    }
+    timers_reset(ctx);
+    launch_fill_u64((unsigned long long *)pk, (uint64_t)parts * part_stride, ~0ull, ctx->compute);
+    ctx->launches++;
+    for (uint32_t c = 0; c < n_chunks; ++c) {
+        const uint64_t g0 = (uint64_t)c * rows_chunk, g1 = std::min(n_ref, g0 + rows_chunk);
+        std::vector<uint64_t> off;
+        build_groups(false, (uint32_t)(g0 / TS), (uint32_t)((g1 + TS - 1) / TS) - (uint32_t)(g0 / TS), Q->dev.nb, &off);
+        void *doff;
+        st = scratch_get(ctx, "grp_off", off.size() * sizeof(uint64_t), &doff);
+        if (st) return st;
+        CU(ctx, cudaMemcpyAsync(doff, off.data(), off.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->compute));
+        CU(ctx, cudaStreamSynchronize(ctx->compute));  // off is local; also fences reuse of the key matrix
+        st = launch_dense(ctx, R, Q, Ed, MODE_DENSE_CROSS, g0, g1, (float *)D, off, (const uint64_t *)doff, nq);
+        if (st) return st;
+        st = timer_begin(ctx);
+        if (st) return st;
+        CU(ctx, launch_select(true, with_aux, (const float *)D, nq, g0, (uint32_t)(g1 - g0), 0, nq, 0, nq,
+                              (unsigned long long *)pk + (uint64_t)c * n_splits * part_stride,
+                              with_aux ? (float *)pa + (uint64_t)c * n_splits * part_stride : nullptr, (uint32_t)knn,
+                              ctx->compute, 1, idx_offset, n_splits, rows_per_split, part_stride));
+        ctx->launches++;
+        st = timer_end(ctx);
+        if (st) return st;
+    }
+    if (partial) {
+        unsigned long long *dk = (unsigned long long *)key_out;
+        float *da = aux_out;
+        if (out_loc == SKD_HOST) {
+            void *p;
+            st = scratch_get(ctx, "knn_idx", nq * knn * 8, &p);
+            if (st) return st;
+            dk = (unsigned long long *)p;
+            st = scratch_get(ctx, "knn_d0", nq * knn * 4, &p);
+            if (st) return st;
+            da = (float *)p;
+        }
+        launch_fill_u64(dk, nq * knn, ~0ull, ctx->compute);
+        launch_knn_finalize((const unsigned long long *)pk, (const float *)pa, parts, part_stride, 0, nq, (uint32_t)knn,
+                            E.kind, nullptr, nullptr, nullptr, dk, with_aux ? da : nullptr, ctx->compute);
+        CU(ctx, cudaGetLastError());
+        ctx->launches += 2;
+        if (out_loc == SKD_HOST) {
+            CU(ctx, cudaMemcpyAsync(key_out, dk, nq * knn * 8, cudaMemcpyDeviceToHost, ctx->compute));
+            if (aux_out && with_aux) CU(ctx, cudaMemcpyAsync(aux_out, da, nq * knn * 4, cudaMemcpyDeviceToHost, ctx->compute));
+        }
+        CU(ctx, cudaStreamSynchronize(ctx->compute));
+        return timers_collect(ctx);
+    }
+    st = finalize_lists(ctx, (const unsigned long long *)pk, (const float *)pa, parts, part_stride, nq, knn, E.kind, idx_out,
+                        d0_out, d1_out, out_loc);
+    if (st) return st;
+    return timers_collect(ctx);
+}
+
 // Row-owned kNN: the tile kernel scans every column for rows [row_begin, row_end).  Output is either the final
 // sparse rows (idx/d0/d1) or, when key_out is set, one sorted composite list per row (a partial result for a
 // merge across column shards; idx_offset is added to the stored neighbour indices).
@@ -380,6 +472,8 @@ skd_status run_knn(skd_ctx *ctx, const skd_db *R, const skd_db *Q, bool self, co
     const uint64_t n_rows = row_end - row_begin;
     timers_reset(ctx);
     if (n_rows == 0) return SKD_OK;
+    if (!self && ctx->knn_symmetric && Q->n <= kFewQueries && knn <= kSymKnnMax && row_begin == 0 && row_end == Q->n)
+        return run_knn_few_queries(ctx, R, Q, E, knn, idx_out, d0_out, d1_out, out_loc, key_out, aux_out, idx_offset);
     const bool with_aux = E.kind == KIND_CORE_ACC;
     const bool partial = key_out != nullptr;
     uint32_t cap = 128;
@@ -406,6 +500,7 @@ skd_status run_knn(skd_ctx *ctx, const skd_db *R, const skd_db *Q, bool self, co
     S.cap = cap;
     S.idx_offset = idx_offset;
     uint32_t want = (uint32_t)((8ull * ctx->sm_count + S.n_rb - 1) / S.n_rb);  // aim for >= 8 waves of CTAs
+    want = std::min(want, 32u);  // the rank-by-search merge is quadratic in the number of lists per row
     S.n_split = std::max(1u, std::min(want, std::max(1u, B->dev.nb)));
     S.cb_per_split = (std::max(1u, B->dev.nb) + S.n_split - 1) / S.n_split;
     S.n_split = (std::max(1u, B->dev.nb) + S.cb_per_split - 1) / S.cb_per_split;

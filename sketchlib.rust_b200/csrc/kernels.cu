@@ -192,13 +192,67 @@ struct TileCoord {
     uint32_t rb, cb;
 };
 
-template <typename CountT>
+// Mismatch counts of one 32-bin half for a thread's 4 x JN pair tile (JN <= TJ column groups of 8 samples).
+// JN < TJ is the narrow-column variant for cross runs with few queries: the column operands that do not
+// exist are neither loaded nor compared, which turns the launch from INT-bound into memory-bound.
+template <int JN>
+__device__ __forceinline__ void half_mismatches(const uint32_t *sa, const uint32_t *sb, int arow0, int bcol0,
+                                                uint32_t one, uint32_t (&mism)[4][TJ]) {
+    uint32_t d[4][JN];
+    const uint4 *a4 = reinterpret_cast<const uint4 *>(sa);
+    const uint4 *b4 = reinterpret_cast<const uint4 *>(sb);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {  // planes 4q .. 4q+3: one LDS.128 per sample
+        uint4 av[4], bv[JN];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) av[i] = a4[q * TS + arow0 + 4 * i];
+#pragma unroll
+        for (int j = 0; j < JN; ++j) bv[j] = b4[q * TS + bcol0 + 8 * j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < JN; ++j) {
+                if (q == 0)
+                    d[i][j] = av[i].x ^ bv[j].x;
+                else
+                    d[i][j] |= av[i].x ^ bv[j].x;
+                d[i][j] |= av[i].y ^ bv[j].y;
+                d[i][j] |= av[i].z ^ bv[j].z;
+                d[i][j] |= av[i].w ^ bv[j].w;
+            }
+    }
+    {  // planes 12, 13: one LDS.64 per sample
+        const uint2 *a2 = reinterpret_cast<const uint2 *>(sa + TAIL_U32);
+        const uint2 *b2 = reinterpret_cast<const uint2 *>(sb + TAIL_U32);
+        uint2 av[4], bv[JN];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) av[i] = a2[arow0 + 4 * i];
+#pragma unroll
+        for (int j = 0; j < JN; ++j) bv[j] = b2[bcol0 + 8 * j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < JN; ++j) {
+                d[i][j] |= av[i].x ^ bv[j].x;
+                d[i][j] |= av[i].y ^ bv[j].y;
+            }
+    }
+    // accumulate on the FMA pipe (IMAD with a run-time 1) so the ALU pipe only sees the LOP3s
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < JN; ++j) mism[i][j] = __popc(d[i][j]) * one + mism[i][j];
+}
+
+// COLS = number of leading columns of the tile that are computed (8, 16, 32 or 64 = all).
+template <typename CountT, int COLS>
 __device__ __forceinline__ void tile_counts(const DevDb &A, const DevDb &B, uint32_t rb, uint32_t cb, int k0, int nk,
                                             uint32_t *stage_mem, uint64_t *full_bar, CountT *counts, int kp,
-                                            uint32_t one, uint32_t &git) {
+                                            uint32_t one, uint64_t row_end, uint32_t &git) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int arow0 = (TJ == 4 ? 16 * (warp >> 1) : 16 * warp) + (lane >> 3);
     const int bcol0 = (TJ == 4 ? 32 * (warp & 1) : 0) + (lane & 7);
+    (void)row_end;
     const uint32_t W = A.W;
     const uint32_t n_it = (uint32_t)nk * W;
 
@@ -236,53 +290,14 @@ __device__ __forceinline__ void tile_counts(const DevDb &A, const DevDb &B, uint
         const uint32_t *sa = stage_mem + (g % NST) * (2 * STAGE_U32);
         const uint32_t *sb = sa + STAGE_U32;
 
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            uint32_t d[4][TJ];
-            const uint4 *a4 = reinterpret_cast<const uint4 *>(sa + half * HALF_U32);
-            const uint4 *b4 = reinterpret_cast<const uint4 *>(sb + half * HALF_U32);
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {  // planes 4q .. 4q+3: one LDS.128 per sample
-                uint4 av[4], bv[TJ];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) av[i] = a4[q * TS + arow0 + 4 * i];
-#pragma unroll
-                for (int j = 0; j < TJ; ++j) bv[j] = b4[q * TS + bcol0 + 8 * j];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < TJ; ++j) {
-                        if (q == 0)
-                            d[i][j] = av[i].x ^ bv[j].x;
-                        else
-                            d[i][j] |= av[i].x ^ bv[j].x;
-                        d[i][j] |= av[i].y ^ bv[j].y;
-                        d[i][j] |= av[i].z ^ bv[j].z;
-                        d[i][j] |= av[i].w ^ bv[j].w;
-                    }
-            }
-            {  // planes 12, 13: one LDS.64 per sample
-                const uint2 *a2 = reinterpret_cast<const uint2 *>(sa + half * HALF_U32 + TAIL_U32);
-                const uint2 *b2 = reinterpret_cast<const uint2 *>(sb + half * HALF_U32 + TAIL_U32);
-                uint2 av[4], bv[TJ];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) av[i] = a2[arow0 + 4 * i];
-#pragma unroll
-                for (int j = 0; j < TJ; ++j) bv[j] = b2[bcol0 + 8 * j];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-#pragma unroll
-                    for (int j = 0; j < TJ; ++j) {
-                        d[i][j] |= av[i].x ^ bv[j].x;
-                        d[i][j] |= av[i].y ^ bv[j].y;
-                    }
-            }
-            // accumulate on the FMA pipe (IMAD with a run-time 1) so the ALU pipe only sees the LOP3s
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < TJ; ++j) mism[i][j] = __popc(d[i][j]) * one + mism[i][j];
-            if (half == 0) ready = it + 1 < n_it && mbar_test(&full_bar[(g + 1) % NST], ((g + 1) / NST) & 1u);
+        if (COLS == TS) {
+            half_mismatches<TJ>(sa, sb, arow0, bcol0, one, mism);
+            ready = it + 1 < n_it && mbar_test(&full_bar[(g + 1) % NST], ((g + 1) / NST) & 1u);
+            half_mismatches<TJ>(sa + HALF_U32, sb + HALF_U32, arow0, bcol0, one, mism);
+        } else if (bcol0 < COLS) {  // narrow variant: warps whose columns lie past COLS only keep the barriers
+            constexpr int JN = COLS >= 8 * TJ ? TJ : COLS / 8;
+            half_mismatches<JN>(sa, sb, arow0, bcol0, one, mism);
+            half_mismatches<JN>(sa + HALF_U32, sb + HALF_U32, arow0, bcol0, one, mism);
         }
 
         if (++w_in_k == W) {  // finished this k: park the match counts in shared memory
@@ -389,7 +404,7 @@ __device__ __forceinline__ void warp_bitonic_sort(unsigned long long *key, float
     __syncwarp();
 }
 
-template <typename CountT>
+template <typename CountT, int COLS>
 __global__ void __launch_bounds__(THREADS, 2)
     tile_kernel(const __grid_constant__ DevDb A, const __grid_constant__ DevDb B, const __grid_constant__ EpiParams E,
                 const __grid_constant__ SchedParams S) {
@@ -428,7 +443,7 @@ __global__ void __launch_bounds__(THREADS, 2)
         const uint32_t cb = cb_first + (uint32_t)(local / rows_in_g);
         if (S.mode == MODE_DENSE_SELF && cb < rb) return;  // below the diagonal (only inside a diagonal group)
 
-        tile_counts<CountT>(A, B, rb, cb, E.k0, E.nk, stage_mem, full_bar, counts, E.kp, S.one, git);
+        tile_counts<CountT, COLS>(A, B, rb, cb, E.k0, E.nk, stage_mem, full_bar, counts, E.kp, S.one, S.row_end, git);
 
         const uint64_t nA = A.n, nB = B.n;
         for (int m = 0; m < (TS * TS) / THREADS; ++m) {
@@ -448,6 +463,8 @@ __global__ void __launch_bounds__(THREADS, 2)
                     idx = (gi - S.row_begin) * S.rect_ld + (gj - S.rect_c0);
                 else
                     idx = nA * gi - ((gi * (gi + 1)) >> 1) + gj - 1 - gi - S.out_base;  // square_to_condensed
+            } else if (rect) {
+                idx = (gi - S.row_begin) * S.rect_ld + gj;  // ref-major kNN keys for select_kernel
             } else {
                 idx = (gi - S.row_begin) * nB + gj;  // ref-major
             }
@@ -525,7 +542,7 @@ __global__ void __launch_bounds__(THREADS, 2)
     __syncthreads();
 
     for (uint32_t cb = cb_lo; cb < cb_hi; ++cb) {
-        tile_counts<CountT>(A, B, rb, cb, E.k0, E.nk, stage_mem, full_bar, counts, E.kp, S.one, git);
+        tile_counts<CountT, COLS>(A, B, rb, cb, E.k0, E.nk, stage_mem, full_bar, counts, E.kp, S.one, S.row_end, git);
         for (int m = 0; m < (TS * TS) / THREADS; ++m) {
             const int pair = m * THREADS + tid;
             const int row = pair / TS;
@@ -588,16 +605,26 @@ cudaError_t launch_tiles(const DevDb &A, const DevDb &B, const EpiParams &E, con
                          bool count32, size_t smem, cudaStream_t st) {
     if (n_ctas == 0) return cudaSuccess;
     if (n_ctas > 0x7fffffffull) return cudaErrorInvalidConfiguration;
-    cudaError_t err;
-    if (count32) {
-        err = cudaFuncSetAttribute(tile_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return err;
-        tile_kernel<uint32_t><<<(unsigned)n_ctas, THREADS, smem, st>>>(A, B, E, S);
-    } else {
-        err = cudaFuncSetAttribute(tile_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (err != cudaSuccess) return err;
-        tile_kernel<uint16_t><<<(unsigned)n_ctas, THREADS, smem, st>>>(A, B, E, S);
-    }
+    // Narrow-column variants: when the column side has at most 8 / 16 / 32 samples (a handful of queries against a
+    // large reference database) only those columns are loaded and compared.
+    const int cols = S.mode == MODE_KNN || TJ != 4 ? TS : (B.n <= 8 ? 8 : B.n <= 16 ? 16 : B.n <= 32 ? 32 : TS);
+    cudaError_t err = cudaSuccess;
+#define SKD_LAUNCH(T, C)                                                                                      \
+    do {                                                                                                      \
+        err = cudaFuncSetAttribute(tile_kernel<T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (err != cudaSuccess) return err;                                                                   \
+        tile_kernel<T, C><<<(unsigned)n_ctas, THREADS, smem, st>>>(A, B, E, S);                                \
+    } while (0)
+#define SKD_LAUNCH_COLS(T)                          \
+    do {                                            \
+        if (cols == 8) SKD_LAUNCH(T, 8);            \
+        else if (cols == 16) SKD_LAUNCH(T, 16);     \
+        else if (cols == 32) SKD_LAUNCH(T, 32);     \
+        else SKD_LAUNCH(T, TS);                     \
+    } while (0)
+    if (count32) SKD_LAUNCH_COLS(uint32_t); else SKD_LAUNCH_COLS(uint16_t);
+#undef SKD_LAUNCH_COLS
+#undef SKD_LAUNCH
     return cudaGetLastError();
 }
 
@@ -665,11 +692,15 @@ void launch_knn_merge(const unsigned long long *part_key, const float *part_aux,
 // One CTA owns 64 targets (rows or columns of D), streams 64x64 sub-tiles of D through shared memory and
 // keeps, per target, the running list L[target][knn] (sorted composites) topped up through a 128-slot
 // buffer with threshold rejection, exactly like the tile kernel's kNN epilogue.
+// cross != 0 (COLS only): D is a ref-major cross matrix (rows = references g0.., columns = all n queries); every
+// row is a candidate of every column, the stored neighbour index is row + idx_offset, and blockIdx.y splits the
+// rows into slices of rows_per_split with one list set per slice (Lkey + slice * part_stride).
 template <bool COLS, bool AUX>
 __global__ void __launch_bounds__(256) select_kernel(const float *__restrict__ D, uint64_t ld, uint64_t g0, uint32_t R,
                                                      uint64_t c0, uint64_t n, uint64_t t0, uint64_t t1,
                                                      unsigned long long *__restrict__ Lkey, float *__restrict__ Laux,
-                                                     uint32_t knn) {
+                                                     uint32_t knn, int cross, uint64_t idx_offset,
+                                                     uint32_t rows_per_split, uint64_t part_stride) {
     constexpr int CAP = 128;
     extern __shared__ __align__(16) unsigned char sm_raw[];
     unsigned long long *buf = reinterpret_cast<unsigned long long *>(sm_raw);           // [64][CAP]
@@ -680,6 +711,15 @@ __global__ void __launch_bounds__(256) select_kernel(const float *__restrict__ D
     uint32_t *cnt = reinterpret_cast<uint32_t *>(thr + TS);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint64_t tbase = t0 + (uint64_t)blockIdx.x * TS;  // first target (global sample index) of this CTA
+    if (cross) {  // this CTA's slice of the rows and its own list set
+        const uint64_t lo = (uint64_t)blockIdx.y * rows_per_split;
+        const uint64_t hi = lo + rows_per_split < R ? lo + rows_per_split : R;
+        Lkey += (uint64_t)blockIdx.y * part_stride;
+        if (AUX) Laux += (uint64_t)blockIdx.y * part_stride;
+        g0 += lo;
+        D += lo * ld * (AUX ? 2 : 1);
+        R = (uint32_t)(hi - lo);
+    }
 
     // start from the lists accumulated so far
     for (int e = tid; e < TS * CAP; e += 256) {
@@ -707,14 +747,14 @@ __global__ void __launch_bounds__(256) select_kernel(const float *__restrict__ D
     // ROWS: targets are rows i in [tbase, +64), candidates are columns j in (i, n)
     // COLS: targets are columns j, candidates are rows i in [g0, min(j, g0 + R))
     const uint64_t s_begin = COLS ? g0 : (tbase + 1 > c0 ? tbase + 1 : c0);
-    const uint64_t s_end = COLS ? (g0 + R < tbase + TS ? g0 + R : tbase + TS) : n;
+    const uint64_t s_end = COLS ? (cross || g0 + R < tbase + TS ? g0 + R : tbase + TS) : n;
     for (uint64_t sb = s_begin / TS * TS; sb < s_end; sb += TS) {
         // load D sub-tile: ROWS: rows = targets, cols = sb..sb+63 ; COLS: rows = sb.., cols = targets
         for (int e = tid; e < TS * TS; e += 256) {
             const int r = e / TS, c = e % TS;
             const uint64_t gi = COLS ? sb + r : tbase + r, gj = COLS ? tbase + c : sb + c;
             float k = 0.f, a = 0.f;
-            if (gi >= g0 && gi < g0 + R && gj < n && gj > gi && gj >= c0) {
+            if (gi >= g0 && gi < g0 + R && gj < n && (cross || gj > gi) && gj >= c0) {
                 const uint64_t off = (gi - g0) * ld + (gj - c0);
                 if (AUX) {
                     float2 v = __ldcs(reinterpret_cast<const float2 *>(D) + off);
@@ -738,11 +778,12 @@ __global__ void __launch_bounds__(256) select_kernel(const float *__restrict__ D
                 const int s = lane + 32 * h;
                 const uint64_t cand = sb + s;  // global index of the candidate sample
                 const uint64_t gi = COLS ? cand : tg, gj = COLS ? tg : cand;
-                bool ok = gi >= g0 && gi < g0 + R && gj < n && gj > gi && gj >= c0;
+                bool ok = gi >= g0 && gi < g0 + R && gj < n && (cross || gj > gi) && gj >= c0;
                 const int r = COLS ? s : t, cc = COLS ? t : s;
                 unsigned long long comp = 0;
                 if (ok) {
-                    comp = ((unsigned long long)float_order_bits(tkey[r * (TS + 1) + cc]) << 32) | (uint32_t)cand;
+                    comp = ((unsigned long long)float_order_bits(tkey[r * (TS + 1) + cc]) << 32) |
+                           (uint32_t)(cand + idx_offset);
                     ok = comp < th;
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, ok);
@@ -778,9 +819,10 @@ __global__ void __launch_bounds__(256) select_kernel(const float *__restrict__ D
 
 cudaError_t launch_select(bool cols, bool aux, const float *D, uint64_t ld, uint64_t g0, uint32_t R, uint64_t c0,
                           uint64_t n, uint64_t t0, uint64_t t1, unsigned long long *Lkey, float *Laux, uint32_t knn,
-                          cudaStream_t st) {
+                          cudaStream_t st, int cross, uint64_t idx_offset, uint32_t n_splits, uint32_t rows_per_split,
+                          uint64_t part_stride) {
     if (t1 <= t0) return cudaSuccess;
-    const unsigned grid = (unsigned)((t1 - t0 + TS - 1) / TS);
+    const dim3 grid((unsigned)((t1 - t0 + TS - 1) / TS), cross ? n_splits : 1u);
     size_t smem = (size_t)TS * 128 * 8 + (aux ? (size_t)TS * 128 * 4 : 0) + (size_t)TS * (TS + 1) * 4 * (aux ? 2 : 1) +
                   TS * 8 + TS * 4;
     cudaError_t err;
@@ -788,7 +830,8 @@ cudaError_t launch_select(bool cols, bool aux, const float *D, uint64_t ld, uint
     do {                                                                                                         \
         err = cudaFuncSetAttribute(select_kernel<C, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (err != cudaSuccess) return err;                                                                      \
-        select_kernel<C, A><<<grid, 256, smem, st>>>(D, ld, g0, R, c0, n, t0, t1, Lkey, Laux, knn);               \
+        select_kernel<C, A><<<grid, 256, smem, st>>>(D, ld, g0, R, c0, n, t0, t1, Lkey, Laux, knn, cross,        \
+                                                     idx_offset, rows_per_split, part_stride);                  \
     } while (0)
     if (cols && aux) SKD_SEL(true, true);
     else if (cols) SKD_SEL(true, false);

@@ -24,7 +24,8 @@ void launch_knn_merge(const unsigned long long *part_key, const float *part_aux,
 
 cudaError_t launch_select(bool cols, bool aux, const float *D, uint64_t ld, uint64_t g0, uint32_t R, uint64_t c0,
                           uint64_t n, uint64_t t0, uint64_t t1, unsigned long long *Lkey, float *Laux, uint32_t knn,
-                          cudaStream_t st);
+                          cudaStream_t st, int cross = 0, uint64_t idx_offset = 0, uint32_t n_splits = 1,
+                          uint32_t rows_per_split = 0, uint64_t part_stride = 0);
 
 void launch_knn_finalize(const unsigned long long *keys, const float *aux, uint32_t n_parts, uint64_t part_stride,
                          uint64_t row0, uint64_t n_rows, uint32_t knn, int kind, unsigned long long *idx_out,
