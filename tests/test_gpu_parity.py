@@ -510,3 +510,42 @@ def test_precluster_vs_oracle(sk, ctx, retain):
     got = sk.self_dists_knn_precluster(g, skq, db.names, 5, sk.set_k(g, 21), completeness_vec=cv)
     oidx, od0 = oracle.self_dists_knn_precluster(db, off, idx, 5, 1, completeness=cv)
     assert np.abs(got.d0.astype(np.float64) - od0).max() <= TOL
+
+
+# ------------------------------------------------------------------ few queries: narrow-column kernels, HBM-bound path
+@pytest.mark.parametrize("nq", [1, 7, 8, 9, 16, 17, 32, 33, 64])
+def test_cross_with_few_queries(sk, ctx, nq):
+    ref = synth_db(330, 16, [17, 21, 25, 29], seed=90, n_families=5)
+    qry = synth_db(nq, 16, [17, 21, 25, 29], seed=90, n_families=5)
+    gr, gq = up(sk, ctx, ref), up(sk, ctx, qry)
+    # raw counts through the (narrow) tiled kernel, refs x queries x K
+    want = oracle.match_counts(ref, qry, all_pairs(330, nq)).reshape(330, nq, 4)
+    assert np.array_equal(sk.match_counts(gr, gq), want)
+    check_close(sk.cross_dists_all(gr, gq, dist_type=sk.set_k(gr)).distances, oracle.cross_dists_all(ref, qry, threads=4))
+    assert np.array_equal(sk.cross_dists_all(gr, gq, dist_type=sk.set_k(gr, 21, ani=True)).distances,
+                          oracle.cross_dists_all(ref, qry, k_idx=1, ani=True, threads=4))
+    # kNN through dense keys + column select
+    got = sk.cross_dists_knn(gr, gq, knn=11, dist_type=sk.set_k(gr, 21))
+    oidx, od0, _ = oracle.cross_dists_knn(ref, qry, 11, k_idx=1, threads=4)
+    assert_knn_matches(got.idx, got.d0, None, oidx, od0, None, True)
+    gotc = sk.cross_dists_knn(gr, gq, knn=11, dist_type=sk.set_k(gr))
+    oidx, od0, od1 = oracle.cross_dists_knn(ref, qry, 11, threads=4)
+    assert_knn_matches(gotc.idx, gotc.d0, gotc.d1, oidx, od0, od1, False)
+
+
+def test_few_queries_knn_equals_row_owned_path(sk, ctx):
+    ref = synth_db(900, 16, [17, 21, 25, 29], seed=91, n_families=12)
+    qry = synth_db(40, 16, [17, 21, 25, 29], seed=91, n_families=12)
+    plain = fresh_ctx(sk, SKD_KNN_SYMMETRIC=0)  # also disables the few-queries route
+    tiny = fresh_ctx(sk, SKD_SYM_CHUNK_MB=1)    # several reference chunks and row slices
+    try:
+        outs = []
+        for c in (ctx, plain, tiny):
+            gr, gq = up(sk, c, ref), up(sk, c, qry)
+            outs.append(sk.cross_dists_knn(gr, gq, knn=25, dist_type=sk.set_k(gr)))
+        for o in outs[1:]:
+            assert np.array_equal(o.idx, outs[0].idx) and np.array_equal(o.d0, outs[0].d0) and np.array_equal(o.d1, outs[0].d1)
+    finally:
+        fresh_ctx(sk, SKD_SYM_CHUNK_MB=2048).close()
+        plain.close()
+        tiny.close()
