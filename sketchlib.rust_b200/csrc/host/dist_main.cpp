@@ -4,7 +4,8 @@
 // of src/cli.rs:88-104), control flow of src/lib.rs:303-453 (extension stripping, --subset via
 // read_sketch_data_block, completeness files, set_k, knn clamping :379-382 / :411-414), and the text
 // writers of src/distances/distance_matrix.rs:175-209 (dense) and :360-401 (sparse), byte for byte.
-// Only `dist` is implemented: the other sub-commands are not on the accelerated path.
+// `dist` is the accelerated path; `sketch` (DNA FASTA only, CPU, sketcher.cpp) is shipped so that inputs can be made
+// without the Rust binary.  The other sub-commands are not implemented.
 // Extra flag: --gpu <id> (default 0).  --threads is accepted for compatibility (the work runs on the GPU).
 #include <algorithm>
 #include <atomic>
@@ -13,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <stdexcept>
+#include <fstream>
 #include <functional>
 #include <string>
 #include <thread>
@@ -22,6 +24,12 @@
 #include "multisketch.hpp"
 
 using namespace skdhost;
+
+namespace skdhost {
+void sketch_files_dna(const std::string &output_prefix,
+                      const std::vector<std::pair<std::string, std::vector<std::string>>> &inputs,
+                      std::vector<uint64_t> kmers, uint64_t sketch_size, bool rc, int threads);
+}
 
 namespace {
 
@@ -137,7 +145,7 @@ DistArgs parse_args(int argc, char **argv) {
         } else if (!saw_dist) {
             if (t != "dist")
                 throw UsageError("unrecognized subcommand '" + t +
-                                 "': this build implements only `dist` (the B200-accelerated path)");
+                                 "': this build implements only `dist` (the B200-accelerated path) and `sketch` (DNA)");
             saw_dist = true;
         } else {
             pos.push_back(t);
@@ -447,8 +455,123 @@ int run(const DistArgs &a) {
 
 }  // namespace
 
+// ---- `sketchlib sketch`: flags of src/cli.rs:128-182 that apply to DNA assemblies
+int run_sketch(int argc, char **argv) {
+    std::vector<std::string> seq_files;
+    std::string file_list, output;
+    std::vector<uint64_t> k_vals, k_seq;
+    uint64_t sketch_size = 1000;  // DEFAULT_SKETCHSIZE, src/cli.rs:17-19
+    bool single_strand = false, verbose = false, quiet = false;
+    long long threads = 1;
+    auto split_u64 = [](const std::string &v, const char *what) {
+        std::vector<uint64_t> out;
+        size_t pos = 0;
+        while (pos <= v.size()) {
+            size_t c = v.find(',', pos);
+            if (c == std::string::npos) c = v.size();
+            out.push_back((uint64_t)parse_uint(v.substr(pos, c - pos), what));
+            pos = c + 1;
+        }
+        return out;
+    };
+    bool saw = false;
+    for (int i = 1; i < argc; ++i) {
+        std::string t = argv[i];
+        auto value = [&](const char *name) -> std::string {
+            size_t eq = t.find('=');
+            if (t.rfind("--", 0) == 0 && eq != std::string::npos) return t.substr(eq + 1);
+            if (t.rfind("--", 0) != 0 && t.size() > 2) return t[2] == '=' ? t.substr(3) : t.substr(2);
+            if (i + 1 >= argc) throw UsageError(std::string("a value is required for '") + name + "' but none was supplied");
+            return argv[++i];
+        };
+        auto is = [&](const char *name) { return t == name || t.rfind(std::string(name) + "=", 0) == 0; };
+        if (t == "-v" || t == "--verbose") verbose = true;
+        else if (t == "--quiet") quiet = true;
+        else if (t == "--single-strand") single_strand = true;
+        else if (is("--k-vals")) k_vals = split_u64(value("--k-vals <K_VALS>"), "--k-vals <K_VALS>");
+        else if (is("--k-seq")) k_seq = split_u64(value("--k-seq <K_SEQ>"), "--k-seq <K_SEQ>");
+        else if (is("--sketch-size")) sketch_size = (uint64_t)parse_uint(value("--sketch-size"), "--sketch-size <SKETCH_SIZE>");
+        else if (is("--threads")) threads = parse_uint(value("--threads"), "--threads <THREADS>");
+        else if (is("--seq-type")) {
+            if (value("--seq-type") != "dna") throw UsageError("this build sketches DNA only (--seq-type dna)");
+        } else if (is("--min-count") || is("--min-qual") || is("--level")) (void)value("option");
+        else if (t == "--concat-fasta") throw UsageError("--concat-fasta currently only supported with --seq-type aa");
+        else if (t.rfind("-k", 0) == 0 && t.rfind("--", 0) != 0) k_vals = split_u64(value("-k <K_VALS>"), "-k <K_VALS>");
+        else if (t.rfind("-s", 0) == 0 && t.rfind("--", 0) != 0) sketch_size = (uint64_t)parse_uint(value("-s"), "-s <SKETCH_SIZE>");
+        else if (t.rfind("-f", 0) == 0 && t.rfind("--", 0) != 0) file_list = value("-f <FILE_LIST>");
+        else if (t.rfind("-o", 0) == 0 && t.rfind("--", 0) != 0) output = value("-o <OUTPUT>");
+        else if (t.size() > 1 && t[0] == '-') throw UsageError("unexpected argument '" + t + "' found");
+        else if (!saw) saw = true;  // the sub-command word itself
+        else seq_files.push_back(t);
+    }
+    g_level = quiet ? 0 : (verbose ? 2 : 1);
+    if (output.empty()) throw UsageError("the following required arguments were not provided:\n  -o <OUTPUT>");
+    if (file_list.empty() == seq_files.empty())
+        throw UsageError("exactly one of <SEQ_FILES>... and -f <FILE_LIST> is required");
+    if (k_vals.empty() == k_seq.empty()) throw UsageError("exactly one of --k-vals and --k-seq is required");
+    std::vector<uint64_t> kmers = k_vals;
+    if (!k_seq.empty()) {  // parse_kmers: (start..=end).step_by(step), src/io.rs:140-160
+        if (k_seq.size() != 3 || k_seq[2] == 0) throw UsageError("--k-seq takes start,end,step");
+        for (uint64_t k = k_seq[0]; k <= k_seq[1]; k += k_seq[2]) kmers.push_back(k);
+    }
+    std::vector<std::pair<std::string, std::vector<std::string>>> inputs;
+    if (!file_list.empty()) {  // get_input_list: src/io.rs:182-224
+        std::ifstream in(file_list);
+        if (!in) throw Panic("Unable to open file_list " + file_list);
+        std::string line;
+        while (std::getline(in, line)) {
+            std::vector<std::string> f;
+            size_t pos = 0;
+            while (pos < line.size()) {
+                while (pos < line.size() && isspace((unsigned char)line[pos])) ++pos;
+                size_t e = pos;
+                while (e < line.size() && !isspace((unsigned char)line[e])) ++e;
+                if (e > pos) f.push_back(line.substr(pos, e - pos));
+                pos = e;
+            }
+            if (f.empty()) throw Panic("Unable to parse line in file_list");
+            if (f.size() == 1) inputs.push_back({f[0], {f[0]}});
+            else inputs.push_back({f[0], std::vector<std::string>(f.begin() + 1, f.end())});
+        }
+    } else {  // read_input_fastas: name = file name without directories, src/io.rs:20-38
+        for (auto &file : seq_files) {
+            size_t slash = file.rfind('/');
+            inputs.push_back({slash == std::string::npos ? file : file.substr(slash + 1), {file}});
+        }
+    }
+    log_info("Parsed " + std::to_string(inputs.size()) + " samples in input list");
+    try {
+        sketch_files_dna(output, inputs, kmers, sketch_size, !single_strand, (int)std::max<long long>(1, threads));
+    } catch (const std::exception &e) {
+        throw Panic(e.what());
+    }
+    return 0;
+}
+
 int main(int argc, char **argv) {
     auto start = std::chrono::steady_clock::now();
+    bool is_sketch = false;
+    for (int i = 1; i < argc; ++i) {
+        if (argv[i][0] == '-') continue;
+        is_sketch = std::string(argv[i]) == "sketch";
+        break;
+    }
+    if (is_sketch) {
+        try {
+            run_sketch(argc, argv);
+        } catch (const UsageError &e) {
+            fprintf(stderr, "error: %s\n", e.what());
+            return 2;
+        } catch (const Panic &e) {
+            fprintf(stderr, "thread 'main' panicked:\n%s\n", e.what());
+            return 101;
+        }
+        if (g_level >= 1) {
+            auto secs = std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - start).count();
+            fprintf(stderr, "\xF0\x9F\xA7\xAC\xF0\x9F\x96\x8B\xEF\xB8\x8F sketchlib done in %llds\n", (long long)secs);
+        }
+        return 0;
+    }
     DistArgs a;
     try {
         a = parse_args(argc, argv);

@@ -100,7 +100,7 @@ def test_cli_host_side_errors(tools, tmp_path):
     assert r.returncode == 2 and "-k <KMER>" in r.stderr                     # clap: requires("kmer")
     r = run([cli, "dist"])
     assert r.returncode == 2 and "<REF_DB>" in r.stderr
-    r = run([cli, "sketch", "x"])
+    r = run([cli, "merge", "x", "y"])
     assert r.returncode == 2 and "only `dist`" in r.stderr
     r = run([cli, "dist", db, "--threads", "0"])
     assert r.returncode == 2
@@ -183,3 +183,79 @@ def test_cli_dense_and_cross_modes(tools, tmp_path):
     # self kNN with knn >= n clamps to n-1 with a warning (src/lib.rs:379-382)
     r = run([cli, "dist", qp, "--knn", "50", "-k", "21"])
     assert len(r.stdout.splitlines()) == 9 * 8 and "knn=50 is higher than number of samples=9" in r.stderr
+
+
+# ---------------------------------------------------------------- `sketchlib sketch` (CPU tool, DNA FASTA)
+def _write_fasta(path, records, gz=False, width=60):
+    import gzip
+    text = "".join(f">{name} some description\n" + "\n".join(seq[i:i + width] for i in range(0, len(seq), width)) + "\n"
+                   for name, seq in records)
+    if gz:
+        with gzip.open(path, "wt") as fh:
+            fh.write(text)
+    else:
+        with open(path, "w") as fh:
+            fh.write(text)
+
+
+def test_sketch_cli_matches_oracle_sketcher(tools, tmp_path):
+    cli, skm_info = tools
+    rng = np.random.default_rng(11)
+    def rand_seq(n):
+        return "".join(rng.choice(list("ACGT"), size=n))
+    anc = rand_seq(30000)
+    mut = list(anc)
+    for p in rng.choice(len(mut), size=600, replace=False):
+        mut[p] = "ACGT"[("ACGT".index(mut[p]) + 1) % 4]
+    a = [("c1", anc[:12000] + "NNNN" + anc[12000:20000].lower()), ("c2", anc[20000:]), ("tiny", "ACGTAC")]
+    b = [("c1", "".join(mut)[:15000] + "RYK" + "".join(mut)[15000:])]
+    _write_fasta(tmp_path / "a.fa", a)
+    _write_fasta(tmp_path / "b.fasta.gz", b, gz=True)
+    _write_fasta(tmp_path / "b2.fa", [("extra", rand_seq(5000))])
+    rfile = tmp_path / "rfile.txt"
+    rfile.write_text(f"sampleA\t{tmp_path / 'a.fa'}\nsampleB\t{tmp_path / 'b.fasta.gz'}\t{tmp_path / 'b2.fa'}\n")
+    out = str(tmp_path / "db")
+    r = run([cli, "sketch", "-o", out, "--k-seq", "15,27,4", "-s", "200", "-f", str(rfile), "--threads", "2", "--quiet"])
+    assert r.returncode == 0, r.stderr
+    got = np.fromfile(out + ".skd", dtype="<u8")
+    kmers = [15, 19, 23, 27]
+    recs_a = [s.encode() for _, s in a]
+    recs_b = [b[0][1].encode()] + oracle.read_fasta_records(str(tmp_path / "b2.fa"))
+    want = np.concatenate([oracle.sketch_dna(recs_a, kmers, 200)[0], oracle.sketch_dna(recs_b, kmers, 200)[0]])
+    assert np.array_equal(got, want)
+    ms = oracle.MultiSketch(out).read_sketch_data()       # our .skm is readable by the independent reader
+    assert ms.names() == ["sampleA", "sampleB"] and ms.kmer_lengths == kmers and ms.sketch_size == 256
+    assert ms.sketch_metadata[0]["non_acgt"] == 4 and ms.sketch_metadata[1]["non_acgt"] == 3
+    assert ms.sketch_metadata[0]["seq_length"] == 30000 + 6
+    info = parse_info(run([skm_info, out]).stdout)        # ... and by the C++ reader
+    assert info["samples"] == [("sampleA", 0), ("sampleB", 1)] and info["kmer_lengths"] == kmers
+    # single strand changes the hashes; positional FASTA arguments name samples by file name
+    r = run([cli, "sketch", "-o", out + "_ss", "--k-vals", "19", "-s", "200", "--single-strand", str(tmp_path / "a.fa")])
+    assert r.returncode == 0
+    ss = np.fromfile(out + "_ss.skd", dtype="<u8")
+    assert np.array_equal(ss, oracle.sketch_dna(recs_a, [19], 200, rc=False)[0])
+    assert oracle.MultiSketch(out + "_ss").names() == ["a.fa"]
+    # errors: reads, k too long for every contig, missing file, missing k
+    fq = tmp_path / "r.fastq"
+    fq.write_text("@r1\nACGT\n+\nIIII\n")
+    assert run([cli, "sketch", "-o", out, "--k-vals", "3", str(fq)]).returncode == 101
+    _write_fasta(tmp_path / "short.fa", [("s", "ACGTACGT")])
+    r = run([cli, "sketch", "-o", out, "--k-vals", "21", str(tmp_path / "short.fa")])
+    assert r.returncode == 101 and "K-mer larger than smallest valid sequence" in r.stderr
+    assert run([cli, "sketch", "-o", out, "--k-vals", "21", str(tmp_path / "nope.fa")]).returncode == 101
+    assert run([cli, "sketch", "-o", out, str(tmp_path / "a.fa")]).returncode == 2
+
+
+def test_sketch_cli_reproduces_reference_skd():
+    ref_in = "/root/reference/tests/test_files_in"
+    if not os.path.exists(os.path.join(ref_in, "rfile.txt")):
+        pytest.skip("reference checkout not present (GPU box)")
+    import tempfile
+    import sketchlib.rust_b200.build as b
+    cli, _ = b.build_host()
+    with tempfile.TemporaryDirectory() as d:
+        for name, k, s in (("sketches1", "31", "1000"), ("sketches2", "31", "10000"), ("sketches3", "21", "1000")):
+            r = run([cli, "sketch", "-o", os.path.join(d, name), "--k-vals", k, "-s", s, "-f", "rfile.txt", "--threads", "4"],
+                    cwd=ref_in)
+            assert r.returncode == 0, r.stderr
+            assert open(os.path.join(d, name + ".skd"), "rb").read() == open(os.path.join(FIXTURES, name + ".skd"), "rb").read()
