@@ -549,3 +549,47 @@ def test_few_queries_knn_equals_row_owned_path(sk, ctx):
         fresh_ctx(sk, SKD_SYM_CHUNK_MB=2048).close()
         plain.close()
         tiny.close()
+
+
+# ------------------------------------------------------------------ randomized differential sweep
+def test_random_shapes_against_oracle(sk, ctx):
+    rng = np.random.default_rng(2026)
+    for trial in range(36):
+        n = int(rng.integers(2, 180))
+        nq = int(rng.integers(1, 90))
+        W = int(rng.choice([1, 2, 3, 5, 16, 17]))
+        K = int(rng.integers(1, 10))
+        kmers = sorted(rng.choice(np.arange(5, 61), size=K, replace=False).tolist())
+        a = synth_db(n, W, kmers, seed=1000 + trial, n_families=max(1, n // 12), unrelated_frac=0.1)
+        b = synth_db(nq, W, kmers, seed=2000 + trial, n_families=max(1, n // 12))
+        # make some queries related to refs: copy a few reference sketches into the query set
+        take = rng.integers(0, n, size=max(1, nq // 3))
+        bb = b.bins.reshape(nq, -1).copy()
+        bb[: len(take)] = a.bins.reshape(n, -1)[take]
+        b = oracle.Db(bb.reshape(-1), nq, kmers, W)
+        ga, gb = up(sk, ctx, a), up(sk, ctx, b)
+        tag = f"trial {trial}: n={n} nq={nq} W={W} kmers={kmers}"
+        # integer parity, dense tile path
+        assert np.array_equal(sk.match_counts(ga, gb), oracle.match_counts(a, b, all_pairs(n, nq)).reshape(n, nq, K)), tag
+        kidx = int(rng.integers(0, K))
+        ani = bool(rng.integers(0, 2))
+        dtj = sk.set_k(ga, kmers[kidx], ani=ani)
+        assert np.array_equal(sk.self_dists_all(ga, dist_type=dtj).distances, oracle.self_dists_all(a, k_idx=kidx, ani=ani)), tag
+        assert np.array_equal(sk.cross_dists_all(ga, gb, dist_type=dtj).distances,
+                              oracle.cross_dists_all(a, b, k_idx=kidx, ani=ani)), tag
+        knn = int(rng.integers(1, min(n - 1, 70) + 1))
+        got = sk.self_dists_knn(ga, knn=knn, dist_type=dtj)
+        oidx, od0, _ = oracle.self_dists_knn(a, knn, k_idx=kidx, ani=ani)
+        assert np.array_equal(got.d0, od0), tag
+        gotx = sk.cross_dists_knn(ga, gb, knn=knn, dist_type=dtj)
+        oidx, od0, _ = oracle.cross_dists_knn(a, b, knn, k_idx=kidx, ani=ani)
+        assert np.array_equal(gotx.d0, od0), tag
+        if K >= 2:
+            dt = sk.set_k(ga)
+            check_close(sk.self_dists_all(ga, dist_type=dt).distances, oracle.self_dists_all(a))
+            check_close(sk.cross_dists_all(ga, gb, dist_type=dt).distances, oracle.cross_dists_all(a, b))
+            got = sk.self_dists_knn(ga, knn=knn, dist_type=dt)
+            oidx, od0, od1 = oracle.self_dists_knn(a, knn)
+            assert_knn_matches(got.idx, got.d0, got.d1, oidx, od0, od1, False)
+        ga.free()
+        gb.free()

@@ -259,3 +259,40 @@ def test_sketch_cli_reproduces_reference_skd():
                     cwd=ref_in)
             assert r.returncode == 0, r.stderr
             assert open(os.path.join(d, name + ".skd"), "rb").read() == open(os.path.join(FIXTURES, name + ".skd"), "rb").read()
+
+
+@pytest.mark.gpu
+def test_full_pipeline_fasta_to_distances(tools, tmp_path):
+    """FASTA -> `sketchlib sketch` -> .skm/.skd -> `sketchlib dist` on the GPU, against the oracle end to end
+    (oracle sketcher + oracle distances on the same sequences)."""
+    cli, _ = tools
+    rng = np.random.default_rng(21)
+    anc = rng.choice(list("ACGT"), size=60000)
+    names, recs = [], {}
+    for g in range(6):
+        seq = anc.copy()
+        pos = rng.choice(len(seq), size=300 * (g + 1), replace=False)
+        seq[pos] = rng.choice(list("ACGT"), size=len(pos))
+        if g % 2:
+            seq = np.concatenate([seq[:20000], seq[26000:]])  # accessory deletion
+        s = "".join(seq)
+        _write_fasta(tmp_path / f"g{g}.fa", [("chr", s[:35000]), ("plasmid", s[35000:])], gz=(g % 3 == 0))
+        names.append(f"g{g}.fa")
+        recs[names[-1]] = [s[:35000].encode(), s[35000:].encode()]
+    files = [str(tmp_path / n) for n in names]
+    out = str(tmp_path / "db")
+    assert run([cli, "sketch", "-o", out, "--k-seq", "13,29,4", "-s", "1000", "--threads", "3"] + files).returncode == 0
+    kmers = [13, 17, 21, 25, 29]
+    bins = np.concatenate([oracle.sketch_dna(recs[n], kmers, 1000)[0] for n in names])
+    db = oracle.Db(bins, 6, kmers, 16, names=names)
+    r = run([cli, "dist", out])
+    assert r.returncode == 0, r.stderr
+    want = oracle.self_dists_all(db)
+    rows = [l.split("\t") for l in r.stdout.splitlines()]
+    assert len(rows) == 15 and [row[:2] for row in rows[:2]] == [["g0.fa", "g1.fa"], ["g0.fa", "g2.fa"]]
+    got = np.array([[float(row[2]), float(row[3])] for row in rows], dtype=np.float32).ravel()
+    assert np.abs(got.astype(np.float64) - want).max() <= 1e-6
+    assert 0 < got[0] < 0.2 and got[1] > 0.01  # related genomes with accessory differences
+    r = run([cli, "dist", out, "-k", "21", "--knn", "2"])
+    oidx, od0, _ = oracle.self_dists_knn(db, 2, k_idx=2)
+    assert [l.split("\t")[2] for l in r.stdout.splitlines()] == [oracle.fmt_f32(v) for v in od0.ravel()]
