@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -62,6 +63,7 @@ struct DistArgs {
     std::string ref_completeness_file, query_completeness_file;
     double completeness_cutoff = 0.64;
     int gpu = 0;
+    int gpus = 1;
     bool verbose = false, quiet = false;
 };
 
@@ -81,6 +83,7 @@ const char *USAGE =
     "      --query-completeness-file <F>  Query completeness estimates (cross-query mode only)\n"
     "      --completeness-cutoff <X>      Minimum c1*c2 for the completeness correction [default: 0.64]\n"
     "      --gpu <ID>                     CUDA device [default: 0]\n"
+    "      --gpus <N>                     Use devices 0..N-1 for --knn runs (one host thread and context per device)\n"
     "  -v, --verbose                      Show progress messages\n"
     "      --quiet                        Don't show any messages\n";
 
@@ -133,6 +136,9 @@ DistArgs parse_args(int argc, char **argv) {
             a.completeness_cutoff = strtod(v.c_str(), &end);
             if (v.empty() || end != v.c_str() + v.size())
                 throw UsageError("invalid value '" + v + "' for '--completeness-cutoff <COMPLETENESS_CUTOFF>'");
+        } else if (is("--gpus")) {
+            a.gpus = (int)parse_uint(value("--gpus <N>"), "--gpus <N>");
+            if (a.gpus < 1) throw UsageError("invalid value for '--gpus <N>': at least one device is needed");
         } else if (is("--gpu")) {
             a.gpu = (int)parse_uint(value("--gpu <ID>"), "--gpu <ID>");
         } else if (t.rfind("-o", 0) == 0 && t.rfind("--", 0) != 0) {
@@ -281,6 +287,133 @@ struct Pinned {
     ~Pinned() { skd_host_free(ctx, p); }
 };
 
+// ---- --gpus N for sparse (kNN) outputs: one host thread + context per device, no device-to-device traffic.
+// Self mode (knn <= 64): every device evaluates an equal-pair block of upper-triangle rows ONCE per unordered
+// pair and returns partial lists for all rows (skd_self_knn_partial).  Cross mode: the references are sharded,
+// each device loads only its part of the .skd (skd_cross_knn_partial).  The partial lists (rows x knn x 12 B per
+// device) are merged on the first device (skd_knn_merge).  Self mode with knn > 64 splits the rows instead.
+struct KnnOut {
+    std::vector<uint64_t> idx;
+    std::vector<float> d0, d1;
+    uint64_t rows = 0, knn = 0;
+};
+
+uint64_t triangle_bound(uint64_t n, int r, int world) {  // same rule as sketchlib.rust_b200.triangle_row_partition
+    if (r <= 0) return 0;
+    if (r >= world) return n;
+    double x = (double)n * (1.0 - std::sqrt(1.0 - (double)r / world));
+    uint64_t b = (uint64_t)std::llround(x / 64.0) * 64;
+    return std::min(n, b);
+}
+
+KnnOut multi_gpu_knn(const DistArgs &a, const MultiSketch &refs, const std::string &ref_prefix,
+                     const std::vector<uint64_t> *subset_idx, const MultiSketch *queries, const std::string &q_prefix,
+                     skd_dist_type dt, uint64_t nn, const double *ref_c, const double *query_c) {
+    const int world = a.gpus;
+    const uint64_t n = refs.number_samples_loaded();
+    const bool cross = queries != nullptr;
+    const uint64_t rows = cross ? queries->number_samples_loaded() : n;
+    const bool with_aux = dt.kind == SKD_CORE_ACC;
+    const bool partial = cross || nn <= 64;
+    std::vector<std::vector<uint64_t>> keys(world);
+    std::vector<std::vector<float>> aux(world), pd0(world), pd1(world);
+    std::vector<std::string> errs(world);
+    std::vector<std::pair<uint64_t, uint64_t>> ranges(world);
+    auto file_indices = [&](uint64_t lo, uint64_t hi) {
+        std::vector<uint64_t> v(hi - lo);
+        for (uint64_t s = lo; s < hi; ++s)
+            v[s - lo] = subset_idx ? (*subset_idx)[s] : refs.sketch_metadata[s].index;
+        return v;
+    };
+    auto worker = [&](int d) {
+        skd_ctx *ctx = nullptr;
+        skd_db *rdb = nullptr, *qdb = nullptr;
+        auto fail = [&](const char *what) {
+            errs[d] = std::string(what) + ": " + skd_last_error(ctx);
+        };
+        if (skd_ctx_create(d, &ctx) != SKD_OK) {
+            errs[d] = std::string("device ") + std::to_string(d) + ": " + skd_last_error(nullptr);
+            return;
+        }
+        do {
+            uint64_t lo = 0, hi = n;  // reference samples this device loads
+            if (cross) {
+                lo = n * d / world;
+                hi = n * (d + 1) / world;
+            }
+            std::vector<uint64_t> fi = file_indices(lo, hi);
+            if (skd_db_load_skd(ctx, (ref_prefix + ".skd").c_str(), fi.data(), hi - lo, refs.sample_stride, refs.kmer_stride,
+                                refs.sketchsize64, refs.sketch_size, refs.kmer_lengths.data(),
+                                (uint32_t)refs.kmer_lengths.size(), &rdb) != SKD_OK) {
+                fail("loading references");
+                break;
+            }
+            if (cross) {
+                if (skd_db_load_skd(ctx, (q_prefix + ".skd").c_str(), nullptr, rows, queries->sample_stride,
+                                    queries->kmer_stride, queries->sketchsize64, queries->sketch_size,
+                                    queries->kmer_lengths.data(), (uint32_t)queries->kmer_lengths.size(), &qdb) != SKD_OK) {
+                    fail("loading queries");
+                    break;
+                }
+                keys[d].resize(rows * nn);
+                if (with_aux) aux[d].resize(rows * nn);
+                if (skd_cross_knn_partial(ctx, rdb, qdb, nn, dt, ref_c ? ref_c + lo : nullptr, query_c, a.completeness_cutoff,
+                                          lo, keys[d].data(), with_aux ? aux[d].data() : nullptr, SKD_HOST) != SKD_OK)
+                    fail("cross kNN");
+            } else if (partial) {
+                const uint64_t r0 = triangle_bound(n, d, world), r1 = triangle_bound(n, d + 1, world);
+                keys[d].resize(n * nn);
+                if (with_aux) aux[d].resize(n * nn);
+                if (skd_self_knn_partial(ctx, rdb, nn, dt, ref_c, a.completeness_cutoff, r0, r1, keys[d].data(),
+                                         with_aux ? aux[d].data() : nullptr, SKD_HOST) != SKD_OK)
+                    fail("self kNN");
+            } else {
+                const uint64_t r0 = n * d / world, r1 = n * (d + 1) / world;
+                ranges[d] = {r0, r1};
+                keys[d].resize((r1 - r0) * nn);  // neighbour indices of this device's rows
+                pd0[d].resize((r1 - r0) * nn);
+                if (with_aux) pd1[d].resize((r1 - r0) * nn);
+                if (skd_self_dists_knn(ctx, rdb, nn, dt, ref_c, a.completeness_cutoff, r0, r1, keys[d].data(), pd0[d].data(),
+                                       with_aux ? pd1[d].data() : nullptr, SKD_HOST) != SKD_OK)
+                    fail("self kNN");
+            }
+        } while (false);
+        if (rdb) skd_db_free(rdb);
+        if (qdb) skd_db_free(qdb);
+        skd_ctx_destroy(ctx);
+    };
+    std::vector<std::thread> pool;
+    for (int d = 0; d < world; ++d) pool.emplace_back(worker, d);
+    for (auto &t : pool) t.join();
+    for (auto &e : errs)
+        if (!e.empty()) throw std::runtime_error(e);
+    KnnOut out;
+    out.rows = rows;
+    out.knn = nn;
+    out.idx.resize(rows * nn);
+    out.d0.resize(rows * nn);
+    if (with_aux) out.d1.resize(rows * nn);
+    if (!partial) {  // row-split: concatenate
+        for (int d = 0; d < world; ++d) {
+            std::copy(keys[d].begin(), keys[d].end(), out.idx.begin() + ranges[d].first * nn);
+            std::copy(pd0[d].begin(), pd0[d].end(), out.d0.begin() + ranges[d].first * nn);
+            if (with_aux) std::copy(pd1[d].begin(), pd1[d].end(), out.d1.begin() + ranges[d].first * nn);
+        }
+        return out;
+    }
+    std::vector<uint64_t> all_keys((size_t)world * rows * nn);
+    std::vector<float> all_aux(with_aux ? (size_t)world * rows * nn : 0);
+    for (int d = 0; d < world; ++d) {
+        std::copy(keys[d].begin(), keys[d].end(), all_keys.begin() + (size_t)d * rows * nn);
+        if (with_aux) std::copy(aux[d].begin(), aux[d].end(), all_aux.begin() + (size_t)d * rows * nn);
+    }
+    Gpu g0;
+    if (skd_ctx_create(0, &g0.ctx) != SKD_OK) throw std::runtime_error(skd_last_error(nullptr));
+    g0.check(skd_knn_merge(g0.ctx, all_keys.data(), with_aux ? all_aux.data() : nullptr, (uint32_t)world, rows, nn, dt,
+                           SKD_HOST, out.idx.data(), out.d0.data(), with_aux ? out.d1.data() : nullptr, SKD_HOST));
+    return out;
+}
+
 int run(const DistArgs &a) {
     g_level = a.quiet ? 0 : (a.verbose ? 2 : 1);
     log_info("Using " + std::to_string(a.threads) + " threads (host); distances run on CUDA device " + std::to_string(a.gpu));
@@ -329,6 +462,54 @@ int run(const DistArgs &a) {
             for (auto &w : warnings) log_warn(w);
         }
     }
+
+    // ---- several devices: sparse outputs only (for dense outputs the text tail, not the GPU, is the bottleneck)
+    if (a.gpus > 1 && a.knn >= 0) {
+        Out out(a);
+        skd_dist_type dt;
+        dt.kind = a.kmer < 0 ? SKD_CORE_ACC : (a.ani ? SKD_ANI : SKD_JACCARD);
+        dt.k_idx = a.kmer < 0 ? 0 : (int32_t)*refs.meta.get_k_idx((uint64_t)a.kmer);
+        if (dt.kind == SKD_CORE_ACC && refs.meta.kmer_lengths.size() < 2)
+            throw Panic("Need at least two k-mer lengths to calculate core/accessory distances");
+        uint64_t nn = (uint64_t)a.knn;
+        if (!a.has_query) {
+            if (n < 2) throw Panic("attempt to subtract with overflow: fewer than two samples loaded");
+            if (nn >= n) {
+                log_warn("knn=" + std::to_string(nn) + " is higher than number of samples=" + std::to_string(n));
+                nn = n - 1;
+            }
+        } else {
+            if (n == 0) throw Panic("Reference database has no loaded samples");
+            if (queries.meta.number_samples_loaded() == 0) throw Panic("Query database has no loaded samples");
+            if (!refs.meta.is_compatible_with(queries.meta))
+                throw std::runtime_error("reference and query databases differ in sketch size or k-mer lengths");
+            if (nn > n) {
+                log_warn("knn=" + std::to_string(nn) + " is higher than number of reference samples=" + std::to_string(n));
+                nn = n;
+            }
+        }
+        if (nn == 0) throw std::runtime_error("knn must be at least 1");
+        log_info("Calculating sparse distances with " + std::to_string(nn) + " nearest neighbours on " +
+                 std::to_string(a.gpus) + " devices");
+        KnnOut r = multi_gpu_knn(a, refs.meta, ref_name, a.subset.empty() ? nullptr : &subset_idx,
+                                 a.has_query ? &queries.meta : nullptr, qname, dt, nn, has_ref_c ? ref_c.data() : nullptr,
+                                 has_query_c ? query_c.data() : nullptr);
+        const MultiSketch &row_meta = a.has_query ? queries.meta : refs.meta;
+        const bool two = dt.kind == SKD_CORE_ACC;
+        for (uint64_t row = 0; row < r.rows; ++row) {
+            const std::string &rn = row_meta.sketch_name(row);
+            for (uint64_t t = 0; t < nn; ++t) {
+                const std::string &cn = refs.meta.sketch_name(r.idx[row * nn + t]);
+                if (two)
+                    out.line(rn, cn, r.d0[row * nn + t], &r.d1[row * nn + t]);
+                else if (r.d0[row * nn + t] < 1.0f || cn != rn)
+                    out.line(rn, cn, r.d0[row * nn + t], nullptr);
+            }
+        }
+        out.flush();
+        return 0;
+    }
+    if (a.gpus > 1) log_info("--gpus applies to --knn runs; dense output uses device " + std::to_string(a.gpu));
 
     // ---- device phase
     Out out(a);

@@ -296,3 +296,24 @@ def test_full_pipeline_fasta_to_distances(tools, tmp_path):
     r = run([cli, "dist", out, "-k", "21", "--knn", "2"])
     oidx, od0, _ = oracle.self_dists_knn(db, 2, k_idx=2)
     assert [l.split("\t")[2] for l in r.stdout.splitlines()] == [oracle.fmt_f32(v) for v in od0.ravel()]
+
+
+@pytest.mark.gpu
+def test_cli_multi_gpu_knn_equals_single_gpu(tools, tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    cli, _ = tools
+    ref = synth_db(700, 16, [17, 21, 25, 29], seed=95, n_families=9)
+    ref.names = [f"r{i}" for i in range(700)]
+    qry = synth_db(90, 16, [17, 21, 25, 29], seed=95, n_families=9)
+    qry.names = [f"q{i}" for i in range(90)]
+    rp, qp = write_skm_skd(str(tmp_path / "ref"), ref), write_skm_skd(str(tmp_path / "qry"), qry)
+    sub = tmp_path / "subset.txt"
+    sub.write_text("".join(f"r{i}\n" for i in range(699, 100, -3)))
+    for args in (["--knn", "20"], ["--knn", "20", "-k", "21"], ["--knn", "80", "-k", "21", "--ani"], [qp, "--knn", "7"],
+                 [qp, "--knn", "7", "-k", "25"], ["--knn", "5", "--subset", str(sub)]):
+        one = run([cli, "dist", rp] + args)
+        two = run([cli, "dist", rp] + args + ["--gpus", "2"])
+        assert one.returncode == 0 and two.returncode == 0, (args, one.stderr, two.stderr)
+        assert one.stdout == two.stdout and len(one.stdout) > 0, args
