@@ -17,13 +17,34 @@ _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 _lib = None
 
 
+def _cpu_stamp() -> str:
+    """The oracle is compiled with -march=native: a library built on another CPU (the build container vs the
+    GPU box) must be rebuilt, or it may use instructions this host lacks."""
+    try:
+        with open("/proc/cpuinfo") as fh:
+            for line in fh:
+                if line.startswith("flags"):
+                    import hashlib
+                    return hashlib.sha1(line.encode()).hexdigest()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def build(force: bool = False) -> str:
     srcs = [os.path.join(_HERE, f) for f in ("sketchdist_oracle.c", "sketcher_oracle.c", "Makefile")]
+    stamp_path = _LIB_PATH + ".cpu"
     stale = (not os.path.exists(_LIB_PATH)) or any(
         os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs
     )
-    if force or stale:
+    try:
+        other_cpu = open(stamp_path).read().strip() != _cpu_stamp()
+    except OSError:
+        other_cpu = True
+    if force or stale or other_cpu:
         subprocess.check_call(["make", "-s", "-C", _HERE, "-B", "liboracle.so"])
+        with open(stamp_path, "w") as fh:
+            fh.write(_cpu_stamp())
     return _LIB_PATH
 
 
