@@ -27,7 +27,7 @@ using namespace skd;
 namespace {
 thread_local std::string g_create_error;
 constexpr size_t kMaxSmem = 232448;           // 227 KB opt-in dynamic shared memory per CTA on sm_100
-constexpr size_t kUploadChunkBytes = 64ull << 20;
+size_t kUploadChunkBytes = 64ull << 20;       // SKD_UPLOAD_CHUNK_MB overrides
 size_t kResultChunkBytes = 64ull << 20;       // SKD_RESULT_CHUNK_MB overrides
 uint32_t kGroup = 8;                          // row blocks per L2 group (SKD_GROUP overrides)
 constexpr uint32_t kSymKnnMax = 64;           // symmetric self-kNN keeps 128-slot lists: knn + 64 candidates per step
@@ -842,6 +842,7 @@ skd_status skd_ctx_create(int device, skd_ctx **out) {
     }
     if (const char *e = getenv("SKD_ZEROCOPY")) ctx->zero_copy = atoi(e) != 0;
     if (const char *e = getenv("SKD_GROUP")) kGroup = (uint32_t)std::max(1, atoi(e));
+    if (const char *e = getenv("SKD_UPLOAD_CHUNK_MB")) kUploadChunkBytes = (size_t)std::max(1, atoi(e)) << 20;
     if (const char *e = getenv("SKD_KNN_SYMMETRIC")) ctx->knn_symmetric = atoi(e) != 0;
     if (const char *e = getenv("SKD_SYM_CHUNK_MB")) g_sym_chunk_bytes = (size_t)std::max(1, atoi(e)) << 20;
     if (const char *e = getenv("SKD_RESULT_CHUNK_MB")) kResultChunkBytes = (size_t)std::max(1, atoi(e)) << 20;
