@@ -55,6 +55,18 @@ def synth_db(n, W, kmers, seed=0, n_families=None, mu_range=(0.001, 0.03), acc_r
     return oracle.Db(usigs.reshape(-1), n, kmers, W)
 
 
+def synth_pair(n_ref, n_query, W, kmers, seed=0, n_families=None, **kw):
+    """A reference and a query database drawn from the SAME families (one synth_db split in two), so that cross
+    comparisons see related pairs, not only unrelated ones."""
+    both = synth_db(n_ref + n_query, W, kmers, seed=seed, n_families=n_families, **kw)
+    rows = both.bins.reshape(n_ref + n_query, -1)
+    rng = np.random.default_rng(seed + 12345)
+    perm = rng.permutation(n_ref + n_query)  # family members end up on both sides
+    ref = oracle.Db(rows[perm[:n_ref]].reshape(-1), n_ref, kmers, W, names=[f"ref{i}" for i in range(n_ref)])
+    qry = oracle.Db(rows[perm[n_ref:]].reshape(-1), n_query, kmers, W, names=[f"qry{i}" for i in range(n_query)])
+    return ref, qry
+
+
 def render_dense_self(names, dists, ncols):
     lines, d = [], 0
     for i in range(len(names)):

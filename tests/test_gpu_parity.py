@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import oracle
-from helpers import FIXTURES, fixture_db, load_json_db, subset_db, synth_db
+from helpers import FIXTURES, fixture_db, load_json_db, subset_db, synth_db, synth_pair
 
 pytestmark = pytest.mark.gpu
 
@@ -67,8 +67,7 @@ def test_match_counts_known_answers(sk, ctx):
 
 
 def test_cross_match_counts_ragged(sk, ctx):
-    a = synth_db(150, 16, [17, 21, 25], seed=5, n_families=3)
-    b = synth_db(70, 16, [17, 21, 25], seed=6, n_families=3)
+    a, b = synth_pair(150, 70, 16, [17, 21, 25], seed=5, n_families=6)
     ga, gb = up(sk, ctx, a), up(sk, ctx, b)
     got = sk.match_counts(ga, gb, rows=(10, 140))
     ref = oracle.match_counts(a, b, all_pairs(150, 70)).reshape(150, 70, 3)[10:140]
@@ -141,8 +140,7 @@ def test_dense_self_row_shards_concatenate(sk, ctx):
 
 
 def test_dense_cross_layout_and_values(sk, ctx):
-    a = synth_db(130, 16, [17, 21, 25, 29], seed=7, n_families=2)
-    b = synth_db(75, 16, [17, 21, 25, 29], seed=8, n_families=2)
+    a, b = synth_pair(130, 75, 16, [17, 21, 25, 29], seed=7, n_families=4)
     ga, gb = up(sk, ctx, a), up(sk, ctx, b)
     got = sk.cross_dists_all(ga, gb, dist_type=sk.set_k(ga))
     check_close(got.distances, oracle.cross_dists_all(a, b, threads=8))
@@ -216,7 +214,7 @@ def test_completeness(sk, ctx):
     a = sk.self_dists_all(g, dist_type=sk.set_k(g, 21), completeness_vec=low).distances
     assert np.array_equal(a, sk.self_dists_all(g, dist_type=sk.set_k(g, 21)).distances)
     # cross: separate vectors per side
-    b = synth_db(40, 16, [17, 21, 25, 29], seed=14, n_families=2)
+    b = oracle.Db(db.bins.reshape(90, -1)[rng.permutation(90)[:40]].reshape(-1), 40, db.kmers, db.W)  # related to db
     gb = up(sk, ctx, b)
     cq = rng.uniform(0.7, 1.0, size=40)
     got = sk.cross_dists_all(g, gb, dist_type=sk.set_k(g), ref_completeness_vec=cv, query_completeness_vec=cq).distances
@@ -281,8 +279,7 @@ def test_self_knn_core_acc_and_row_shards(sk, ctx):
 
 
 def test_cross_knn(sk, ctx):
-    ref = synth_db(700, 16, [17, 21, 25, 29], seed=23, n_families=10)
-    qry = synth_db(90, 16, [17, 21, 25, 29], seed=23, n_families=10)
+    ref, qry = synth_pair(700, 90, 16, [17, 21, 25, 29], seed=23, n_families=10)
     gr, gq = up(sk, ctx, ref), up(sk, ctx, qry)
     got = sk.cross_dists_knn(gr, gq, knn=7, dist_type=sk.set_k(gr, 21))
     oidx, od0, _ = oracle.cross_dists_knn(ref, qry, 7, k_idx=1, threads=8)
@@ -294,6 +291,7 @@ def test_cross_knn(sk, ctx):
     # rows are queries, columns refs (tests/distance.rs:465-490)
     line = str(gotc).split("\n")[0].split("\t")
     assert line[0] == qry.names[0] and line[1] in ref.names and len(line) == 4
+    assert (gotc.d0 < 1.0).mean() > 0.5  # the query set really has relatives among the references
     # knn >= n_ref is clamped to n_ref and returns every ref (tests/distance.rs:665-687)
     small = synth_db(5, 16, [17, 21, 25, 29], seed=24, n_families=1)
     gs = up(sk, ctx, small)
@@ -443,8 +441,7 @@ def test_self_knn_partials_merge_like_ranks(sk, ctx):
 
 
 def test_cross_knn_ref_shards_merge(sk, ctx):
-    ref = synth_db(500, 16, [17, 21, 25, 29], seed=72, n_families=6)
-    qry = synth_db(130, 16, [17, 21, 25, 29], seed=72, n_families=6)
+    ref, qry = synth_pair(500, 130, 16, [17, 21, 25, 29], seed=72, n_families=6)
     gq = up(sk, ctx, qry)
     whole_ref = up(sk, ctx, ref)
     bounds = [0, 100, 101, 320, 500]  # ragged shards, one with a single reference
@@ -515,8 +512,7 @@ def test_precluster_vs_oracle(sk, ctx, retain):
 # ------------------------------------------------------------------ few queries: narrow-column kernels, HBM-bound path
 @pytest.mark.parametrize("nq", [1, 7, 8, 9, 16, 17, 32, 33, 64])
 def test_cross_with_few_queries(sk, ctx, nq):
-    ref = synth_db(330, 16, [17, 21, 25, 29], seed=90, n_families=5)
-    qry = synth_db(nq, 16, [17, 21, 25, 29], seed=90, n_families=5)
+    ref, qry = synth_pair(330, nq, 16, [17, 21, 25, 29], seed=90, n_families=5)
     gr, gq = up(sk, ctx, ref), up(sk, ctx, qry)
     # raw counts through the (narrow) tiled kernel, refs x queries x K
     want = oracle.match_counts(ref, qry, all_pairs(330, nq)).reshape(330, nq, 4)
@@ -534,8 +530,7 @@ def test_cross_with_few_queries(sk, ctx, nq):
 
 
 def test_few_queries_knn_equals_row_owned_path(sk, ctx):
-    ref = synth_db(900, 16, [17, 21, 25, 29], seed=91, n_families=12)
-    qry = synth_db(40, 16, [17, 21, 25, 29], seed=91, n_families=12)
+    ref, qry = synth_pair(900, 40, 16, [17, 21, 25, 29], seed=91, n_families=12)
     plain = fresh_ctx(sk, SKD_KNN_SYMMETRIC=0)  # also disables the few-queries route
     tiny = fresh_ctx(sk, SKD_SYM_CHUNK_MB=1)    # several reference chunks and row slices
     try:
@@ -593,3 +588,30 @@ def test_random_shapes_against_oracle(sk, ctx):
             assert_knn_matches(got.idx, got.d0, got.d1, oidx, od0, od1, False)
         ga.free()
         gb.free()
+
+
+def test_knn_paths_with_completeness(sk, ctx):
+    ref, qry = synth_pair(420, 50, 16, [17, 21, 25, 29], seed=97, n_families=6)
+    rng = np.random.default_rng(3)
+    rc, qc = rng.uniform(0.65, 1.0, size=420), rng.uniform(0.65, 1.0, size=50)
+    gr, gq = up(sk, ctx, ref), up(sk, ctx, qry)
+    # symmetric self kNN (single GPU) and its row-owned twin
+    plain = fresh_ctx(sk, SKD_KNN_SYMMETRIC=0)
+    try:
+        gp = up(sk, plain, ref)
+        for dtf in (lambda g: sk.set_k(g), lambda g: sk.set_k(g, 21), lambda g: sk.set_k(g, 21, ani=True)):
+            a = sk.self_dists_knn(gr, knn=15, dist_type=dtf(gr), completeness_vec=rc)
+            b = sk.self_dists_knn(gp, knn=15, dist_type=dtf(gp), completeness_vec=rc)
+            assert np.array_equal(a.idx, b.idx) and np.array_equal(a.d0, b.d0)
+            kidx, ani = (-1, False) if a.dist_type.kind == sk.CORE_ACC else (1, a.dist_type.kind == sk.ANI)
+            oidx, od0, od1 = oracle.self_dists_knn(ref, 15, k_idx=kidx, ani=ani, completeness=rc, threads=4)
+            assert_knn_matches(a.idx, a.d0, a.d1, oidx, od0, od1, False)
+    finally:
+        plain.close()
+    # cross kNN, few-queries route: separate vectors per side (query = rows)
+    got = sk.cross_dists_knn(gr, gq, knn=9, dist_type=sk.set_k(gr), ref_completeness_vec=rc, query_completeness_vec=qc)
+    oidx, od0, od1 = oracle.cross_dists_knn(ref, qry, 9, ref_c=rc, query_c=qc, threads=4)
+    assert_knn_matches(got.idx, got.d0, got.d1, oidx, od0, od1, False)
+    nocomp = sk.cross_dists_knn(gr, gq, knn=9, dist_type=sk.set_k(gr))
+    # a constant factor on J shifts ln J for every k alike: the slope (core) stays, the intercept (accessory) moves
+    assert not np.array_equal(nocomp.d1, got.d1)

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import oracle
-from helpers import FIXTURES, fixture_db, load_json_db, synth_db, write_skm_skd
+from helpers import FIXTURES, fixture_db, load_json_db, synth_db, synth_pair, write_skm_skd
 
 
 @pytest.fixture(scope="module")
@@ -139,10 +139,7 @@ def test_cli_reproduces_reference_goldens(tools, tmp_path):
 @pytest.mark.gpu
 def test_cli_dense_and_cross_modes(tools, tmp_path):
     cli, _ = tools
-    ref = synth_db(70, 16, [17, 21, 25, 29], seed=60, n_families=3)
-    ref.names = [f"ref{i}" for i in range(70)]
-    qry = synth_db(9, 16, [17, 21, 25, 29], seed=61, n_families=3)
-    qry.names = [f"qry{i}" for i in range(9)]
+    ref, qry = synth_pair(70, 9, 16, [17, 21, 25, 29], seed=60, n_families=3)
     rp, qp = write_skm_skd(str(tmp_path / "ref"), ref), write_skm_skd(str(tmp_path / "qry"), qry)
     # dense self, text = oracle rendered with Rust float formatting
     r = run([cli, "dist", rp, "--threads", "4"])
@@ -304,10 +301,9 @@ def test_cli_multi_gpu_knn_equals_single_gpu(tools, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (gpurun --gpus 2)")
     cli, _ = tools
-    ref = synth_db(700, 16, [17, 21, 25, 29], seed=95, n_families=9)
+    ref, qry = synth_pair(700, 90, 16, [17, 21, 25, 29], seed=95, n_families=9)
     ref.names = [f"r{i}" for i in range(700)]
-    qry = synth_db(90, 16, [17, 21, 25, 29], seed=95, n_families=9)
-    qry.names = [f"q{i}" for i in range(90)]
+    ref = oracle.Db(ref.bins, 700, ref.kmers, ref.W, names=ref.names)
     rp, qp = write_skm_skd(str(tmp_path / "ref"), ref), write_skm_skd(str(tmp_path / "qry"), qry)
     sub = tmp_path / "subset.txt"
     sub.write_text("".join(f"r{i}\n" for i in range(699, 100, -3)))
