@@ -279,7 +279,7 @@ def main():
 
     def step_e2e():
         if world == 1:
-            gg = sk.SketchDb.upload(ctx, pin_in.array, n, KMERS, W)
+            gg = sk.SketchDb.upload(ctx, pin_in.array, n, KMERS, W, async_upload=True)  # overlaps PCIe with the tiles
         else:
             ctx.memcpy(raw_slice.data_ptr(), sk.SKD_DEVICE, pin_in.array[s0 * per_sample:s1 * per_sample], sk.SKD_HOST,
                        h2d_bytes)

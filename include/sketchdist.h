@@ -89,6 +89,14 @@ skd_status skd_memcpy(skd_ctx *ctx, void *dst, skd_loc dst_loc, const void *src,
 skd_status skd_db_upload(skd_ctx *ctx, const uint64_t *bins, skd_loc bins_loc, uint64_t n_samples,
                          uint64_t sample_stride, uint64_t kmer_stride, uint64_t sketchsize64,
                          uint64_t sketch_size, const uint64_t *kmer_lengths, uint32_t n_kmers, skd_db **out);
+/* Same as skd_db_upload for a PINNED host array (skd_host_alloc), but returns as soon as the host-to-device
+ * copies are queued: the caller must keep `bins` unchanged until the first compute call on the database (or
+ * skd_ctx_synchronize) has returned.  The planes are re-tiled chunk by chunk by that first call; a dense
+ * skd_self_dists_all interleaves the re-tiling with the distance tiles of the chunks that have arrived, so the
+ * PCIe transfer overlaps the computation.  Falls back to the synchronous path for pageable memory. */
+skd_status skd_db_upload_async(skd_ctx *ctx, const uint64_t *bins, uint64_t n_samples, uint64_t sample_stride,
+                               uint64_t kmer_stride, uint64_t sketchsize64, uint64_t sketch_size,
+                               const uint64_t *kmer_lengths, uint32_t n_kmers, skd_db **out);
 /* Replaces read_sketch_data / read_sketch_data_block + SketchArrayReader (multisketch.rs:167-210,
  * src/sketch/sketch_datafile.rs:159-194): streams an .skd file into HBM through pinned staging.
  * `sample_indices` (nullable) lists the FILE positions (Sketch::index) of the samples to load, in the

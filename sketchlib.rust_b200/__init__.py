@@ -71,6 +71,7 @@ def load_library(build=True):
         "skd_device_free": (None, [vp, vp]),
         "skd_memcpy": (C.c_int, [vp, vp, C.c_int, vp, C.c_int, C.c_size_t]),
         "skd_db_upload": (C.c_int, [vp, vp, C.c_int, u64, u64, u64, u64, u64, vp, u32, C.POINTER(vp)]),
+        "skd_db_upload_async": (C.c_int, [vp, vp, u64, u64, u64, u64, u64, vp, u32, C.POINTER(vp)]),
         "skd_db_load_skd": (C.c_int, [vp, C.c_char_p, vp, u64, u64, u64, u64, u64, vp, u32, C.POINTER(vp)]),
         "skd_db_free": (None, [vp]),
         "skd_db_n_samples": (u64, [vp]),
@@ -203,8 +204,10 @@ class SketchDb:
 
     @classmethod
     def upload(cls, ctx, bins, n_samples, kmer_lengths, sketchsize64, sketch_size=None, sample_stride=None,
-               kmer_stride=None, names=None, bins_loc=SKD_HOST):
-        """bins: numpy u64 array in the reference's layout, or an int device pointer with bins_loc=SKD_DEVICE."""
+               kmer_stride=None, names=None, bins_loc=SKD_HOST, async_upload=False):
+        """bins: numpy u64 array in the reference's layout, or an int device pointer with bins_loc=SKD_DEVICE.
+        async_upload=True (pinned host arrays from Context.pinned): return once the copies are queued; the array
+        must stay unchanged until the first compute call on the database has returned (skd_db_upload_async)."""
         kmers = np.ascontiguousarray(kmer_lengths, dtype=np.uint64)
         W = int(sketchsize64)
         kmer_stride = int(kmer_stride if kmer_stride is not None else W * 14)
@@ -215,8 +218,12 @@ class SketchDb:
             if bins.size < int(n_samples) * sample_stride:
                 raise ValueError("bins array shorter than n_samples * sample_stride")
         h = C.c_void_p()
-        ctx._check(ctx.lib.skd_db_upload(ctx.handle, _ptr(bins), bins_loc, int(n_samples), sample_stride, kmer_stride,
-                                         W, sketch_size, _ptr(kmers), len(kmers), C.byref(h)))
+        if async_upload and bins_loc == SKD_HOST:
+            ctx._check(ctx.lib.skd_db_upload_async(ctx.handle, _ptr(bins), int(n_samples), sample_stride, kmer_stride,
+                                                   W, sketch_size, _ptr(kmers), len(kmers), C.byref(h)))
+        else:
+            ctx._check(ctx.lib.skd_db_upload(ctx.handle, _ptr(bins), bins_loc, int(n_samples), sample_stride,
+                                             kmer_stride, W, sketch_size, _ptr(kmers), len(kmers), C.byref(h)))
         names = names if names is not None else [f"s{i}" for i in range(int(n_samples))]
         return cls(ctx, h, names, kmers.tolist(), W, sketch_size)
 

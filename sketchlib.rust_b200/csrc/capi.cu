@@ -59,6 +59,16 @@ struct skd_db {
     std::vector<uint64_t> kmers;
     uint64_t sketch_size = 0, W = 0, n = 0;
     double *lny_dev = nullptr;  // [nbins + 1]
+    // skd_db_upload_async: the raw planes are still arriving (copy stream, one event per chunk of whole sample
+    // blocks); they are re-tiled by the first compute call -- band by band, interleaved with the tile kernel, when
+    // that call is a dense self run, so that the PCIe transfer overlaps the distance computation.
+    struct Pending {
+        uint64_t *raw = nullptr;                 // device copy in the reference layout
+        uint64_t sample_stride = 0, kmer_stride = 0;
+        std::vector<cudaEvent_t> ready;          // chunk c has arrived
+        std::vector<uint32_t> block_end;         // chunk c covers sample blocks [block_end[c-1], block_end[c])
+    } pending;
+    bool is_pending() const { return pending.raw != nullptr; }
 };
 
 namespace {
@@ -230,30 +240,73 @@ skd_status build_epi(skd_ctx *ctx, const skd_db *A, const skd_db *B, skd_dist_ty
     return SKD_OK;
 }
 
-skd_status check_pair(skd_ctx *ctx, const skd_db *A, const skd_db *B) {
+skd_status materialize(skd_ctx *ctx, const skd_db *cdb);
+
+skd_status check_pair(skd_ctx *ctx, const skd_db *A, const skd_db *B, bool keep_pending = false) {
     if (!ctx || !A || !B) return fail(ctx, SKD_ERR_INVALID, "null context or database");
     if (A->ctx != ctx || B->ctx != ctx) return fail(ctx, SKD_ERR_INVALID, "database belongs to another context");
     if (A != B && !skd_db_compatible(A, B))
         return fail(ctx, SKD_ERR_INCOMPATIBLE, "reference and query databases differ in sketch size or k-mer lengths");
+    if (!keep_pending) {  // an asynchronously uploaded database is re-tiled before anything but a dense self run
+        skd_status st = materialize(ctx, A);
+        if (st) return st;
+        if (B != A) st = materialize(ctx, B);
+        if (st) return st;
+    }
     return SKD_OK;
 }
 
 // Group offsets for a dense launch over row blocks [rb0, rb0 + n_rb).
-void build_groups(bool self, uint32_t rb0, uint32_t n_rb, uint32_t nbB, std::vector<uint64_t> *off) {
+void build_groups(bool self, uint32_t rb0, uint32_t n_rb, uint32_t nbB, std::vector<uint64_t> *off, uint32_t cb_lo = 0,
+                  uint32_t cb_hi = 0) {
     uint32_t n_groups = (n_rb + kGroup - 1) / kGroup;
     off->assign(n_groups + 1, 0);
+    const uint32_t hi = cb_hi ? std::min(cb_hi, nbB) : nbB;
     for (uint32_t g = 0; g < n_groups; ++g) {
         uint32_t rows = std::min(kGroup, n_rb - g * kGroup);
-        uint64_t cols = self ? (uint64_t)nbB - (rb0 + g * kGroup) : nbB;
+        const uint32_t first = std::max(self ? rb0 + g * kGroup : 0u, cb_lo);  // the kernel's cb_first
+        uint64_t cols = hi > first ? hi - first : 0;
         (*off)[g + 1] = (*off)[g] + (uint64_t)rows * cols;
     }
+}
+
+// Re-tile chunk c of an asynchronously uploaded database (compute stream waits for its arrival).
+skd_status retile_chunk(skd_ctx *ctx, skd_db *db, size_t c) {
+    auto &p = db->pending;
+    const uint32_t b0 = c ? p.block_end[c - 1] : 0, b1 = p.block_end[c];
+    const uint64_t s0 = (uint64_t)b0 * TS, s1 = std::min<uint64_t>(db->n, (uint64_t)b1 * TS);
+    CU(ctx, cudaStreamWaitEvent(ctx->compute, p.ready[c], 0));
+    launch_repack(p.raw + s0 * p.sample_stride, s1 - s0, p.sample_stride, p.kmer_stride, db->tiled, db->dev, b0, b1 - b0,
+                  ctx->compute);
+    CU(ctx, cudaGetLastError());
+    ctx->launches++;
+    return SKD_OK;
+}
+skd_status finish_pending(skd_ctx *ctx, skd_db *db) {
+    auto &p = db->pending;
+    for (auto e : p.ready) cudaEventDestroy(e);
+    p.ready.clear();
+    p.block_end.clear();
+    if (p.raw) CU(ctx, cudaFreeAsync(p.raw, ctx->compute));
+    p.raw = nullptr;
+    return SKD_OK;
+}
+// Every compute entry point that does not interleave calls this first.
+skd_status materialize(skd_ctx *ctx, const skd_db *cdb) {
+    skd_db *db = const_cast<skd_db *>(cdb);
+    if (!db || !db->is_pending()) return SKD_OK;
+    for (size_t c = 0; c < db->pending.ready.size(); ++c) {
+        skd_status st = retile_chunk(ctx, db, c);
+        if (st) return st;
+    }
+    return finish_pending(ctx, db);
 }
 
 // Launch the tile kernel for rows [r0, r1) writing to device memory `dout`.  `d_grp_off` is the device copy
 // of `off` (group offsets built by build_groups for exactly this row range).
 skd_status launch_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, const EpiParams &E, int mode, uint64_t r0,
                         uint64_t r1, float *dout, const std::vector<uint64_t> &off, const uint64_t *d_grp_off,
-                        uint64_t rect_ld = 0) {
+                        uint64_t rect_ld = 0, uint32_t cb_lo = 0, uint32_t cb_hi = 0, uint64_t out_row_begin = ~0ull) {
     SchedParams S{};
     S.mode = mode;
     S.one = 1;
@@ -265,9 +318,13 @@ skd_status launch_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, const Ep
     S.grp_off = d_grp_off;
     S.row_begin = r0;
     S.row_end = r1;
-    S.out_base = S.self_mode ? condensed(r0, r0 + 1, A->n) : 0;
+    // `dout` starts at the first pair of row out_row_begin (default: r0)
+    const uint64_t ob = out_row_begin == ~0ull ? r0 : out_row_begin;
+    S.out_base = S.self_mode ? condensed(ob, ob + 1, A->n) : 0;
     S.out = dout;
     S.rect_ld = rect_ld;
+    S.cb_lo = cb_lo;
+    S.cb_hi = cb_hi;
     const bool count32 = E.nbins >= 65536;
     size_t smem = tile_kernel_smem(E.nk, count32, false, 0, false);
     if (smem > kMaxSmem)
@@ -340,12 +397,54 @@ skd_status run_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, bool self, 
     const uint64_t *d_off = (const uint64_t *)doff;
 
     if (out_loc == SKD_DEVICE) {
+        skd_db *pa = const_cast<skd_db *>(A);
+        if (self && mode == MODE_DENSE_SELF && pa->is_pending()) {
+            // The database is still arriving: re-tile each chunk as it lands and immediately run the tiles whose
+            // column block lies in it (their row blocks arrived earlier), so PCIe and the tile kernel overlap.
+            const size_t nc = pa->pending.ready.size();
+            std::vector<std::vector<uint64_t>> offs(nc);
+            std::vector<size_t> pos(nc);
+            std::vector<uint64_t> flat;
+            const uint32_t rb0 = (uint32_t)(row_begin / TS);
+            for (size_t c = 0; c < nc; ++c) {
+                const uint32_t b0 = c ? pa->pending.block_end[c - 1] : 0, b1 = pa->pending.block_end[c];
+                const uint64_t r1 = std::min<uint64_t>(row_end, (uint64_t)b1 * TS);
+                pos[c] = flat.size();
+                if (r1 > row_begin) {
+                    build_groups(true, rb0, (uint32_t)((r1 + TS - 1) / TS) - rb0, A->dev.nb, &offs[c], b0, b1);
+                    flat.insert(flat.end(), offs[c].begin(), offs[c].end());
+                }
+            }
+            void *dband;
+            st = scratch_get(ctx, "grp_band", std::max<size_t>(1, flat.size()) * sizeof(uint64_t), &dband);
+            if (st) return st;
+            CU(ctx, cudaMemcpyAsync(dband, flat.data(), flat.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->compute));
+            CU(ctx, cudaStreamSynchronize(ctx->compute));  // flat is pageable
+            for (size_t c = 0; c < nc; ++c) {
+                st = retile_chunk(ctx, pa, c);
+                if (st) return st;
+                if (offs[c].empty() || offs[c].back() == 0) continue;
+                const uint32_t b0 = c ? pa->pending.block_end[c - 1] : 0, b1 = pa->pending.block_end[c];
+                const uint64_t r1 = std::min<uint64_t>(row_end, (uint64_t)b1 * TS);
+                st = launch_dense(ctx, A, B, E, mode, row_begin, r1, out, offs[c], (const uint64_t *)dband + pos[c], 0, b0, b1,
+                                  row_begin);
+                if (st) return st;
+            }
+            st = finish_pending(ctx, pa);
+            if (st) return st;
+            CU(ctx, cudaStreamSynchronize(ctx->compute));
+            return timers_collect(ctx);
+        }
         for (auto &c : chunks) {
             st = launch_dense(ctx, A, B, E, mode, c.r0, c.r1, out + elems_before(c.r0) * ncols, c.off, d_off + c.off_pos);
             if (st) return st;
         }
         CU(ctx, cudaStreamSynchronize(ctx->compute));
         return timers_collect(ctx);
+    }
+    {   // staged host path: the database must be complete
+        st = materialize(ctx, A);
+        if (st) return st;
     }
     void *dbuf[2];
     st = scratch_get(ctx, "dense0", chunk_elems * ncols * 4, &dbuf[0]);
@@ -669,6 +768,7 @@ struct ChunkSource {
     skd_loc loc = SKD_HOST;
     int fd = -1;                       // .skd file
     const uint64_t *indices = nullptr; // file positions, nullable
+    bool async = false;                // pinned host array: return once the copies are queued (skd_db_upload_async)
 };
 
 skd_status db_build(skd_ctx *ctx, const ChunkSource &src, uint64_t n, uint64_t sample_stride, uint64_t kmer_stride,
@@ -715,7 +815,43 @@ skd_status db_build(skd_ctx *ctx, const ChunkSource &src, uint64_t n, uint64_t s
         CUB(cudaMemcpyAsync(db->lny_dev, lny.data(), lny.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->compute));
         CUB(cudaStreamSynchronize(ctx->compute));  // lny is a local vector
     }
-    if (n > 0) {
+    bool async_ok = false;
+    if (n > 0 && src.async && src.direct && src.loc == SKD_HOST) {
+        cudaPointerAttributes attr;
+        async_ok = cudaPointerGetAttributes(&attr, src.direct) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+        if (!async_ok) (void)cudaGetLastError();
+    }
+    if (async_ok) {
+        // queue the chunked H2D copies on the copy stream and return; the chunks are re-tiled by the first
+        // compute call (materialize / the interleaved dense self path)
+        auto &p = db->pending;
+        p.sample_stride = sample_stride;
+        p.kmer_stride = kmer_stride;
+        CUB(cudaMallocAsync((void **)&p.raw, (size_t)n * sample_stride * 8, ctx->compute));
+        CUB(cudaEventRecord(ctx->ev_a[0], ctx->compute));
+        CUB(cudaStreamWaitEvent(ctx->copy, ctx->ev_a[0], 0));  // the allocation is ordered before the copies
+        // Geometric chunks (1/8, 1/8, 1/4, 1/2 of the sample blocks): the dense-self tiles enabled by a chunk grow
+        // with the square of the columns received while the transfer grows linearly, so early chunks must be small
+        // for the kernel to start early and late ones large for few, well-filled launches.
+        std::vector<uint32_t> ends;
+        for (uint32_t div : {8u, 4u, 2u, 1u}) {
+            uint32_t e = std::max(1u, db->dev.nb / div);
+            if (ends.empty() || e > ends.back()) ends.push_back(e);
+        }
+        ends.back() = db->dev.nb;
+        uint32_t b0 = 0;
+        for (size_t ci = 0; ci < ends.size(); b0 = ends[ci], ++ci) {
+            const uint32_t b1 = ends[ci];
+            const uint64_t s0 = (uint64_t)b0 * TS, s1 = std::min<uint64_t>(n, (uint64_t)b1 * TS);
+            CUB(cudaMemcpyAsync(p.raw + s0 * sample_stride, src.direct + s0 * sample_stride,
+                                (size_t)(s1 - s0) * sample_stride * 8, cudaMemcpyHostToDevice, ctx->copy));
+            cudaEvent_t ev;
+            CUB(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            CUB(cudaEventRecord(ev, ctx->copy));
+            p.ready.push_back(ev);
+            p.block_end.push_back(b1);
+        }
+    } else if (n > 0) {
         if (src.direct && src.loc == SKD_DEVICE) {
             launch_repack(src.direct, n, sample_stride, kmer_stride, db->tiled, db->dev, 0, db->dev.nb, ctx->compute);
             CUB(cudaGetLastError());
@@ -928,6 +1064,19 @@ skd_status skd_db_upload(skd_ctx *ctx, const uint64_t *bins, skd_loc bins_loc, u
                     out);
 }
 
+skd_status skd_db_upload_async(skd_ctx *ctx, const uint64_t *bins, uint64_t n_samples, uint64_t sample_stride,
+                               uint64_t kmer_stride, uint64_t sketchsize64, uint64_t sketch_size,
+                               const uint64_t *kmer_lengths, uint32_t n_kmers, skd_db **out) {
+    if (!ctx) return fail(nullptr, SKD_ERR_INVALID, "null context");
+    if (n_samples > 0 && !bins) return fail(ctx, SKD_ERR_INVALID, "null bins");
+    ChunkSource src;
+    src.direct = bins;
+    src.loc = SKD_HOST;
+    src.async = true;
+    return db_build(ctx, src, n_samples, sample_stride, kmer_stride, sketchsize64, sketch_size, kmer_lengths, n_kmers,
+                    out);
+}
+
 skd_status skd_db_load_skd(skd_ctx *ctx, const char *skd_path, const uint64_t *sample_indices, uint64_t n_samples,
                            uint64_t sample_stride, uint64_t kmer_stride, uint64_t sketchsize64, uint64_t sketch_size,
                            const uint64_t *kmer_lengths, uint32_t n_kmers, skd_db **out) {
@@ -962,6 +1111,11 @@ void skd_db_free(skd_db *db) {
     if (!db) return;
     if (db->ctx) cudaSetDevice(db->ctx->device);
     cudaStream_t st = db->ctx ? db->ctx->compute : nullptr;
+    if (db->is_pending()) {  // never used: wait for the copies still reading the caller's buffer
+        if (db->ctx) cudaStreamSynchronize(db->ctx->copy);
+        for (auto e : db->pending.ready) cudaEventDestroy(e);
+        cudaFreeAsync(db->pending.raw, st);
+    }
     if (db->tiled) cudaFreeAsync(db->tiled, st);  // back to the device pool: the next upload reuses it
     if (db->lny_dev) cudaFreeAsync(db->lny_dev, st);
     delete db;
@@ -1001,7 +1155,7 @@ uint64_t skd_self_pairs_in_rows(uint64_t n, uint64_t row_begin, uint64_t row_end
 
 skd_status skd_self_dists_all(skd_ctx *ctx, const skd_db *db, skd_dist_type dist, const double *completeness,
                               double cutoff, uint64_t row_begin, uint64_t row_end, float *out, skd_loc out_loc) {
-    skd_status st = check_pair(ctx, db, db);
+    skd_status st = check_pair(ctx, db, db, /*keep_pending=*/true);  // run_dense overlaps an upload in flight
     if (st) return st;
     CU(ctx, cudaSetDevice(ctx->device));
     EpiParams E;

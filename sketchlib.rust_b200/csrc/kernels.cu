@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(THREADS, 2)
         const uint32_t rows_in_g = min(S.group, S.n_rb - g * S.group);
         const uint64_t local = t - S.grp_off[g];
         const uint32_t rb = S.rb0 + g * S.group + (uint32_t)(local % rows_in_g);
-        const uint32_t cb_first = S.mode == MODE_DENSE_SELF ? S.rb0 + g * S.group : 0u;
+        const uint32_t cb_first = max(S.mode == MODE_DENSE_SELF ? S.rb0 + g * S.group : 0u, S.cb_lo);
         const uint32_t cb = cb_first + (uint32_t)(local / rows_in_g);
         if (S.mode == MODE_DENSE_SELF && cb < rb) return;  // below the diagonal (only inside a diagonal group)
 

@@ -84,6 +84,7 @@ struct SchedParams {
     uint64_t rect_ld;     // dense self, if non-zero: write kNN keys row-major at [(i - row_begin) * rect_ld + (j - rect_c0)]
     uint64_t rect_c0;     //   (only j > i is written): the symmetric self-kNN path reads them back by row and by column
     uint64_t idx_offset;  // kNN: added to the neighbour index stored in the composite (column shards of a bigger database)
+    uint32_t cb_lo, cb_hi; // dense: only column blocks [cb_lo, cb_hi) (cb_hi == 0: all); bands follow an upload in flight
     float *out;           // dense: distances; counts mode: reinterpret as uint32_t*
     uint32_t one;         // always 1: a multiplier the compiler cannot fold, see tile_counts
     uint32_t pad0_;

@@ -615,3 +615,33 @@ def test_knn_paths_with_completeness(sk, ctx):
     nocomp = sk.cross_dists_knn(gr, gq, knn=9, dist_type=sk.set_k(gr))
     # a constant factor on J shifts ln J for every k alike: the slope (core) stays, the intercept (accessory) moves
     assert not np.array_equal(nocomp.d1, got.d1)
+
+
+def test_async_upload_overlapped_dense_and_other_calls(sk, ctx):
+    db = synth_db(1500, 16, [17, 21, 25, 29], seed=98, n_families=20)
+    pin = ctx.pinned((db.bins.size,), np.uint64)
+    pin.array[:] = db.bins
+    want = sk.self_dists_all(up(sk, ctx, db), dist_type=sk.DistType(sk.CORE_ACC)).distances
+    for rows in (None, (0, 700), (130, 1500), (900, 901)):
+        g = sk.SketchDb.upload(ctx, pin.array, db.n, db.kmers, db.W, async_upload=True)
+        got = sk.self_dists_all(g, dist_type=sk.set_k(g), rows=rows).distances  # pinned result: interleaved bands
+        lo, hi = (0, 1500) if rows is None else rows
+        first = int(ctx.lib.skd_self_pairs_in_rows(1500, 0, lo))
+        cnt = int(ctx.lib.skd_self_pairs_in_rows(1500, lo, hi))
+        assert np.array_equal(got, want[2 * first:2 * (first + cnt)])
+        # the database is complete afterwards: any other call works on it
+        assert np.array_equal(sk.self_dists_all(g, dist_type=sk.set_k(g, 21)).distances,
+                              oracle.self_dists_all(db, k_idx=1, threads=8))
+        g.free()
+    # first call is not a dense self run: the planes are re-tiled up front
+    g = sk.SketchDb.upload(ctx, pin.array, db.n, db.kmers, db.W, async_upload=True)
+    a = sk.self_dists_knn(g, knn=10, dist_type=sk.set_k(g, 21))
+    oidx, od0, _ = oracle.self_dists_knn(db, 10, k_idx=1, threads=8)
+    assert np.array_equal(a.d0, od0)
+    g.free()
+    g = sk.SketchDb.upload(ctx, pin.array, db.n, db.kmers, db.W, async_upload=True)
+    g.free()  # never used: freeing waits for the copies
+    # pageable memory silently takes the synchronous path
+    g = sk.SketchDb.upload(ctx, db.bins, db.n, db.kmers, db.W, async_upload=True)
+    assert np.array_equal(sk.self_dists_all(g, dist_type=sk.set_k(g), pinned=False).distances, want)
+    pin.free()

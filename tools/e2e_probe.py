@@ -10,9 +10,11 @@ pin = ctx.pinned((n * 8 * W * 14,), np.uint64)
 pin.array[:] = rng.integers(0, 1 << 64, size=pin.array.size, dtype=np.uint64)
 npairs = n * (n - 1) // 2
 out = ctx.pinned((npairs * 2,), np.float32)
+import os
+ASYNC = os.environ.get('E2E_ASYNC', '1') == '1'
 for it in range(6):
     t0 = time.perf_counter()
-    g = sk.SketchDb.upload(ctx, pin.array, n, kmers, W)
+    g = sk.SketchDb.upload(ctx, pin.array, n, kmers, W, async_upload=ASYNC)
     t1 = time.perf_counter()
     dt = sk.set_k(g)
     ctx._check(ctx.lib.skd_self_dists_all(ctx.handle, g.handle, dt.c, None, 0.64, 0, n, out.array.ctypes.data, sk.SKD_HOST))
