@@ -27,11 +27,7 @@ using namespace skd;
 namespace {
 thread_local std::string g_create_error;
 constexpr size_t kMaxSmem = 232448;           // 227 KB opt-in dynamic shared memory per CTA on sm_100
-size_t kUploadChunkBytes = 64ull << 20;       // SKD_UPLOAD_CHUNK_MB overrides
-size_t kResultChunkBytes = 64ull << 20;       // SKD_RESULT_CHUNK_MB overrides
-uint32_t kGroup = 8;                          // row blocks per L2 group (SKD_GROUP overrides)
 constexpr uint32_t kSymKnnMax = 64;           // symmetric self-kNN keeps 128-slot lists: knn + 64 candidates per step
-size_t g_sym_chunk_bytes = 2ull << 30;        // HBM buffer of one symmetric-kNN row group (SKD_SYM_CHUNK_MB)
 }  // namespace
 
 struct skd_ctx {
@@ -49,6 +45,11 @@ struct skd_ctx {
     int sm_count = 148;
     bool knn_symmetric = true;  // SKD_KNN_SYMMETRIC=0: whole-matrix self kNN evaluates both (i,j) and (j,i)
     bool zero_copy = true;   // dense kernels store straight into pinned host results (SKD_ZEROCOPY=0 disables)
+    // Tunables, read once from the environment when the context is created.
+    size_t upload_chunk_bytes = 64ull << 20;  // SKD_UPLOAD_CHUNK_MB: staging chunk of a pageable/file upload
+    size_t result_chunk_bytes = 64ull << 20;  // SKD_RESULT_CHUNK_MB: staged D2H chunk of dense results
+    uint32_t group = 8;                       // SKD_GROUP: row blocks per L2 group of the tile scheduler
+    size_t sym_chunk_bytes = 2ull << 30;      // SKD_SYM_CHUNK_MB: HBM key buffer of one symmetric-kNN row group
 };
 
 struct skd_db {
@@ -257,14 +258,14 @@ skd_status check_pair(skd_ctx *ctx, const skd_db *A, const skd_db *B, bool keep_
 }
 
 // Group offsets for a dense launch over row blocks [rb0, rb0 + n_rb).
-void build_groups(bool self, uint32_t rb0, uint32_t n_rb, uint32_t nbB, std::vector<uint64_t> *off, uint32_t cb_lo = 0,
-                  uint32_t cb_hi = 0) {
-    uint32_t n_groups = (n_rb + kGroup - 1) / kGroup;
+void build_groups(uint32_t group, bool self, uint32_t rb0, uint32_t n_rb, uint32_t nbB, std::vector<uint64_t> *off,
+                  uint32_t cb_lo = 0, uint32_t cb_hi = 0) {
+    uint32_t n_groups = (n_rb + group - 1) / group;
     off->assign(n_groups + 1, 0);
     const uint32_t hi = cb_hi ? std::min(cb_hi, nbB) : nbB;
     for (uint32_t g = 0; g < n_groups; ++g) {
-        uint32_t rows = std::min(kGroup, n_rb - g * kGroup);
-        const uint32_t first = std::max(self ? rb0 + g * kGroup : 0u, cb_lo);  // the kernel's cb_first
+        uint32_t rows = std::min(group, n_rb - g * group);
+        const uint32_t first = std::max(self ? rb0 + g * group : 0u, cb_lo);  // the kernel's cb_first
         uint64_t cols = hi > first ? hi - first : 0;
         (*off)[g + 1] = (*off)[g] + (uint64_t)rows * cols;
     }
@@ -313,7 +314,7 @@ skd_status launch_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, const Ep
     S.self_mode = mode == MODE_DENSE_SELF;
     S.rb0 = (uint32_t)(r0 / TS);
     S.n_rb = (uint32_t)((r1 + TS - 1) / TS) - S.rb0;
-    S.group = kGroup;
+    S.group = ctx->group;
     S.n_groups = (uint32_t)off.size() - 1;
     S.grp_off = d_grp_off;
     S.row_begin = r0;
@@ -358,7 +359,7 @@ skd_status run_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, bool self, 
             (void)cudaGetLastError();
         }
     }
-    // Plan: one chunk when the result stays on the device; otherwise row chunks of about kResultChunkBytes
+    // Plan: one chunk when the result stays on the device; otherwise row chunks of about ctx->result_chunk_bytes
     // on two device buffers, so that the D2H copy of chunk c overlaps the kernel of chunk c+1.
     struct Chunk {
         uint64_t r0, r1;
@@ -369,7 +370,7 @@ skd_status run_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, bool self, 
     uint64_t rows_per_chunk = row_end - row_begin + TS;
     if (out_loc == SKD_HOST) {
         const uint64_t widest = self ? (A->n - 1 - std::min(row_begin, A->n - 1)) : B->n;
-        rows_per_chunk = kResultChunkBytes / std::max<uint64_t>(1, widest * ncols * 4);
+        rows_per_chunk = ctx->result_chunk_bytes / std::max<uint64_t>(1, widest * ncols * 4);
         rows_per_chunk = std::max<uint64_t>(TS, rows_per_chunk / TS * TS);
     }
     size_t chunk_elems = 0, off_total = 0;
@@ -377,7 +378,7 @@ skd_status run_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, bool self, 
         Chunk c;
         c.r0 = r;
         c.r1 = std::min(row_end, (r / TS) * TS + rows_per_chunk);
-        build_groups(self, (uint32_t)(c.r0 / TS), (uint32_t)((c.r1 + TS - 1) / TS) - (uint32_t)(c.r0 / TS), B->dev.nb,
+        build_groups(ctx->group, self, (uint32_t)(c.r0 / TS), (uint32_t)((c.r1 + TS - 1) / TS) - (uint32_t)(c.r0 / TS), B->dev.nb,
                      &c.off);
         c.off_pos = off_total;
         off_total += c.off.size();
@@ -411,7 +412,7 @@ skd_status run_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, bool self, 
                 const uint64_t r1 = std::min<uint64_t>(row_end, (uint64_t)b1 * TS);
                 pos[c] = flat.size();
                 if (r1 > row_begin) {
-                    build_groups(true, rb0, (uint32_t)((r1 + TS - 1) / TS) - rb0, A->dev.nb, &offs[c], b0, b1);
+                    build_groups(ctx->group, true, rb0, (uint32_t)((r1 + TS - 1) / TS) - rb0, A->dev.nb, &offs[c], b0, b1);
                     flat.insert(flat.end(), offs[c].begin(), offs[c].end());
                 }
             }
@@ -488,7 +489,7 @@ skd_status run_knn_few_queries(skd_ctx *ctx, const skd_db *R, const skd_db *Q, c
     const uint64_t elt = with_aux ? 8 : 4;
     EpiParams Ed = E;  // dense launch: rows = refs, columns = queries
     std::swap(Ed.a_comp, Ed.b_comp);
-    uint64_t rows_chunk = std::max<uint64_t>(TS, g_sym_chunk_bytes / (nq * elt) / TS * TS);
+    uint64_t rows_chunk = std::max<uint64_t>(TS, ctx->sym_chunk_bytes / (nq * elt) / TS * TS);
     rows_chunk = std::min<uint64_t>(rows_chunk, (n_ref + TS - 1) / TS * TS);
     const uint32_t n_chunks = (uint32_t)((n_ref + rows_chunk - 1) / rows_chunk);
     const uint32_t tgt_groups = (uint32_t)((nq + TS - 1) / TS);
@@ -513,7 +514,7 @@ skd_status run_knn_few_queries(skd_ctx *ctx, const skd_db *R, const skd_db *Q, c
     for (uint32_t c = 0; c < n_chunks; ++c) {
         const uint64_t g0 = (uint64_t)c * rows_chunk, g1 = std::min(n_ref, g0 + rows_chunk);
         std::vector<uint64_t> off;
-        build_groups(false, (uint32_t)(g0 / TS), (uint32_t)((g1 + TS - 1) / TS) - (uint32_t)(g0 / TS), Q->dev.nb, &off);
+        build_groups(ctx->group, false, (uint32_t)(g0 / TS), (uint32_t)((g1 + TS - 1) / TS) - (uint32_t)(g0 / TS), Q->dev.nb, &off);
         void *doff;
         st = scratch_get(ctx, "grp_off", off.size() * sizeof(uint64_t), &doff);
         if (st) return st;
@@ -712,7 +713,7 @@ skd_status run_knn_symmetric(skd_ctx *ctx, const skd_db *db, const EpiParams &E,
     for (uint64_t g0 = row_begin; g0 < row_end && g0 + 1 < n;) {
         const uint64_t C = n - g0;                     // columns g0 .. n-1
         const uint64_t ld = (C + 3) / 4 * 4;
-        uint64_t R = std::max<uint64_t>(TS, g_sym_chunk_bytes / (ld * elt) / TS * TS);
+        uint64_t R = std::max<uint64_t>(TS, ctx->sym_chunk_bytes / (ld * elt) / TS * TS);
         R = std::min<uint64_t>(R, (row_end - g0 + TS - 1) / TS * TS);
         const uint64_t g1 = std::min<uint64_t>({g0 + R, row_end, n});
         void *D;
@@ -725,9 +726,9 @@ skd_status run_knn_symmetric(skd_ctx *ctx, const skd_db *db, const EpiParams &E,
         S.self_mode = 1;
         S.rb0 = (uint32_t)(g0 / TS);
         S.n_rb = (uint32_t)((g1 + TS - 1) / TS) - S.rb0;
-        S.group = kGroup;
+        S.group = ctx->group;
         std::vector<uint64_t> off;
-        build_groups(true, S.rb0, S.n_rb, db->dev.nb, &off);
+        build_groups(ctx->group, true, S.rb0, S.n_rb, db->dev.nb, &off);
         S.n_groups = (uint32_t)off.size() - 1;
         void *doff;
         st = scratch_get(ctx, "grp_off", off.size() * sizeof(uint64_t), &doff);
@@ -860,7 +861,7 @@ skd_status db_build(skd_ctx *ctx, const ChunkSource &src, uint64_t n, uint64_t s
         } else {
             // chunks of whole sample blocks: host -> (pinned) -> device raw -> repack, double buffered
             const size_t block_bytes = (size_t)TS * sample_stride * 8;
-            const uint32_t blocks_per_chunk = (uint32_t)std::max<size_t>(1, kUploadChunkBytes / block_bytes);
+            const uint32_t blocks_per_chunk = (uint32_t)std::max<size_t>(1, ctx->upload_chunk_bytes / block_bytes);
             const size_t chunk_bytes = (size_t)blocks_per_chunk * block_bytes;
             void *raw[2];
             skd_status st = scratch_get(ctx, "raw0", chunk_bytes, &raw[0]);
@@ -977,11 +978,11 @@ skd_status skd_ctx_create(int device, skd_ctx **out) {
         }
     }
     if (const char *e = getenv("SKD_ZEROCOPY")) ctx->zero_copy = atoi(e) != 0;
-    if (const char *e = getenv("SKD_GROUP")) kGroup = (uint32_t)std::max(1, atoi(e));
-    if (const char *e = getenv("SKD_UPLOAD_CHUNK_MB")) kUploadChunkBytes = (size_t)std::max(1, atoi(e)) << 20;
+    if (const char *e = getenv("SKD_GROUP")) ctx->group = (uint32_t)std::max(1, atoi(e));
+    if (const char *e = getenv("SKD_UPLOAD_CHUNK_MB")) ctx->upload_chunk_bytes = (size_t)std::max(1, atoi(e)) << 20;
     if (const char *e = getenv("SKD_KNN_SYMMETRIC")) ctx->knn_symmetric = atoi(e) != 0;
-    if (const char *e = getenv("SKD_SYM_CHUNK_MB")) g_sym_chunk_bytes = (size_t)std::max(1, atoi(e)) << 20;
-    if (const char *e = getenv("SKD_RESULT_CHUNK_MB")) kResultChunkBytes = (size_t)std::max(1, atoi(e)) << 20;
+    if (const char *e = getenv("SKD_SYM_CHUNK_MB")) ctx->sym_chunk_bytes = (size_t)std::max(1, atoi(e)) << 20;
+    if (const char *e = getenv("SKD_RESULT_CHUNK_MB")) ctx->result_chunk_bytes = (size_t)std::max(1, atoi(e)) << 20;
     for (int i = 0; i < 2; ++i) {
         cudaEventCreateWithFlags(&ctx->ev_a[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_b[i], cudaEventDisableTiming);
