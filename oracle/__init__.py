@@ -226,6 +226,15 @@ def sketch_dna(seq_records, kmers, sketch_size, rc=True):
     return out, bool(dens)
 
 
+def bin_minima(seq_records, k, nbins, rc=True) -> np.ndarray:
+    """Densified bin minima (u64[nbins]) of one sample at one k; nbins need not be a multiple of 64 (the inverted
+    index sketches with exactly --sketch-size bins, src/lib.rs:583)."""
+    seq = np.frombuffer(b"\n".join(seq_records), dtype=np.uint8)
+    out = np.zeros(nbins, dtype=np.uint64)
+    lib().oracle_bin_minima(_p(seq), C.c_uint64(len(seq)), C.c_uint64(k), C.c_uint64(nbins), C.c_int(rc), _p(out))
+    return out
+
+
 def fill_usigs(bins16) -> np.ndarray:
     """bins16: uint16[..., nbins] (nbins % 64 == 0) -> u64[..., nbins/64*14] bit planes (fill_usigs)."""
     bins16 = np.ascontiguousarray(bins16, dtype=np.uint16)

@@ -56,43 +56,48 @@ static int densify_bin(uint64_t *signs, uint64_t nbins) {
     return 1;
 }
 
+/* Bin minima of all canonical k-mer hashes of one sample over `nbins` bins, then densify_bin
+ * (Sketch::get_signs, src/sketch/mod.rs:132-153; with any nbins: get_signs_no_densify :156-176 + densify_bin, as
+ * the inverted index uses them, src/inverted.rs:355-386).  seq: bytes of all records; any non-ACGTU byte is a
+ * break, and the caller separates records with a '\n' byte (also a break).  Returns 1 if densified. */
+int oracle_bin_minima(const uint8_t *seq, uint64_t len, uint64_t k, uint64_t nbins, int rc, uint64_t *signs) {
+    uint64_t bin_size = (SIGN_MOD + nbins - 1) / nbins;
+    for (uint64_t b = 0; b < nbins; ++b) signs[b] = UINT64_MAX;
+    uint64_t run = 0; /* valid bases since the last break */
+    for (uint64_t pos = 0; pos < len; ++pos) {
+        if (!valid_base(seq[pos])) {
+            run = 0;
+            continue;
+        }
+        run += 1;
+        if (run < k) continue;
+        /* k-mer = seq[pos-k+1 .. pos]; direct (non-rolling) evaluation of the same function */
+        uint64_t fh = 0, rh = 0;
+        const uint8_t *km = seq + pos + 1 - k;
+        for (uint64_t i = 0; i < k; ++i) fh = srol(fh) ^ SEED[(km[i] >> 1) & 3];
+        if (rc) {
+            for (uint64_t i = k; i-- > 0;) rh = srol(rh) ^ SEED[((km[i] >> 1) & 3) ^ 2];
+            if (rh < fh) fh = rh;
+        }
+        uint64_t sign = fh % SIGN_MOD;
+        uint64_t bin = sign / bin_size;
+        if (sign < signs[bin]) signs[bin] = sign;
+    }
+    return densify_bin(signs, nbins);
+}
+
 /*
- * seq: bytes of all records of one sample; any non-ACGTU byte is a break, and the
- * caller separates records with a '\n' byte (also a break).  Writes n_k * W * 14 u64
- * in the .skd per-sample layout (k-major, then 64-bin word, then bit plane;
+ * Writes n_k * W * 14 u64 in the .skd per-sample layout (k-major, then 64-bin word, then bit plane;
  * fill_usigs src/sketch/mod.rs:215-223).  Returns 1 if any k needed densifying.
  */
 int oracle_sketch_dna(const uint8_t *seq, uint64_t len, const uint64_t *kmers, uint64_t n_k, uint64_t sketch_size,
                       int rc, uint64_t *usigs_out) {
     uint64_t W = (sketch_size + 63) / 64, nbins = W * 64; /* num_bins: src/sketch/mod.rs:49-54 */
-    uint64_t bin_size = (SIGN_MOD + nbins - 1) / nbins;
     uint64_t *signs = (uint64_t *)malloc(sizeof(uint64_t) * nbins);
     int densified = 0;
     memset(usigs_out, 0, sizeof(uint64_t) * n_k * W * BBITS);
     for (uint64_t ki = 0; ki < n_k; ++ki) {
-        uint64_t k = kmers[ki];
-        for (uint64_t b = 0; b < nbins; ++b) signs[b] = UINT64_MAX;
-        uint64_t run = 0; /* valid bases since the last break */
-        for (uint64_t pos = 0; pos < len; ++pos) {
-            if (!valid_base(seq[pos])) {
-                run = 0;
-                continue;
-            }
-            run += 1;
-            if (run < k) continue;
-            /* k-mer = seq[pos-k+1 .. pos]; direct (non-rolling) evaluation of the same function */
-            uint64_t fh = 0, rh = 0;
-            const uint8_t *km = seq + pos + 1 - k;
-            for (uint64_t i = 0; i < k; ++i) fh = srol(fh) ^ SEED[(km[i] >> 1) & 3];
-            if (rc) {
-                for (uint64_t i = k; i-- > 0;) rh = srol(rh) ^ SEED[((km[i] >> 1) & 3) ^ 2];
-                if (rh < fh) fh = rh;
-            }
-            uint64_t sign = fh % SIGN_MOD;
-            uint64_t bin = sign / bin_size;
-            if (sign < signs[bin]) signs[bin] = sign;
-        }
-        densified |= densify_bin(signs, nbins);
+        densified |= oracle_bin_minima(seq, len, kmers[ki], nbins, rc, signs);
         uint64_t *us = usigs_out + ki * W * BBITS;
         for (uint64_t b = 0; b < nbins; ++b)
             for (int p = 0; p < BBITS; ++p) us[(b / 64) * BBITS + p] |= ((signs[b] >> p) & 1) << (b % 64);

@@ -48,11 +48,11 @@ def build_host(force=False):
     os.makedirs(BIN, exist_ok=True)
     cli, info = os.path.join(BIN, "sketchlib"), os.path.join(BIN, "skm_info")
     srcs = [os.path.join(HOST, f) for f in ("dist_main.cpp", "multisketch.cpp", "multisketch.hpp", "skm_info.cpp",
-                                            "sketcher.cpp")]
+                                            "sketcher.cpp", "inverted.cpp", "inverted.hpp")]
     srcs.append(os.path.join(HERE, "..", "include", "sketchdist.h"))
     newest = max(os.path.getmtime(s) for s in srcs)
     if force or not os.path.exists(cli) or os.path.getmtime(cli) < max(newest, os.path.getmtime(LIB)):
-        subprocess.check_call(["g++"] + HOST_FLAGS + ["-o", cli, "dist_main.cpp", "multisketch.cpp", "sketcher.cpp", "-lz",
+        subprocess.check_call(["g++"] + HOST_FLAGS + ["-o", cli, "dist_main.cpp", "multisketch.cpp", "sketcher.cpp", "inverted.cpp", "-lz",
                                                     "-L", os.path.dirname(LIB), "-lsketchdist",
                                                     "-Wl,-rpath,$ORIGIN/../lib", "-ldl", "-lpthread", "-lrt"], cwd=HOST)
     if force or not os.path.exists(info) or os.path.getmtime(info) < newest:

@@ -4,8 +4,9 @@
 // of src/cli.rs:88-104), control flow of src/lib.rs:303-453 (extension stripping, --subset via
 // read_sketch_data_block, completeness files, set_k, knn clamping :379-382 / :411-414), and the text
 // writers of src/distances/distance_matrix.rs:175-209 (dense) and :360-401 (sparse), byte for byte.
-// `dist` is the accelerated path; `sketch` (DNA FASTA only, CPU, sketcher.cpp) is shipped so that inputs can be made
-// without the Rust binary.  The other sub-commands are not implemented.
+// `dist` and `inverted precluster` are the accelerated paths; `sketch` and `inverted build` (DNA FASTA only, CPU,
+// sketcher.cpp / inverted.cpp) are shipped so that inputs can be made without the Rust binary.  The other
+// sub-commands are not implemented.
 // Extra flag: --gpu <id> (default 0).  --threads is accepted for compatibility (the work runs on the GPU).
 #include <algorithm>
 #include <atomic>
@@ -22,6 +23,7 @@
 #include <vector>
 
 #include "../../../include/sketchdist.h"
+#include "inverted.hpp"
 #include "multisketch.hpp"
 
 using namespace skdhost;
@@ -151,7 +153,7 @@ DistArgs parse_args(int argc, char **argv) {
         } else if (!saw_dist) {
             if (t != "dist")
                 throw UsageError("unrecognized subcommand '" + t +
-                                 "': this build implements only `dist` (the B200-accelerated path) and `sketch` (DNA)");
+                                 "': this build implements only `dist`, `inverted` (the B200-accelerated paths) and `sketch` (DNA)");
             saw_dist = true;
         } else {
             pos.push_back(t);
@@ -634,6 +636,36 @@ int run(const DistArgs &a) {
     return 0;
 }
 
+// get_input_list: src/io.rs:182-224 (file list: name [file...] per line) / read_input_fastas: src/io.rs:20-38
+InputList get_input_list(const std::string &file_list, const std::vector<std::string> &seq_files) {
+    InputList inputs;
+    if (!file_list.empty()) {
+        std::ifstream in(file_list);
+        if (!in) throw Panic("Unable to open file_list " + file_list);
+        std::string line;
+        while (std::getline(in, line)) {
+            std::vector<std::string> f;
+            size_t pos = 0;
+            while (pos < line.size()) {
+                while (pos < line.size() && isspace((unsigned char)line[pos])) ++pos;
+                size_t e = pos;
+                while (e < line.size() && !isspace((unsigned char)line[e])) ++e;
+                if (e > pos) f.push_back(line.substr(pos, e - pos));
+                pos = e;
+            }
+            if (f.empty()) throw Panic("Unable to parse line in file_list");
+            if (f.size() == 1) inputs.push_back({f[0], {f[0]}});
+            else inputs.push_back({f[0], std::vector<std::string>(f.begin() + 1, f.end())});
+        }
+    } else {  // name = file name without directories
+        for (auto &file : seq_files) {
+            size_t slash = file.rfind('/');
+            inputs.push_back({slash == std::string::npos ? file : file.substr(slash + 1), {file}});
+        }
+    }
+    return inputs;
+}
+
 }  // namespace
 
 // ---- `sketchlib sketch`: flags of src/cli.rs:128-182 that apply to DNA assemblies
@@ -695,31 +727,7 @@ int run_sketch(int argc, char **argv) {
         if (k_seq.size() != 3 || k_seq[2] == 0) throw UsageError("--k-seq takes start,end,step");
         for (uint64_t k = k_seq[0]; k <= k_seq[1]; k += k_seq[2]) kmers.push_back(k);
     }
-    std::vector<std::pair<std::string, std::vector<std::string>>> inputs;
-    if (!file_list.empty()) {  // get_input_list: src/io.rs:182-224
-        std::ifstream in(file_list);
-        if (!in) throw Panic("Unable to open file_list " + file_list);
-        std::string line;
-        while (std::getline(in, line)) {
-            std::vector<std::string> f;
-            size_t pos = 0;
-            while (pos < line.size()) {
-                while (pos < line.size() && isspace((unsigned char)line[pos])) ++pos;
-                size_t e = pos;
-                while (e < line.size() && !isspace((unsigned char)line[e])) ++e;
-                if (e > pos) f.push_back(line.substr(pos, e - pos));
-                pos = e;
-            }
-            if (f.empty()) throw Panic("Unable to parse line in file_list");
-            if (f.size() == 1) inputs.push_back({f[0], {f[0]}});
-            else inputs.push_back({f[0], std::vector<std::string>(f.begin() + 1, f.end())});
-        }
-    } else {  // read_input_fastas: name = file name without directories, src/io.rs:20-38
-        for (auto &file : seq_files) {
-            size_t slash = file.rfind('/');
-            inputs.push_back({slash == std::string::npos ? file : file.substr(slash + 1), {file}});
-        }
-    }
+    InputList inputs = get_input_list(file_list, seq_files);
     log_info("Parsed " + std::to_string(inputs.size()) + " samples in input list");
     try {
         sketch_files_dna(output, inputs, kmers, sketch_size, !single_strand, (int)std::max<long long>(1, threads));
@@ -729,23 +737,395 @@ int run_sketch(int argc, char **argv) {
     return 0;
 }
 
+
+// ---- `sketchlib inverted build | query | precluster`: flags of src/cli.rs:324-462, control flow of src/lib.rs:484-792.
+// build / query are host-only; precluster makes the candidate lists on the host (Inverted::any_shared_bins over the
+// .skq bins) and runs the distances + per-row top-k on the GPU (skd_self_dists_knn_candidates).
+const char *INVERTED_USAGE =
+    "Usage: sketchlib inverted build [OPTIONS] -o <OUTPUT> [SEQ_FILES]...\n"
+    "         -f <FILE_LIST>  --write-skq  --species-names <F>  --metadata <F>  -s <SKETCH_SIZE> [1000]  -k <KMER> [21]\n"
+    "         --single-strand  --threads <N>\n"
+    "       sketchlib inverted query [OPTIONS] <SKI> [SEQ_FILES]...\n"
+    "         -f <FILE_LIST>  -o <OUTPUT>  --query-type <match-count|all-bins|any-bins>  --threads <N>\n"
+    "       sketchlib inverted precluster [OPTIONS] <SKI> (--skd <DB> | --count)\n"
+    "         -o <OUTPUT>  --knn <KNN> [50]  --ani  --threads <N>  --ref-completeness-file <F>\n"
+    "         --completeness-cutoff <X> [0.64]  --retain-unmatched <singleton|bruteforce>  --gpu <ID>\n";
+
+struct InvArgs {
+    std::string cmd;  // build | query | precluster
+    std::vector<std::string> pos;
+    std::string file_list, output, species_names, metadata, skd, query_type = "match-count", retain, ref_completeness_file;
+    bool has_output = false, write_skq = false, single_strand = false, count = false, ani = false, verbose = false,
+         quiet = false;
+    uint64_t sketch_size = 1000, kmer = 21, knn = 50;  // DEFAULT_SKETCHSIZE, DEFAULT_KMER, DEFAULT_KNN
+    long long threads = 1;
+    double completeness_cutoff = 0.64;
+    int gpu = 0;
+};
+
+InvArgs parse_inverted_args(int argc, char **argv) {
+    InvArgs a;
+    int words = 0;
+    for (int i = 1; i < argc; ++i) {
+        std::string t = argv[i];
+        auto value = [&](const char *name) -> std::string {
+            size_t eq = t.find('=');
+            if (t.rfind("--", 0) == 0 && eq != std::string::npos) return t.substr(eq + 1);
+            if (t.rfind("--", 0) != 0 && t.size() > 2) return t[2] == '=' ? t.substr(3) : t.substr(2);
+            if (i + 1 >= argc) throw UsageError(std::string("a value is required for '") + name + "' but none was supplied");
+            return argv[++i];
+        };
+        auto is = [&](const char *name) { return t == name || t.rfind(std::string(name) + "=", 0) == 0; };
+        auto shortopt = [&](char c) { return t.size() >= 2 && t[0] == '-' && t[1] == c; };
+        if (t == "-h" || t == "--help") {
+            fputs(INVERTED_USAGE, stdout);
+            exit(0);
+        } else if (t == "-v" || t == "--verbose") a.verbose = true;
+        else if (t == "--quiet") a.quiet = true;
+        else if (t == "--write-skq") a.write_skq = true;
+        else if (t == "--single-strand") a.single_strand = true;
+        else if (t == "--count") a.count = true;
+        else if (t == "--ani") a.ani = true;
+        else if (is("--species-names")) a.species_names = value("--species-names <SPECIES_NAMES>");
+        else if (is("--metadata")) a.metadata = value("--metadata <METADATA>");
+        else if (is("--sketch-size")) a.sketch_size = (uint64_t)parse_uint(value("--sketch-size"), "--sketch-size <SKETCH_SIZE>");
+        else if (is("--kmer-length")) a.kmer = (uint64_t)parse_uint(value("--kmer-length"), "--kmer-length <KMER_LENGTH>");
+        else if (is("--skd")) a.skd = value("--skd <SKD>");
+        else if (is("--knn")) a.knn = (uint64_t)parse_uint(value("--knn <KNN>"), "--knn <KNN>");
+        else if (is("--query-type")) a.query_type = value("--query-type <QUERY_TYPE>");
+        else if (is("--retain-unmatched")) a.retain = value("--retain-unmatched <RETAIN_UNMATCHED>");
+        else if (is("--ref-completeness-file")) a.ref_completeness_file = value("--ref-completeness-file");
+        else if (is("--completeness-cutoff")) {
+            std::string v = value("--completeness-cutoff");
+            char *end = nullptr;
+            a.completeness_cutoff = strtod(v.c_str(), &end);
+            if (v.empty() || end != v.c_str() + v.size())
+                throw UsageError("invalid value '" + v + "' for '--completeness-cutoff <COMPLETENESS_CUTOFF>'");
+        } else if (is("--threads")) {
+            a.threads = parse_uint(value("--threads"), "--threads <THREADS>");
+            if (a.threads < 1) throw UsageError("invalid value for '--threads <THREADS>': Threads must be one or higher");
+        } else if (is("--gpu")) a.gpu = (int)parse_uint(value("--gpu <ID>"), "--gpu <ID>");
+        else if (is("--min-count") || is("--min-qual")) (void)value("option");  // reads are not supported by this build
+        else if (t.rfind("--", 0) == 0) throw UsageError("unexpected argument '" + t + "' found");
+        else if (shortopt('o')) {
+            a.output = value("-o <OUTPUT>");
+            a.has_output = true;
+        } else if (shortopt('f')) a.file_list = value("-f <FILE_LIST>");
+        else if (shortopt('s')) a.sketch_size = (uint64_t)parse_uint(value("-s"), "-s <SKETCH_SIZE>");
+        else if (shortopt('k')) a.kmer = (uint64_t)parse_uint(value("-k"), "-k <KMER_LENGTH>");
+        else if (t.size() > 1 && t[0] == '-') throw UsageError("unexpected argument '" + t + "' found");
+        else if (words == 0) ++words;  // "inverted"
+        else if (words == 1) {
+            a.cmd = t;
+            ++words;
+        } else a.pos.push_back(t);
+    }
+    if (a.cmd != "build" && a.cmd != "query" && a.cmd != "precluster")
+        throw UsageError("inverted needs a subcommand: build, query or precluster");
+    return a;
+}
+
+FILE *open_output(const InvArgs &a) {
+    if (!a.has_output) return stdout;
+    FILE *f = fopen(a.output.c_str(), "wb");
+    if (!f) throw Panic("could not create " + a.output);
+    return f;
+}
+
+int inverted_build(const InvArgs &a) {
+    if (a.output.empty()) throw UsageError("the following required arguments were not provided:\n  -o <OUTPUT>");
+    if (a.file_list.empty() == a.pos.empty())
+        throw UsageError("exactly one of <SEQ_FILES>... and -f <FILE_LIST> is required");
+    log_info("Getting input files");
+    InputList inputs = get_input_list(a.file_list, a.pos);
+    log_info("Parsed " + std::to_string(inputs.size()) + " samples in input list");
+    std::vector<std::string> distinct;  // first-appearance order
+    {
+        std::unordered_map<std::string, size_t> seen;
+        for (auto &in : inputs)
+            if (seen.emplace(in.first, distinct.size()).second) distinct.push_back(in.first);
+    }
+    std::vector<size_t> order(inputs.size());
+    std::unordered_map<std::string, std::string> label_of;
+    bool have_labels = false;
+    if (!a.species_names.empty()) {
+        log_info("Reordering samples using labels in " + a.species_names);
+        std::vector<std::string> msgs;
+        try {
+            order = reorder_input_files(inputs, a.species_names, &label_of, &have_labels, &msgs);
+        } catch (const std::exception &e) {
+            throw Panic(e.what());
+        }
+        for (auto &m : msgs) log_info(m);
+        if (!have_labels) log_warn("Could not find any sample names in " + a.species_names);
+    } else {
+        std::unordered_map<std::string, size_t> pos;
+        for (size_t i = 0; i < distinct.size(); ++i) pos[distinct[i]] = i;
+        for (size_t i = 0; i < inputs.size(); ++i) order[i] = pos[inputs[i].first];
+    }
+    std::optional<std::vector<std::string>> labels, metadata;
+    if (have_labels) {
+        labels.emplace(distinct.size(), "");
+        for (size_t i = 0; i < inputs.size(); ++i) {
+            auto it = label_of.find(inputs[i].first);
+            if (order[i] < labels->size()) (*labels)[order[i]] = it == label_of.end() ? "" : it->second;
+        }
+    }
+    if (!a.metadata.empty()) {  // parse_metadata_info: src/io.rs:118-137
+        std::ifstream f(a.metadata);
+        if (!f) throw Panic("Unable to open species name file " + a.metadata);
+        std::unordered_map<std::string, std::string> dict;
+        std::string line;
+        while (std::getline(f, line)) {
+            size_t tab = line.find('\t');
+            if (tab == std::string::npos) throw Panic("index out of bounds: metadata lines need label<tab>metadata");
+            size_t tab2 = line.find('\t', tab + 1);
+            if (!dict.emplace(line.substr(0, tab), line.substr(tab + 1, tab2 == std::string::npos ? tab2 : tab2 - tab - 1)).second)
+                throw Panic("Some entry in metadata is duplicated");
+        }
+        log_info("Got metadata for " + std::to_string(dict.size()) + " labels");
+        metadata.emplace(distinct.size(), "");
+        for (size_t i = 0; i < inputs.size(); ++i) {
+            auto it = dict.find(inputs[i].first);
+            if (it == dict.end()) throw Panic("no metadata for sample " + inputs[i].first);
+            if (order[i] < metadata->size()) (*metadata)[order[i]] = it->second;
+        }
+    }
+    const std::string skq = a.write_skq ? a.output + ".skq" : "";
+    log_info("Creating sketches");
+    if (!skq.empty()) log_info("Writing bins for use with precluster as " + skq);
+    try {
+        Inverted inv = Inverted::build(inputs, order, a.kmer, a.sketch_size, !a.single_strand, (int)a.threads, skq, metadata,
+                                       labels, nullptr);
+        log_info("Saving inverted index to " + a.output + ".ski");
+        inv.save(a.output);
+        log_info("Index info:\n" + inv.debug_info());
+    } catch (const std::exception &e) {
+        throw Panic(e.what());
+    }
+    return 0;
+}
+
+Inverted load_ski(const std::string &ski) {
+    const std::string prefix = strip_sketch_extension(ski);
+    log_info("Loading inverted index from " + prefix + ".ski");
+    return Inverted::load(prefix);  // std::runtime_error -> "Error: ..." exit 1, like the reference's `?`
+}
+
+int inverted_query(const InvArgs &a) {
+    if (a.pos.empty()) throw UsageError("the following required arguments were not provided:\n  <SKI>");
+    int mode = a.query_type == "match-count" ? 0 : a.query_type == "all-bins" ? 1 : a.query_type == "any-bins" ? 2 : -1;
+    if (mode < 0)
+        throw UsageError("invalid value '" + a.query_type + "' for '--query-type <QUERY_TYPE>'\n  [possible values: match-count, all-bins, any-bins]");
+    std::vector<std::string> seq_files(a.pos.begin() + 1, a.pos.end());
+    if (a.file_list.empty() == seq_files.empty())
+        throw UsageError("exactly one of <SEQ_FILES>... and -f <FILE_LIST> is required");
+    FILE *out = open_output(a);
+    Inverted inv = load_ski(a.pos[0]);
+    log_info("Read inverted index:\n" + inv.debug_info());
+    log_info("Getting input queries");
+    InputList inputs = get_input_list(a.file_list, seq_files);
+    log_info("Parsed " + std::to_string(inputs.size()) + " samples in input query list");
+    log_info("Sketching input queries");
+    std::vector<size_t> order(inputs.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+    std::vector<std::vector<uint16_t>> queries;
+    std::vector<std::string> names;
+    try {
+        Inverted::sketch_files(inputs, order, inv.kmer_size, inv.sketch_size(), inv.rc, (int)a.threads, &queries, &names);
+    } catch (const std::exception &e) {
+        throw Panic(e.what());
+    }
+    log_info("Running queries in mode: " + a.query_type);
+    std::string text = "Query";
+    if (mode == 0) {
+        for (auto &n : inv.sample_names) text += "\t" + n;
+        text += "\n";
+    } else {
+        text += "\tMatches\n";
+    }
+    for (size_t q = 0; q < queries.size(); ++q) {  // the reference writes rows in completion order; here: input order
+        text += names[q];
+        if (mode == 0) {
+            for (uint32_t c : inv.query_against_inverted_index(queries[q].data())) text += "\t" + std::to_string(c);
+        } else {
+            std::vector<uint32_t> hits = mode == 1 ? inv.all_shared_bins(queries[q].data()) : inv.any_shared_bins(queries[q].data());
+            for (size_t h = 0; h < hits.size(); ++h) text += (h ? "," : "\t") + inv.sample_names[hits[h]];
+        }
+        text += "\n";
+    }
+    fwrite(text.data(), 1, text.size(), out);
+    if (out != stdout) fclose(out);
+    return 0;
+}
+
+int inverted_precluster(const InvArgs &a) {
+    if (a.pos.empty()) throw UsageError("the following required arguments were not provided:\n  <SKI>");
+    if (a.pos.size() > 1) throw UsageError("unexpected argument '" + a.pos[1] + "' found");
+    if (a.count == !a.skd.empty())
+        throw UsageError(a.count ? "the argument '--skd <SKD>' cannot be used with '--count'"
+                                 : "the following required arguments were not provided:\n  <--skd <SKD>|--count>");
+    int retain = 0;
+    if (!a.retain.empty()) {
+        retain = a.retain == "singleton" ? 1 : a.retain == "bruteforce" ? 2 : -1;
+        if (retain < 0)
+            throw UsageError("invalid value '" + a.retain + "' for '--retain-unmatched <RETAIN_UNMATCHED>'\n  [possible values: singleton, bruteforce]");
+    }
+    Gpu gpu;  // destroyed after the database
+    const std::string input_prefix = strip_sketch_extension(a.pos[0]);
+    Inverted inv = load_ski(a.pos[0]);
+    if (a.count) {
+        const uint64_t ns = inv.n_samples();
+        printf("Identified %llu prefilter pairs from a max of %llu\n", (unsigned long long)inv.any_shared_bin_pairs(),
+               (unsigned long long)(ns * (ns - 1) / 2));
+        return 0;
+    }
+    FILE *out = open_output(a);
+    const std::string skq_file = input_prefix + ".skq";
+    log_info("Loading queries from " + skq_file);
+    const size_t stride = inv.sketch_size();
+    std::vector<uint16_t> skq;
+    try {
+        skq = read_skq(skq_file, inv.n_samples() * stride);
+    } catch (const std::exception &e) {
+        throw Panic(e.what());
+    }
+    const std::string ref_name = strip_sketch_extension(a.skd);
+    Loaded refs;
+    try {
+        refs.meta = MultiSketch::load_metadata(ref_name);
+    } catch (const std::exception &) {
+        throw Panic("Could not read sketch metadata from " + ref_name + ".skm");
+    }
+    const uint64_t n = refs.meta.number_samples_loaded();
+    if (n < 2) throw Panic("attempt to subtract with overflow: fewer than two samples loaded");
+    uint64_t knn = a.knn;
+    if (knn >= n) {
+        log_warn("knn=" + std::to_string(knn) + " is higher than number of samples=" + std::to_string(n));
+        knn = n - 1;
+    }
+    if (knn == 0) throw std::runtime_error("knn must be at least 1");
+    if (!refs.meta.get_k_idx(inv.kmer_size))
+        throw Panic("K-mer size " + std::to_string(inv.kmer_size) + " used for .ski not found in .skd: K-mer size " +
+                    std::to_string(inv.kmer_size) + " not found in file");
+    std::vector<double> ref_c;
+    if (!a.ref_completeness_file.empty()) {
+        std::vector<std::string> warnings;
+        ref_c = read_completeness_file(a.ref_completeness_file, refs.meta, &warnings);
+        for (auto &w : warnings) log_warn(w);
+    }
+    // i (skd order) -> ski index, and back (src/distances/mod.rs:412-438)
+    std::unordered_map<std::string, size_t> ski_of;
+    for (size_t s = 0; s < inv.n_samples(); ++s) ski_of[inv.sample_names[s]] = s;
+    std::vector<size_t> ski_index(n);
+    std::vector<int64_t> skd_from_ski(inv.n_samples(), -1);
+    std::string not_found;
+    for (uint64_t i = 0; i < n; ++i) {
+        auto it = ski_of.find(refs.meta.sketch_name(i));
+        if (it == ski_of.end()) {
+            not_found += (not_found.empty() ? "\"" : ", \"") + refs.meta.sketch_name(i) + "\"";
+            continue;
+        }
+        ski_index[i] = it->second;
+        skd_from_ski[it->second] = (int64_t)i;
+    }
+    if (!not_found.empty())
+        throw Panic("The following samples in the .skd could not be found in the .ski:\n[" + not_found + "]");
+    log_info("Calculating sparse ref vs ref distances with " + std::to_string(knn) + " nearest neighbours");
+    log_info("Preclustering with k=" + std::to_string(inv.kmer_size) + " and s=" + std::to_string(stride));
+    if (retain) log_info(std::string("Retain unmatched mode: ") + (retain == 1 ? "Retain as singletons" : "Brute-force against all"));
+
+    // Candidate lists (CSR over .skd indices), --threads rows at a time
+    std::vector<std::vector<uint64_t>> cand(n);
+    {
+        std::atomic<uint64_t> next{0};
+        auto worker = [&] {
+            for (;;) {
+                const uint64_t i = next.fetch_add(1);
+                if (i >= n) break;
+                bool other = false;
+                for (uint32_t j : inv.any_shared_bins(skq.data() + ski_index[i] * stride)) {
+                    const int64_t skd_j = skd_from_ski[j];
+                    if (skd_j < 0) continue;  // in the .ski only
+                    cand[i].push_back((uint64_t)skd_j);
+                    other |= (uint64_t)skd_j != i;
+                }
+                if (retain == 2 && !other) {  // brute force: every sample is a candidate (mod.rs:501-524)
+                    cand[i].resize(n);
+                    for (uint64_t j = 0; j < n; ++j) cand[i][j] = j;
+                } else {
+                    std::sort(cand[i].begin(), cand[i].end());
+                }
+            }
+        };
+        std::vector<std::thread> pool;
+        for (long long t = 0; t < a.threads; ++t) pool.emplace_back(worker);
+        for (auto &t : pool) t.join();
+    }
+    std::vector<uint64_t> off(n + 1, 0), flat;
+    for (uint64_t i = 0; i < n; ++i) off[i + 1] = off[i] + cand[i].size();
+    flat.reserve(off[n]);
+    for (auto &c : cand) flat.insert(flat.end(), c.begin(), c.end());
+    log_info(std::to_string(off[n]) + " candidate comparisons (of " + std::to_string(n * (n - 1)) + ")");
+
+    if (skd_ctx_create(a.gpu, &gpu.ctx) != SKD_OK) throw std::runtime_error(skd_last_error(nullptr));
+    log_info("Loading sketch data from " + ref_name + ".skd");
+    load_db(gpu, refs, ref_name, nullptr);
+    skd_dist_type dt;
+    if (skd_set_k(gpu.ctx, refs.db, (int64_t)inv.kmer_size, a.ani ? 1 : 0, &dt) != SKD_OK)
+        throw Panic(std::string("Error setting k size: ") + skd_last_error(gpu.ctx));
+    std::vector<uint64_t> idx(n * knn);
+    std::vector<float> d0(n * knn);
+    gpu.check(skd_self_dists_knn_candidates(gpu.ctx, refs.db, knn, dt, ref_c.empty() ? nullptr : ref_c.data(),
+                                            a.completeness_cutoff, off.data(), flat.data(), retain, idx.data(), d0.data()));
+    log_info("Writing out in sparse matrix form");
+    std::string text;
+    for (uint64_t r = 0; r < n; ++r) {
+        const std::string &rn = refs.meta.sketch_name(r);
+        for (uint64_t t = 0; t < knn; ++t) {
+            const std::string &cn = refs.meta.sketch_name(idx[r * knn + t]);
+            if (d0[r * knn + t] < 1.0f || cn != rn) append_line(text, rn, cn, d0[r * knn + t], nullptr);
+        }
+        if (text.size() > (1 << 22)) {
+            fwrite(text.data(), 1, text.size(), out);
+            text.clear();
+        }
+    }
+    fwrite(text.data(), 1, text.size(), out);
+    if (out != stdout) fclose(out);
+    return 0;
+}
+
+int run_inverted(int argc, char **argv) {
+    InvArgs a = parse_inverted_args(argc, argv);
+    g_level = a.quiet ? 0 : (a.verbose ? 2 : 1);
+    if (a.cmd == "build") return inverted_build(a);
+    if (a.cmd == "query") return inverted_query(a);
+    return inverted_precluster(a);
+}
+
 int main(int argc, char **argv) {
     auto start = std::chrono::steady_clock::now();
-    bool is_sketch = false;
+    bool is_sketch = false, is_inverted = false;
     for (int i = 1; i < argc; ++i) {
         if (argv[i][0] == '-') continue;
         is_sketch = std::string(argv[i]) == "sketch";
+        is_inverted = std::string(argv[i]) == "inverted";
         break;
     }
-    if (is_sketch) {
+    if (is_sketch || is_inverted) {
         try {
-            run_sketch(argc, argv);
+            if (is_sketch) run_sketch(argc, argv);
+            else run_inverted(argc, argv);
         } catch (const UsageError &e) {
             fprintf(stderr, "error: %s\n", e.what());
             return 2;
         } catch (const Panic &e) {
             fprintf(stderr, "thread 'main' panicked:\n%s\n", e.what());
             return 101;
+        } catch (const std::exception &e) {
+            fprintf(stderr, "Error: %s\n", e.what());
+            return 1;
         }
         if (g_level >= 1) {
             auto secs = std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - start).count();

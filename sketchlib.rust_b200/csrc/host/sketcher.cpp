@@ -26,6 +26,8 @@
 
 namespace skdhost {
 
+std::string snappy_frame_encode(const std::string &payload);
+
 namespace {
 constexpr int kBBits = 14;
 constexpr uint64_t kSignMod = ((uint64_t)1 << 61) - 1;  // src/sketch/mod.rs:36
@@ -118,6 +120,45 @@ bool densify(std::vector<uint64_t> &signs) {  // src/sketch/mod.rs:226-258
     return true;
 }
 
+// Bin minima of every canonical k-mer hash of `seq` (records separated by '\n'); `signs` must be pre-filled by the
+// caller (UINT64_MAX = empty bin).  Returns false when no k-mer fits.  src/sketch/mod.rs:132-153, 156-176.
+bool bin_minima(const std::string &seq, uint64_t k, bool rc, std::vector<uint64_t> &signs) {
+    const uint64_t nbins = signs.size(), bin_size = (kSignMod + nbins - 1) / nbins;
+    uint64_t out_f[4], in_r[4];  // srol^k(seed[b]) leaving the forward hash; srol^(k-1)(seed[rc b]) entering the reverse
+    for (int b = 0; b < 4; ++b) {
+        out_f[b] = srol_n(kSeed[b], k);
+        in_r[b] = srol_n(kSeed[b ^ 2], k - 1);
+    }
+    uint64_t fh = 0, rh = 0, run = 0;
+    bool any = false;
+    const size_t len = seq.size();
+    for (size_t pos = 0; pos < len; ++pos) {
+        const unsigned char c = (unsigned char)seq[pos];
+        if (!valid_base(c)) {
+            run = 0;
+            fh = rh = 0;
+            continue;
+        }
+        const int b = (c >> 1) & 3;
+        if (run < k) {  // still filling the first window after a break
+            fh = srol(fh) ^ kSeed[b];
+            rh ^= srol_n(kSeed[b ^ 2], run);
+            ++run;
+            if (run < k) continue;
+        } else {        // roll: drop seq[pos-k], add seq[pos]
+            const int old = ((unsigned char)seq[pos - k] >> 1) & 3;
+            fh = srol(fh) ^ kSeed[b] ^ out_f[old];
+            rh = sror(rh ^ kSeed[old ^ 2]) ^ in_r[b];
+        }
+        any = true;
+        const uint64_t h = rc ? std::min(fh, rh) : fh;
+        const uint64_t sign = h % kSignMod;
+        uint64_t &slot = signs[sign / bin_size];
+        if (sign < slot) slot = sign;
+    }
+    return any;
+}
+
 void sketch_sample(Sample &s, const std::vector<uint64_t> &kmers, uint64_t W, bool rc) {
     std::string seq;
     read_sequences(s, seq);
@@ -132,45 +173,13 @@ void sketch_sample(Sample &s, const std::vector<uint64_t> &kmers, uint64_t W, bo
         }
     }
     if (total_valid == 0) throw std::runtime_error("Sample " + s.name + " has no valid sequence");
-    const uint64_t nbins = 64 * W, bin_size = (kSignMod + nbins - 1) / nbins;
+    const uint64_t nbins = 64 * W;
     s.usigs.assign(kmers.size() * W * kBBits, 0);
     std::vector<uint64_t> signs(nbins);
     for (size_t ki = 0; ki < kmers.size(); ++ki) {
-        const uint64_t k = kmers[ki];
         std::fill(signs.begin(), signs.end(), UINT64_MAX);
-        uint64_t out_f[4], in_r[4];  // srol^k(seed[b]) leaving the forward hash; srol^(k-1)(seed[rc b]) entering the reverse
-        for (int b = 0; b < 4; ++b) {
-            out_f[b] = srol_n(kSeed[b], k);
-            in_r[b] = srol_n(kSeed[b ^ 2], k - 1);
-        }
-        uint64_t fh = 0, rh = 0, run = 0;
-        bool any = false;
-        const size_t len = seq.size();
-        for (size_t pos = 0; pos < len; ++pos) {
-            const unsigned char c = (unsigned char)seq[pos];
-            if (!valid_base(c)) {
-                run = 0;
-                fh = rh = 0;
-                continue;
-            }
-            const int b = (c >> 1) & 3;
-            if (run < k) {  // still filling the first window after a break
-                fh = srol(fh) ^ kSeed[b];
-                rh ^= srol_n(kSeed[b ^ 2], run);
-                ++run;
-                if (run < k) continue;
-            } else {        // roll: drop seq[pos-k], add seq[pos]
-                const int old = ((unsigned char)seq[pos - k] >> 1) & 3;
-                fh = srol(fh) ^ kSeed[b] ^ out_f[old];
-                rh = sror(rh ^ kSeed[old ^ 2]) ^ in_r[b];
-            }
-            any = true;
-            const uint64_t h = rc ? std::min(fh, rh) : fh;
-            const uint64_t sign = h % kSignMod;
-            uint64_t &slot = signs[sign / bin_size];
-            if (sign < slot) slot = sign;
-        }
-        if (!any) throw std::runtime_error("K-mer larger than smallest valid sequence");  // nthash_iterator.rs:60
+        if (!bin_minima(seq, kmers[ki], rc, signs))
+            throw std::runtime_error("K-mer larger than smallest valid sequence");  // nthash_iterator.rs:60
         s.densified |= densify(signs);
         uint64_t *us = s.usigs.data() + ki * W * kBBits;
         for (uint64_t bin = 0; bin < nbins; ++bin)  // fill_usigs, src/sketch/mod.rs:215-223
@@ -262,6 +271,16 @@ void write_skm(const std::string &prefix, const std::vector<Sample> &samples, co
     cbor_text(c, "hash_type");
     cbor_text(c, "DNA");
 
+    const std::string out = snappy_frame_encode(c);
+    std::ofstream f(prefix + ".skm", std::ios::binary);
+    if (!f) throw std::runtime_error("could not create " + prefix + ".skm");
+    f.write(out.data(), (std::streamsize)out.size());
+}
+
+}  // namespace
+
+// Snappy frame stream of uncompressed chunks (any snappy frame reader accepts them).
+std::string snappy_frame_encode(const std::string &c) {
     std::string out("\xff\x06\x00\x00sNaPpY", 10);
     for (size_t off = 0; off < c.size(); off += 65536) {
         const size_t n = std::min<size_t>(65536, c.size() - off);
@@ -275,12 +294,30 @@ void write_skm(const std::string &prefix, const std::vector<Sample> &samples, co
         for (int i = 0; i < 4; ++i) out.push_back((char)((masked >> (8 * i)) & 0xff));
         out.append(c, off, n);
     }
-    std::ofstream f(prefix + ".skm", std::ios::binary);
-    if (!f) throw std::runtime_error("could not create " + prefix + ".skm");
-    f.write(out.data(), (std::streamsize)out.size());
+    return out;
 }
 
-}  // namespace
+// Sketch::get_signs_no_densify for one DNA sample at one k over `nbins` bins (src/sketch/mod.rs:156-176; used by the
+// inverted index, whose bin count need not be a multiple of 64).  UINT64_MAX marks an empty bin.
+std::vector<uint64_t> dna_bin_minima(const std::string &name, const std::vector<std::string> &files, uint64_t k,
+                                     uint64_t nbins, bool rc) {
+    Sample s;
+    s.name = name;
+    s.files = files;
+    std::string seq;
+    read_sequences(s, seq);
+    std::vector<uint64_t> signs(nbins, UINT64_MAX);
+    bool valid = false;
+    for (unsigned char c : seq)
+        if (c != '\n' && valid_base(c)) {
+            valid = true;
+            break;
+        }
+    if (!valid) throw std::runtime_error("Genome " + name + " has no valid sequence");
+    if (!bin_minima(seq, k, rc, signs)) throw std::runtime_error("K-mer larger than smallest valid sequence");
+    return signs;
+}
+bool densify_bins(std::vector<uint64_t> &signs) { return densify(signs); }
 
 // Entry point used by the CLI.  inputs: (name, files).  Throws std::runtime_error.
 void sketch_files_dna(const std::string &output_prefix, const std::vector<std::pair<std::string, std::vector<std::string>>> &inputs,

@@ -1,6 +1,6 @@
 """Candidate-list ("precluster") kNN: host side of the reference's self_dists_knn_precluster
 (src/distances/mod.rs:399-553).  The reference gets its candidates from an inverted index (`.ski`,
-src/inverted.rs, out of scope here: roaring bitmaps in MessagePack); the same candidate sets follow from the
+src/inverted.rs; read and written by the C++ CLI, csrc/host/inverted.cpp); the same candidate sets follow from the
 untransposed bins the reference also requires for this mode (`.skq`, u16 per bin, src/inverted.rs:92-100):
 sample j is a candidate of sample i iff they hold the same value in at least one bin position
 (Inverted::any_shared_bins, src/inverted.rs:259-268).  Distances and the per-row top-k run on the GPU

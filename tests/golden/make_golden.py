@@ -8,11 +8,17 @@
   with `--k-seq 17,31,4 -s 10000` (reference tests/distance.rs:281-301); input of the
   dists_knn_* / dists_subset goldens.
 * rfile_k17-29_s1024.{skd,json}: BASELINE.json configs[0] (default sketch size, k=17..29 step 4).
+* inverted.ski, reordered_inv.{ski,skq}: inverted indexes of the same 4 genomes (`inverted build -k 21 -s 10
+  --write-skq [--species-names species_names.txt]`, reference tests/inverted.rs:256-266, 360-373) written by this
+  repo's C++ builder (the reference ships no .ski); its .skq is checked byte for byte against the reference's
+  inverted.skq fixture before anything is written.
 """
 import json
 import os
 import shutil
+import subprocess
 import sys
+import tempfile
 
 import numpy as np
 
@@ -34,9 +40,21 @@ def main():
     for f in ("subset.txt", "rfile.txt", "completeness.txt"):
         shutil.copyfile(os.path.join(IN, f), os.path.join(fx, f))
     for f in ("dists_knn_ca", "dists_knn_jaccard", "dists_knn_ani", "dists_subset", "inverted_precluster",
-              "inverted_precluster_ani"):
+              "inverted_precluster_ani", "inverted_query_count", "inverted_query_any", "inverted_query_all"):
         shutil.copyfile(os.path.join(OUT, f + ".stdout"), os.path.join(fx, f + ".stdout"))
     shutil.copyfile(os.path.join(OUT, "inverted.skq"), os.path.join(fx, "inverted.skq"))  # 4 samples x 10 u16 bins
+
+    shutil.copyfile(os.path.join(IN, "species_names.txt"), os.path.join(fx, "species_names.txt"))
+    import sketchlib.rust_b200.build as b
+    cli, _ = b.build_host()
+    with tempfile.TemporaryDirectory() as d:
+        subprocess.check_call([cli, "inverted", "build", "-o", os.path.join(d, "inverted"), "-k", "21", "-s", "10", "-f",
+                               "rfile.txt", "--write-skq", "--quiet"], cwd=IN)
+        assert open(os.path.join(d, "inverted.skq"), "rb").read() == open(os.path.join(OUT, "inverted.skq"), "rb").read()
+        subprocess.check_call([cli, "inverted", "build", "-o", os.path.join(d, "reordered_inv"), "-k", "21", "-s", "10",
+                               "-f", "rfile.txt", "--write-skq", "--species-names", "species_names.txt", "--quiet"], cwd=IN)
+        for f in ("inverted.ski", "reordered_inv.ski", "reordered_inv.skq"):
+            shutil.copyfile(os.path.join(d, f), os.path.join(fx, f))
 
     names = [l.split()[0] for l in open(os.path.join(IN, "rfile.txt"))]
     recs = {n: oracle.read_fasta_records(os.path.join(IN, n)) for n in names}

@@ -313,3 +313,204 @@ def test_cli_multi_gpu_knn_equals_single_gpu(tools, tmp_path):
         two = run([cli, "dist", rp] + args + ["--gpus", "2"])
         assert one.returncode == 0 and two.returncode == 0, (args, one.stderr, two.stderr)
         assert one.stdout == two.stdout and len(one.stdout) > 0, args
+
+
+# ---------------------------------------------------------------- inverted index (.ski / .skq) and precluster
+
+def _roaring_values(blob):
+    """Independent reader of the portable RoaringBitmap layout without run containers (cookie 12346)."""
+    import struct
+    cookie, n = struct.unpack_from("<II", blob, 0)
+    assert cookie == 12346
+    desc = [struct.unpack_from("<HH", blob, 8 + 4 * i) for i in range(n)]
+    offs = struct.unpack_from(f"<{n}I", blob, 8 + 4 * n)
+    out = []
+    for (key, card_m1), off in zip(desc, offs):
+        card = card_m1 + 1
+        if card > 4096:
+            words = np.frombuffer(blob, dtype="<u8", count=1024, offset=off)
+            bits = np.unpackbits(words.view(np.uint8), bitorder="little")
+            vals = np.flatnonzero(bits)
+            assert len(vals) == card
+        else:
+            vals = np.frombuffer(blob, dtype="<u2", count=card, offset=off)
+        out += [(key << 16) | int(v) for v in vals]
+    return out
+
+
+def _read_ski(path):
+    import msgpack
+    from oracle import skm
+    obj = msgpack.unpackb(skm.snappy_frame_decode(open(path, "rb").read()), raw=False, strict_map_key=False)
+    assert len(obj) == 9   # index, n_samples, sample_names, metadata, labels, kmer_size, sketch_version, rc, hash_type
+    index = [{k: _roaring_values(v) for k, v in bin_.items()} for bin_ in obj[0]]
+    return index, obj[1:]
+
+
+def test_inverted_build_reproduces_reference_skq_and_query_goldens(tools, tmp_path):
+    ref_in = "/root/reference/tests/test_files_in"
+    if not os.path.exists(os.path.join(ref_in, "rfile.txt")):
+        pytest.skip("reference checkout not present (GPU box)")
+    cli, _ = tools
+    out = str(tmp_path / "inverted")
+    r = run([cli, "inverted", "build", "-o", out, "-v", "-k", "21", "-s", "10", "-f", "rfile.txt", "--write-skq"], cwd=ref_in)
+    assert r.returncode == 0, r.stderr
+    assert "sketch_size=10\nn_samples=4\nkmer=21\nrc=true\ninverted=true" in r.stderr
+    # reference tests/inverted.rs:268-272: the .skq the reference's own build wrote
+    assert open(out + ".skq", "rb").read() == open(os.path.join(FIXTURES, "inverted.skq"), "rb").read()
+    assert open(out + ".ski", "rb").read() == open(os.path.join(FIXTURES, "inverted.ski"), "rb").read()
+    r = run([cli, "inverted", "precluster", "-v", "--count", out + ".ski"])   # tests/inverted.rs:277-285
+    assert r.stdout == "Identified 2 prefilter pairs from a max of 6\n"
+    for qt, gold in ((None, "inverted_query_count"), ("any-bins", "inverted_query_any"), ("all-bins", "inverted_query_all")):
+        cmd = [cli, "inverted", "query", "-v", "-f", "rfile.txt", out + ".ski"] + (["--query-type", qt] if qt else [])
+        r = run(cmd, cwd=ref_in)
+        assert r.returncode == 0, r.stderr
+        want = open(os.path.join(FIXTURES, gold + ".stdout")).read().splitlines()
+        got = r.stdout.splitlines()
+        assert got[0] == want[0] and sorted(got[1:]) == sorted(want[1:])     # rows are unordered in the reference
+    # --species-names reorders the index (tests/inverted.rs:131-166, inverted_sketch_info_reorder.stdout)
+    files = ["14412_3#82.contigs_velvet.fa.gz", "14412_3#84.contigs_velvet.fa.gz", "R6.fa.gz", "TIGR4.fa.gz"]
+    r = run([cli, "inverted", "build", "-o", out + "_re", "-k", "61", "-s", "63", "--species-names", "species_names.txt"] + files,
+            cwd=ref_in)
+    assert r.returncode == 0, r.stderr
+    _, meta = _read_ski(out + "_re.ski")
+    assert meta[1] == ["TIGR4.fa.gz", "R6.fa.gz", files[0], files[1]] and meta[3] == ["Spn", "Spn", "N m", ""]
+    assert meta[4:] == [61, "0.3.0", True, "DNA"]
+
+
+def test_inverted_index_content_and_ski_format(tools, tmp_path):
+    """Synthetic genomes: the .ski decoded by an independent MessagePack + roaring reader equals the inverted index of
+    the .skq bins; queries agree with numpy; an index loaded back from the .ski gives the same answers."""
+    cli, _ = tools
+    rng = np.random.default_rng(5)
+    anc = rng.choice(list("ACGT"), size=(3, 20000))
+    names, rows = [], []
+    for g in range(12):
+        seq = anc[g % 3].copy()
+        pos = rng.choice(seq.size, size=40 * (g // 3 + 1), replace=False)
+        seq[pos] = rng.choice(list("ACGT"), size=pos.size)
+        _write_fasta(tmp_path / f"g{g}.fa", [("c", "".join(seq))])
+        names.append(f"g{g}")
+        rows.append(f"g{g}\t{tmp_path / f'g{g}.fa'}")
+    (tmp_path / "rfile.txt").write_text("\n".join(rows) + "\n")
+    out = str(tmp_path / "inv")
+    r = run([cli, "inverted", "build", "-o", out, "-k", "17", "-s", "37", "-f", str(tmp_path / "rfile.txt"), "--write-skq",
+             "--threads", "3"])
+    assert r.returncode == 0, r.stderr
+    skq = np.fromfile(out + ".skq", dtype="<u2").reshape(12, 37)
+    # bins = low 16 bits of the densified bin minima (src/inverted.rs:392): oracle sketcher, 37 bins, no transpose
+    for g in (0, 7):
+        signs = oracle.bin_minima(oracle.read_fasta_records(str(tmp_path / f"g{g}.fa")), 17, 37)
+        assert np.array_equal(skq[g], (signs & 0xFFFF).astype(np.uint16))
+    index, meta = _read_ski(out + ".ski")
+    assert meta[0] == 12 and meta[1] == names and meta[2] is None and meta[3] is None and meta[4] == 17
+    assert len(index) == 37
+    for b in range(37):
+        want = {}
+        for g in range(12):
+            want.setdefault(int(skq[g, b]), []).append(g)
+        assert index[b] == want
+    rq = run([cli, "inverted", "query", "-f", str(tmp_path / "rfile.txt"), out + ".ski"])
+    counts = np.array([[int(x) for x in l.split("\t")[1:]] for l in rq.stdout.splitlines()[1:]])
+    assert np.array_equal(counts, (skq[:, None, :] == skq[None, :, :]).sum(axis=2))
+    ra = run([cli, "inverted", "query", "-f", str(tmp_path / "rfile.txt"), out + ".ski", "--query-type", "any-bins"])
+    for g, line in enumerate(ra.stdout.splitlines()[1:]):
+        assert line.split("\t")[1].split(",") == [names[j] for j in np.flatnonzero(counts[g] > 0)]
+    pairs = int(((counts > 0).sum() - 12) // 2)
+    assert run([cli, "inverted", "precluster", "--count", out]).stdout == f"Identified {pairs} prefilter pairs from a max of 66\n"
+    # > 4096 samples with the same value in a bin: bitmap containers (one tiny genome listed 5000 times under new names)
+    (tmp_path / "many.txt").write_text("".join(f"s{i}\t{tmp_path / 'g0.fa'}\n" for i in range(5000)) +
+                                       f"other\t{tmp_path / 'g1.fa'}\n")
+    r = run([cli, "inverted", "build", "-o", out + "_many", "-k", "17", "-s", "3", "-f", str(tmp_path / "many.txt"), "--threads", "8"])
+    assert r.returncode == 0, r.stderr
+    index, meta = _read_ski(out + "_many.ski")
+    assert meta[0] == 5001 and all(sorted(len(v) for v in b.values())[-1] >= 5000 for b in index)
+    assert sorted(v for vals in index[0].values() for v in vals) == list(range(5001))
+    r = run([cli, "inverted", "query", out + "_many.ski", str(tmp_path / "g1.fa"), "--query-type", "all-bins"])
+    assert r.stdout.splitlines()[1] == "g1.fa\tother"
+    # errors
+    assert run([cli, "inverted", "precluster", out]).returncode == 2                       # needs --skd or --count
+    assert run([cli, "inverted", "query", out + ".ski", "--query-type", "x", str(tmp_path / "g0.fa")]).returncode == 2
+    assert run([cli, "inverted", "precluster", "--count", str(tmp_path / "nope.ski")]).returncode == 1
+    (tmp_path / "bad.ski").write_bytes(b"\xff\x06\x00\x00sNaPpY\x01\x05\x00\x00" + b"\x00" * 5)
+    assert run([cli, "inverted", "precluster", "--count", str(tmp_path / "bad.ski")]).returncode == 1
+
+
+def _precluster_inputs(tmp_path, ski):
+    import shutil
+    for f in ("sketches3.skm", "sketches3.skd"):
+        shutil.copyfile(os.path.join(FIXTURES, f), tmp_path / f.replace("sketches3", "standard"))
+    for ext in (".ski", ".skq"):
+        shutil.copyfile(os.path.join(FIXTURES, ski + ext), tmp_path / (ski + ext))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ski", ["inverted", "reordered_inv"])
+def test_cli_inverted_precluster_goldens(tools, tmp_path, ski):
+    """reference tests/inverted.rs:244-452: `inverted precluster` over the .ski/.skq pair (same order as the .skd, and
+    reordered by --species-names) against the reference's golden stdout files."""
+    cli, _ = tools
+    _precluster_inputs(tmp_path, ski)
+    base = [cli, "inverted", "precluster", "-v", "--skd", "standard", ski + ".ski"]
+    for extra, gold in ((["--knn", "1"], "inverted_precluster"), (["--knn", "1", "--ani"], "inverted_precluster_ani"),
+                        (["--knn", "50"], "inverted_precluster"), ([], "inverted_precluster")):
+        r = run(base + extra, cwd=tmp_path)
+        assert r.returncode == 0, r.stderr
+        assert sorted(r.stdout.splitlines()) == sorted(golden(gold).splitlines()), (extra, r.stdout)
+    assert "knn=50 is higher than number of samples=4" in r.stderr
+    # completeness: both index orders give the same text (tests/inverted.rs:525-607), equal to the oracle's values
+    comp = tmp_path / "c.txt"
+    names = ["14412_3#82.contigs_velvet.fa.gz", "14412_3#84.contigs_velvet.fa.gz", "R6.fa.gz", "TIGR4.fa.gz"]
+    cv = [0.7, 0.8, 0.9, 0.95]
+    comp.write_text("".join(f"{n}\t{c}\n" for n, c in zip(names, cv)))
+    r = run(base + ["--knn", "1", "--ref-completeness-file", str(comp)], cwd=tmp_path)
+    assert r.returncode == 0, r.stderr
+    db = fixture_db("sketches3")
+    oidx, od0, _ = oracle.self_dists_knn(db, 1, k_idx=0, completeness=np.array(cv), cutoff=0.64)
+    want = [f"{names[i]}\t{names[int(oidx[i, 0])]}\t{oracle.fmt_f32(od0[i, 0])}" for i in range(4)]
+    assert r.stdout.splitlines() == want
+    # knn=3 lists only true candidates: no self matches, no padding (tests/inverted.rs:657-701)
+    r = run(base + ["--knn", "3"], cwd=tmp_path)
+    assert sorted(r.stdout.splitlines()) == sorted(golden("inverted_precluster").splitlines())
+    for mode in ("singleton", "bruteforce"):   # every genome has a candidate here: same output (:703-803)
+        r = run(base + ["--knn", "1", "--retain-unmatched", mode], cwd=tmp_path)
+        assert sorted(r.stdout.splitlines()) == sorted(golden("inverted_precluster").splitlines())
+    r = run(base + ["-o", "out.tsv", "--knn", "1", "--threads", "2"], cwd=tmp_path)
+    assert r.returncode == 0 and r.stdout == "" and sorted((tmp_path / "out.tsv").read_text().splitlines()) == \
+        sorted(golden("inverted_precluster").splitlines())
+
+
+@pytest.mark.gpu
+def test_cli_inverted_precluster_unmatched_and_mismatched_inputs(tools, tmp_path):
+    """--retain-unmatched on an index in which no bins are shared (k/s chosen so), and the reference's panics for a
+    .ski whose samples or k-mer do not match the .skd (src/distances/mod.rs:429-431, src/lib.rs:748-751)."""
+    cli, _ = tools
+    _precluster_inputs(tmp_path, "inverted")
+    db = fixture_db("sketches3")
+    names = db.names
+    # an .skq/.ski pair in which every sample has unique bins: written through the C++ builder from tiny unrelated genomes
+    rng = np.random.default_rng(9)
+    rows = []
+    for n in names:
+        _write_fasta(tmp_path / (n + ".fa"), [("c", "".join(rng.choice(list("ACGT"), size=3000)))])
+        rows.append(f"{n}\t{tmp_path / (n + '.fa')}")
+    (tmp_path / "r.txt").write_text("\n".join(rows) + "\n")
+    assert run([cli, "inverted", "build", "-o", "lonely", "-k", "21", "-s", "4", "-f", "r.txt", "--write-skq"], cwd=tmp_path).returncode == 0
+    assert run([cli, "inverted", "precluster", "--count", "lonely.ski"], cwd=tmp_path).stdout.startswith("Identified 0 ")
+    base = [cli, "inverted", "precluster", "--skd", "standard", "lonely.ski", "--knn", "2"]
+    assert run(base, cwd=tmp_path).stdout == ""                                  # only padding, which is not printed
+    r = run(base + ["--retain-unmatched", "singleton"], cwd=tmp_path)
+    assert r.stdout.splitlines() == [f"{n}\t{n}\t0" for n in names]
+    r = run(base + ["--retain-unmatched", "bruteforce"], cwd=tmp_path)
+    oidx, od0, _ = oracle.self_dists_knn(db, 2, k_idx=0)
+    assert r.stdout.splitlines() == [f"{names[i]}\t{names[int(oidx[i, t])]}\t{oracle.fmt_f32(od0[i, t])}"
+                                     for i in range(4) for t in range(2)]
+    # .ski built at another k: set_k panics
+    assert run([cli, "inverted", "build", "-o", "k31", "-k", "31", "-s", "4", "-f", "r.txt", "--write-skq"], cwd=tmp_path).returncode == 0
+    r = run([cli, "inverted", "precluster", "--skd", "standard", "k31.ski"], cwd=tmp_path)
+    assert r.returncode == 101 and "K-mer size 31 used for .ski not found in .skd" in r.stderr
+    # .ski without one of the .skd's samples
+    (tmp_path / "r3.txt").write_text("\n".join(rows[:3]) + "\n")
+    assert run([cli, "inverted", "build", "-o", "three", "-k", "21", "-s", "4", "-f", "r3.txt", "--write-skq"], cwd=tmp_path).returncode == 0
+    r = run([cli, "inverted", "precluster", "--skd", "standard", "three.ski"], cwd=tmp_path)
+    assert r.returncode == 101 and "could not be found in the .ski" in r.stderr and names[3] in r.stderr
