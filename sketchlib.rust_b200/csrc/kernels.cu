@@ -601,10 +601,194 @@ size_t tile_kernel_smem(int nk, bool count32, bool knn_mode, uint32_t cap, bool 
     return off;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Few queries (<= 8) against many references: HBM-bound (second roofline).
+// The tile kernel stages both sides through shared memory and needs a CTA barrier per 64-bin word; with so few
+// columns the work per word is too small to hide that, and it stalls at about half of the HBM rate.  Here the
+// whole query side lives in shared memory (nq x K x W x 112 bytes, read with broadcast LDS), every thread owns ONE
+// reference sample and streams its bit planes straight from global memory (a warp reads the quads of 32
+// consecutive samples: 512 contiguous bytes per request, one word ahead in registers), and nothing in the main
+// loop synchronises.  Counts go to a per-warp slice of shared memory in the [pair][kp] layout pair_epilogue reads.
+constexpr int STREAM_THREADS = 512;
+
+struct RefWord {  // the 14 planes of both 32-bin halves of one 64-bin word of one sample
+    uint4 q[2][3];
+    uint2 t[2];
+};
+
+template <int NQ>
+__global__ void __launch_bounds__(STREAM_THREADS, 1)
+    stream_kernel(const __grid_constant__ DevDb A, const __grid_constant__ DevDb B, const __grid_constant__ EpiParams E,
+                  const __grid_constant__ SchedParams S) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint32_t W = A.W, n_words = (uint32_t)E.nk * W;
+    uint4 *qquad = reinterpret_cast<uint4 *>(smem_raw);                   // [word][half][quad][NQ]
+    uint2 *qtail = reinterpret_cast<uint2 *>(qquad + (size_t)n_words * 6 * NQ);  // [word][half][NQ]
+    uint16_t *counts_all = reinterpret_cast<uint16_t *>(qtail + (size_t)n_words * 2 * NQ);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t nq = (uint32_t)B.n;
+    const uint32_t hb0 = (uint32_t)(S.row_begin / 32), hb1 = (uint32_t)((S.row_end + 31) / 32);
+    const uint32_t n_warps = gridDim.x * (STREAM_THREADS / 32);
+    const uint32_t first = hb0 + blockIdx.x * (STREAM_THREADS / 32) + warp;
+
+    for (uint32_t e = tid; e < n_words * 2 * NQ; e += STREAM_THREADS) {
+        const uint32_t q = e % NQ, step = e / NQ, h = step & 1, kw = step >> 1;
+        const uint32_t *slab = B.tiled + slab_index(B, (uint32_t)E.k0 + kw / W, kw % W, 0) * STAGE_U32 + h * HALF_U32;
+        const bool live = q < nq;
+#pragma unroll
+        for (int quad = 0; quad < 3; ++quad)
+            qquad[((size_t)step * 3 + quad) * NQ + q] =
+                live ? *reinterpret_cast<const uint4 *>(slab + quad * QUAD_U32 + q * 4) : make_uint4(0, 0, 0, 0);
+        qtail[(size_t)step * NQ + q] = live ? *reinterpret_cast<const uint2 *>(slab + TAIL_U32 + q * 2) : make_uint2(0, 0);
+    }
+    uint16_t *counts = counts_all + (size_t)warp * 32 * NQ * E.kp;
+    if (E.kp != E.nk)  // padding slots of the per-pair count words must hold a valid table index
+        for (int e = lane; e < 32 * NQ * E.kp; e += 32) counts[e] = 0;
+    __syncthreads();
+
+    const uint32_t nbins = 64u * W;
+    const uint64_t word_stride = (uint64_t)A.nb * STAGE_U32;  // u32 between consecutive (k, w) slabs of one block
+    for (uint32_t hb = first; hb < hb1; hb += n_warps) {
+        const uint32_t b = hb >> 1, s = (hb & 1) * 32 + lane;
+        const uint64_t gi = (uint64_t)b * TS + s;
+        const uint32_t *p = A.tiled + slab_index(A, (uint32_t)E.k0, 0, b) * STAGE_U32 + s * 4;
+        // the tail pair of sample s sits at s * 2, not s * 4: fold the difference into the tail offset
+        const int tail_fix = -(int)(s * 2);
+        RefWord cur, nxt;
+        auto load = [&](RefWord &r, const uint32_t *base) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+#pragma unroll
+                for (int q = 0; q < 3; ++q)
+                    r.q[h][q] = __ldcs(reinterpret_cast<const uint4 *>(base + h * HALF_U32 + q * QUAD_U32));
+                r.t[h] = __ldcs(reinterpret_cast<const uint2 *>(base + h * HALF_U32 + TAIL_U32 + tail_fix));
+            }
+        };
+        load(nxt, p);
+        uint32_t mism[NQ];
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) mism[q] = 0;
+        uint32_t w_in_k = 0, kk = 0;
+        for (uint32_t kw = 0; kw < n_words; ++kw) {
+            cur = nxt;
+            p += word_stride;
+            if (kw + 1 < n_words) load(nxt, p);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint4 *qq = qquad + ((size_t)kw * 2 + h) * 3 * NQ;
+                const uint2 *qt = qtail + ((size_t)kw * 2 + h) * NQ;
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    const uint4 a = qq[q], bq = qq[NQ + q], c = qq[2 * NQ + q];
+                    const uint2 t = qt[q];
+                    uint32_t d = cur.q[h][0].x ^ a.x;
+                    d |= cur.q[h][0].y ^ a.y;
+                    d |= cur.q[h][0].z ^ a.z;
+                    d |= cur.q[h][0].w ^ a.w;
+                    d |= cur.q[h][1].x ^ bq.x;
+                    d |= cur.q[h][1].y ^ bq.y;
+                    d |= cur.q[h][1].z ^ bq.z;
+                    d |= cur.q[h][1].w ^ bq.w;
+                    d |= cur.q[h][2].x ^ c.x;
+                    d |= cur.q[h][2].y ^ c.y;
+                    d |= cur.q[h][2].z ^ c.z;
+                    d |= cur.q[h][2].w ^ c.w;
+                    d |= cur.t[h].x ^ t.x;
+                    d |= cur.t[h].y ^ t.y;
+                    mism[q] += __popc(d);
+                }
+            }
+            if (++w_in_k == W) {
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    counts[(lane * NQ + q) * E.kp + kk] = (uint16_t)(nbins - mism[q]);
+                    mism[q] = 0;
+                }
+                w_in_k = 0;
+                ++kk;
+            }
+        }
+        __syncwarp();
+        if (gi >= S.row_begin && gi < S.row_end) {
+            const bool rect = S.rect_ld != 0;
+            for (uint32_t q = 0; q < nq; ++q) {
+                const int pair = lane * NQ + (int)q;
+                if (S.mode == MODE_COUNTS) {
+                    uint32_t *o = reinterpret_cast<uint32_t *>(S.out) + ((gi - S.row_begin) * nq + q) * (uint64_t)E.nk;
+                    for (int k = 0; k < E.nk; ++k) o[k] = counts[pair * E.kp + k];
+                    continue;
+                }
+                const uint64_t idx = (gi - S.row_begin) * (rect ? S.rect_ld : (uint64_t)nq) + q;
+                float d0, d1;
+                if (E.has_c)
+                    pair_epilogue<uint16_t, true>(counts, pair, E, gi, q, rect, d0, d1);
+                else
+                    pair_epilogue<uint16_t, false>(counts, pair, E, gi, q, rect, d0, d1);
+                if (rect) {  // kNN keys, read back soon by select_kernel
+                    if (E.kind == KIND_CORE_ACC)
+                        reinterpret_cast<float2 *>(S.out)[idx] = make_float2(d0, d1);
+                    else
+                        S.out[idx] = d0;
+                } else if (E.kind == KIND_CORE_ACC) {
+                    __stcs(reinterpret_cast<float2 *>(S.out) + idx, make_float2(d0, d1));
+                } else {
+                    __stcs(S.out + idx, d0);
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// Shared memory of stream_kernel<NQ>; 0 if the query side does not fit.
+static size_t stream_smem(const DevDb &A, const EpiParams &E, int NQ) {
+    const size_t n_words = (size_t)E.nk * A.W;
+    const size_t bytes = n_words * 2 * NQ * (3 * 16 + 8) + (size_t)(STREAM_THREADS / 32) * 32 * NQ * E.kp * 2;
+    return bytes <= 232448 ? bytes : 0;
+}
+
+static bool stream_applies(const DevDb &A, const DevDb &B, const EpiParams &E, const SchedParams &S, bool count32) {
+    if (count32 || B.n == 0 || B.n > 8 || A.W != B.W) return false;
+    if (S.mode != MODE_DENSE_CROSS && S.mode != MODE_COUNTS) return false;
+    if (S.mode == MODE_COUNTS && S.self_mode) return false;
+    const int NQ = B.n <= 1 ? 1 : B.n <= 2 ? 2 : B.n <= 4 ? 4 : 8;
+    return stream_smem(A, E, NQ) != 0;
+}
+
+static cudaError_t launch_stream(const DevDb &A, const DevDb &B, const EpiParams &E, const SchedParams &S, cudaStream_t st) {
+    static int sm_count = 0;
+    if (sm_count == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int NQ = B.n <= 1 ? 1 : B.n <= 2 ? 2 : B.n <= 4 ? 4 : 8;
+    const size_t smem = stream_smem(A, E, NQ);
+    const uint64_t units = (S.row_end + 31) / 32 - S.row_begin / 32;
+    if (units == 0) return cudaSuccess;
+    const unsigned ctas = (unsigned)std::min<uint64_t>((uint64_t)sm_count, (units + STREAM_THREADS / 32 - 1) / (STREAM_THREADS / 32));
+    cudaError_t err = cudaSuccess;
+#define SKD_STREAM(N)                                                                                          \
+    do {                                                                                                       \
+        err = cudaFuncSetAttribute(stream_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+        if (err != cudaSuccess) return err;                                                                    \
+        stream_kernel<N><<<ctas, STREAM_THREADS, smem, st>>>(A, B, E, S);                                      \
+    } while (0)
+    if (NQ == 1) SKD_STREAM(1);
+    else if (NQ == 2) SKD_STREAM(2);
+    else if (NQ == 4) SKD_STREAM(4);
+    else SKD_STREAM(8);
+#undef SKD_STREAM
+    return cudaGetLastError();
+}
+
 cudaError_t launch_tiles(const DevDb &A, const DevDb &B, const EpiParams &E, const SchedParams &S, uint64_t n_ctas,
                          bool count32, size_t smem, cudaStream_t st) {
     if (n_ctas == 0) return cudaSuccess;
     if (n_ctas > 0x7fffffffull) return cudaErrorInvalidConfiguration;
+    if (stream_applies(A, B, E, S, count32)) return launch_stream(A, B, E, S, st);
     // Narrow-column variants: when the column side has at most 8 / 16 / 32 samples (a handful of queries against a
     // large reference database) only those columns are loaded and compared.
     const int cols = S.mode == MODE_KNN || TJ != 4 ? TS : (B.n <= 8 ? 8 : B.n <= 16 ? 16 : B.n <= 32 ? 32 : TS);
@@ -815,6 +999,120 @@ __global__ void __launch_bounds__(256) select_kernel(const float *__restrict__ D
             if (AUX) Laux[tg * knn + e] = baux[t * CAP + e];
         }
     }
+}
+
+// Cross-mode selection for at most 8 target columns (a handful of queries): select_kernel gives every target to one
+// warp, which leaves a single warp per CTA busy when there is one query.  Here the ROWS of a split are divided over
+// the 8 warps instead; warp w keeps one list per target (list w * 8 + q), lanes take 32 consecutive rows at a time,
+// and the 8 lists of a target are merged at the end.  D is [R][ld] keys (float2 key/aux with AUX), ld >= nq.
+template <bool AUX>
+__global__ void __launch_bounds__(256) select_few_kernel(const float *__restrict__ D, uint64_t ld, uint64_t g0, uint32_t R,
+                                                         uint32_t nq, unsigned long long *__restrict__ Lkey,
+                                                         float *__restrict__ Laux, uint32_t knn, uint64_t idx_offset,
+                                                         uint32_t rows_per_split, uint64_t part_stride) {
+    constexpr int CAP = 128;
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    unsigned long long *buf = reinterpret_cast<unsigned long long *>(sm_raw);  // [8 warps][8 targets][CAP]
+    float *baux = reinterpret_cast<float *>(buf + TS * CAP);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint64_t lo = (uint64_t)blockIdx.x * rows_per_split;
+    const uint64_t hi = lo + rows_per_split < R ? lo + rows_per_split : R;
+    Lkey += (uint64_t)blockIdx.x * part_stride;
+    if (AUX) Laux += (uint64_t)blockIdx.x * part_stride;
+    for (int e = lane; e < 8 * CAP; e += 32) buf[warp * 8 * CAP + e] = ~0ull;
+    __syncwarp();
+
+    const uint64_t span = hi > lo ? hi - lo : 0;
+    const uint64_t per_warp = ((span + 7) / 8 + 31) / 32 * 32;
+    const uint64_t w_lo = lo + (uint64_t)warp * per_warp;
+    const uint64_t w_hi = w_lo + per_warp < hi ? w_lo + per_warp : hi;
+    uint32_t cnt[8];
+    unsigned long long thr[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        cnt[q] = 0;
+        thr[q] = ~0ull;
+    }
+    for (uint64_t r0 = w_lo; r0 < w_hi; r0 += 32) {
+        const uint64_t row = r0 + lane;
+        const bool in = row < w_hi;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (q >= (int)nq) break;
+            unsigned long long *list = buf + (warp * 8 + q) * CAP;
+            float key = 0.f, a = 0.f;
+            if (in) {
+                if (AUX) {
+                    const float2 v = __ldcs(reinterpret_cast<const float2 *>(D) + row * ld + q);
+                    key = v.x;
+                    a = v.y;
+                } else {
+                    key = __ldcs(D + row * ld + q);
+                }
+            }
+            const unsigned long long comp =
+                ((unsigned long long)float_order_bits(key) << 32) | (uint32_t)(g0 + row + idx_offset);
+            const bool ok = in && comp < thr[q];
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (m == 0) continue;
+            if (ok) {
+                const uint32_t slot = cnt[q] + __popc(m & ((1u << lane) - 1u));
+                list[slot] = comp;
+                if (AUX) baux[(warp * 8 + q) * CAP + slot] = a;
+            }
+            cnt[q] += __popc(m);
+            __syncwarp();
+            if (cnt[q] + 32 > CAP) {
+                warp_bitonic_sort(list, AUX ? baux + (warp * 8 + q) * CAP : nullptr, CAP, lane);
+                for (int e = knn + lane; e < CAP; e += 32) list[e] = ~0ull;
+                __syncwarp();
+                cnt[q] = knn;
+                thr[q] = list[knn - 1];
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        if (q < (int)nq) warp_bitonic_sort(buf + (warp * 8 + q) * CAP, AUX ? baux + (warp * 8 + q) * CAP : nullptr, CAP, lane);
+    __syncthreads();
+    // warp q merges the 8 lists of target q (each sorted, best knn <= 64 first) into list q of warp 0
+    if (warp < (int)nq) {
+        const int q = warp;
+        unsigned long long *acc = buf + q * CAP;
+        float *acc_a = AUX ? baux + q * CAP : nullptr;
+        for (int w = 1; w < 8; ++w) {
+            const unsigned long long *src = buf + (w * 8 + q) * CAP;
+            for (int e = lane; e < CAP - (int)knn; e += 32) {
+                acc[knn + e] = e < (int)knn ? src[e] : ~0ull;
+                if (AUX) acc_a[knn + e] = e < (int)knn ? baux[(w * 8 + q) * CAP + e] : 0.f;
+            }
+            __syncwarp();
+            warp_bitonic_sort(acc, acc_a, CAP, lane);
+        }
+        for (uint32_t e = lane; e < knn; e += 32) {
+            Lkey[(uint64_t)q * knn + e] = acc[e];
+            if (AUX) Laux[(uint64_t)q * knn + e] = acc_a[e];
+        }
+    }
+}
+
+cudaError_t launch_select_few(bool aux, const float *D, uint64_t ld, uint64_t g0, uint32_t R, uint32_t nq,
+                              unsigned long long *Lkey, float *Laux, uint32_t knn, cudaStream_t st, uint64_t idx_offset,
+                              uint32_t n_splits, uint32_t rows_per_split, uint64_t part_stride) {
+    const size_t smem = (size_t)TS * 128 * 8 + (aux ? (size_t)TS * 128 * 4 : 0);
+    cudaError_t err;
+    if (aux) {
+        err = cudaFuncSetAttribute(select_few_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        select_few_kernel<true><<<n_splits, 256, smem, st>>>(D, ld, g0, R, nq, Lkey, Laux, knn, idx_offset, rows_per_split,
+                                                             part_stride);
+    } else {
+        err = cudaFuncSetAttribute(select_few_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        select_few_kernel<false><<<n_splits, 256, smem, st>>>(D, ld, g0, R, nq, Lkey, Laux, knn, idx_offset, rows_per_split,
+                                                              part_stride);
+    }
+    return cudaGetLastError();
 }
 
 cudaError_t launch_select(bool cols, bool aux, const float *D, uint64_t ld, uint64_t g0, uint32_t R, uint64_t c0,

@@ -27,6 +27,11 @@ cudaError_t launch_select(bool cols, bool aux, const float *D, uint64_t ld, uint
                           cudaStream_t st, int cross = 0, uint64_t idx_offset = 0, uint32_t n_splits = 1,
                           uint32_t rows_per_split = 0, uint64_t part_stride = 0);
 
+// Cross mode with at most 8 target columns: rows of every split divided over the warps (see select_few_kernel).
+cudaError_t launch_select_few(bool aux, const float *D, uint64_t ld, uint64_t g0, uint32_t R, uint32_t nq,
+                              unsigned long long *Lkey, float *Laux, uint32_t knn, cudaStream_t st, uint64_t idx_offset,
+                              uint32_t n_splits, uint32_t rows_per_split, uint64_t part_stride);
+
 void launch_knn_finalize(const unsigned long long *keys, const float *aux, uint32_t n_parts, uint64_t part_stride,
                          uint64_t row0, uint64_t n_rows, uint32_t knn, int kind, unsigned long long *idx_out,
                          float *d0_out, float *d1_out, unsigned long long *key_out, float *aux_out, cudaStream_t st);

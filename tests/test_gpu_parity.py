@@ -386,6 +386,55 @@ def test_scale_properties(sk, ctx):
     assert np.array_equal(np.sort(full, axis=1)[:, :50], knn.d0)
 
 
+def test_full_size_config2_properties(sk, ctx):
+    """BASELINE.json configs[1] at FULL size (n=10 000, 1024 bins, 8 k-mer lengths; 49 995 000 pairs): the oracle
+    cannot do the whole matrix in seconds, so the result is checked through size-independent properties -- a checksum
+    of the bit patterns over rank-style row shards, symmetry through the cross driver, kNN against the dense matrix --
+    plus whole oracle rows at sampled positions."""
+    n, kmers = 10000, [15, 17, 19, 21, 23, 25, 27, 29]
+    db = synth_db(n, 16, kmers, seed=2, n_families=200)
+    g = up(sk, ctx, db)
+    dt = sk.set_k(g)
+    d = sk.self_dists_all(g, dist_type=dt).distances
+    assert d.size == n * (n - 1) and np.isfinite(d).all() and d.min() >= 0.0 and d.max() <= 1.0
+    bits = d.view(np.uint32).astype(np.uint64)
+    whole = int(bits.sum())
+    # (1) checksum of checksums over the row blocks 3 and 8 ranks would own
+    for world in (3, 8):
+        assert sum(int(sk.self_dists_all(g, dist_type=dt, rows=sk.triangle_row_partition(n, r, world)).distances
+                       .view(np.uint32).astype(np.uint64).sum()) for r in range(world)) == whole
+    # (2) oracle rows: first, last, block edges, random
+    d2 = d.reshape(-1, 2)
+    for i in (0, 63, 64, 4999, 9936, 9997, 9998):
+        first = int(oracle.lib().oracle_square_to_condensed(i, i + 1, n))
+        cnt = n - 1 - i
+        ref = oracle.self_dists_all(db, first=first - first % 1000, count=cnt + first % 1000, threads=8)[2 * (first % 1000):]
+        check_close(d2[first:first + cnt].ravel(), ref)
+    # (3) the cross driver on (db, db) is the symmetric completion of the self result (sampled reference rows)
+    for r0 in (0, 5120, 9936):
+        x = sk.cross_dists_all(g, g, dist_type=dt, rows=(r0, r0 + 64)).distances.reshape(64, n, 2)
+        for i in range(r0, r0 + 64):
+            lo = int(oracle.lib().oracle_square_to_condensed(i, i + 1, n)) if i < n - 1 else 0
+            assert np.array_equal(x[i - r0, i + 1:], d2[lo:lo + n - 1 - i])
+            assert np.array_equal(x[i - r0, i], np.zeros(2, np.float32))
+    # (4) kNN-50 core distances are the 50 smallest of every row of the dense matrix (ties: values only)
+    knn = sk.self_dists_knn(g, knn=50, dist_type=dt)
+    full = np.full((n, n), np.inf, dtype=np.float32)
+    iu = np.triu_indices(n, 1)
+    full[iu] = d2[:, 0]
+    full.T[iu] = d2[:, 0]
+    del iu
+    full.partition(49, axis=1)
+    assert np.array_equal(np.sort(full[:, :50], axis=1), knn.d0)
+    # single-k Jaccard at full size: integer counts, so bit-exact rows and an idempotent second run
+    dj = sk.self_dists_all(g, dist_type=sk.set_k(g, 21)).distances
+    for i in (0, 7777):
+        first = int(oracle.lib().oracle_square_to_condensed(i, i + 1, n))
+        ref = oracle.self_dists_all(db, k_idx=3, first=first - first % 1000, count=n - 1 - i + first % 1000, threads=8)
+        assert np.array_equal(dj[first:first + n - 1 - i], ref[first % 1000:])
+    assert np.array_equal(dj, sk.self_dists_all(g, dist_type=sk.set_k(g, 21)).distances)
+
+
 # ------------------------------------------------------------------ symmetric self kNN, partial lists, merges
 def fresh_ctx(sk, **env):
     old = {k: os.environ.get(k) for k in env}
@@ -529,17 +578,23 @@ def test_cross_with_few_queries(sk, ctx, nq):
     assert_knn_matches(gotc.idx, gotc.d0, gotc.d1, oidx, od0, od1, False)
 
 
-def test_few_queries_knn_equals_row_owned_path(sk, ctx):
-    ref, qry = synth_pair(900, 40, 16, [17, 21, 25, 29], seed=91, n_families=12)
+@pytest.mark.parametrize("n_ref,nq,knn", [(900, 40, 25), (20000, 3, 64), (5000, 8, 1), (3000, 1, 50)])
+def test_few_queries_knn_equals_row_owned_path(sk, ctx, n_ref, nq, knn):
+    """nq <= 8 runs the streaming kernel + select_few_kernel, larger nq the narrow tile variants + select_kernel."""
+    ref, qry = synth_pair(n_ref, nq, 16, [17, 21, 25, 29], seed=91, n_families=12)
     plain = fresh_ctx(sk, SKD_KNN_SYMMETRIC=0)  # also disables the few-queries route
     tiny = fresh_ctx(sk, SKD_SYM_CHUNK_MB=1)    # several reference chunks and row slices
     try:
         outs = []
         for c in (ctx, plain, tiny):
             gr, gq = up(sk, c, ref), up(sk, c, qry)
-            outs.append(sk.cross_dists_knn(gr, gq, knn=25, dist_type=sk.set_k(gr)))
+            outs.append((sk.cross_dists_knn(gr, gq, knn=knn, dist_type=sk.set_k(gr)),
+                         sk.cross_dists_knn(gr, gq, knn=knn, dist_type=sk.set_k(gr, 21, ani=True))))
         for o in outs[1:]:
-            assert np.array_equal(o.idx, outs[0].idx) and np.array_equal(o.d0, outs[0].d0) and np.array_equal(o.d1, outs[0].d1)
+            for a, b in zip(o, outs[0]):
+                # ties are broken by the neighbour index on every path (composite keys): exact equality
+                assert np.array_equal(a.idx, b.idx) and np.array_equal(a.d0, b.d0)
+                assert a.d1 is None or np.array_equal(a.d1, b.d1)
     finally:
         fresh_ctx(sk, SKD_SYM_CHUNK_MB=2048).close()
         plain.close()
