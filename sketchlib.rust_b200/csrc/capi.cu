@@ -492,12 +492,10 @@ skd_status run_knn_few_queries(skd_ctx *ctx, const skd_db *R, const skd_db *Q, c
     uint64_t rows_chunk = std::max<uint64_t>(TS, ctx->sym_chunk_bytes / (nq * elt) / TS * TS);
     rows_chunk = std::min<uint64_t>(rows_chunk, (n_ref + TS - 1) / TS * TS);
     const uint32_t n_chunks = (uint32_t)((n_ref + rows_chunk - 1) / rows_chunk);
-    const uint32_t tgt_groups = (uint32_t)((nq + TS - 1) / TS);
+    const uint32_t tgt_groups = (uint32_t)((nq + 7) / 8);  // select_few_kernel: 8 queries per CTA
     uint32_t n_splits = (uint32_t)std::max<uint64_t>(1, (4ull * ctx->sm_count) / ((uint64_t)tgt_groups * n_chunks));
-    n_splits = std::min<uint32_t>({n_splits, 64u, (uint32_t)(rows_chunk / TS)});
-    const bool few_targets = nq <= 8;  // select_few_kernel: rows of a split are shared by the 8 warps of a CTA
-    if (few_targets) n_splits = std::min<uint32_t>(n_splits, 16u);  // fewer, longer lists: the final merge is O(parts^2)
-    n_splits = std::max(1u, n_splits);
+    // at most 16 row splits: few, long lists, since the final merge is O(parts^2) per query
+    n_splits = std::max(1u, std::min<uint32_t>({n_splits, 16u, (uint32_t)(rows_chunk / TS)}));
     const uint32_t rows_per_split = (uint32_t)(((rows_chunk + n_splits - 1) / n_splits + TS - 1) / TS * TS);
     const uint32_t parts = n_chunks * n_splits;
     const uint64_t part_stride = nq * knn;
@@ -526,16 +524,10 @@ skd_status run_knn_few_queries(skd_ctx *ctx, const skd_db *R, const skd_db *Q, c
         if (st) return st;
         st = timer_begin(ctx);
         if (st) return st;
-        if (few_targets)
-            CU(ctx, launch_select_few(with_aux, (const float *)D, nq, g0, (uint32_t)(g1 - g0), (uint32_t)nq,
-                                      (unsigned long long *)pk + (uint64_t)c * n_splits * part_stride,
-                                      with_aux ? (float *)pa + (uint64_t)c * n_splits * part_stride : nullptr,
-                                      (uint32_t)knn, ctx->compute, idx_offset, n_splits, rows_per_split, part_stride));
-        else
-            CU(ctx, launch_select(true, with_aux, (const float *)D, nq, g0, (uint32_t)(g1 - g0), 0, nq, 0, nq,
+        CU(ctx, launch_select_few(with_aux, (const float *)D, nq, g0, (uint32_t)(g1 - g0), (uint32_t)nq,
                                   (unsigned long long *)pk + (uint64_t)c * n_splits * part_stride,
                                   with_aux ? (float *)pa + (uint64_t)c * n_splits * part_stride : nullptr, (uint32_t)knn,
-                                  ctx->compute, 1, idx_offset, n_splits, rows_per_split, part_stride));
+                                  ctx->compute, idx_offset, n_splits, rows_per_split, part_stride));
         ctx->launches++;
         st = timer_end(ctx);
         if (st) return st;

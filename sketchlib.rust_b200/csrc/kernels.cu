@@ -620,7 +620,7 @@ struct RefWord {  // the 14 planes of both 32-bin halves of one 64-bin word of o
 template <int NQ>
 __global__ void __launch_bounds__(STREAM_THREADS, 1)
     stream_kernel(const __grid_constant__ DevDb A, const __grid_constant__ DevDb B, const __grid_constant__ EpiParams E,
-                  const __grid_constant__ SchedParams S) {
+                  const __grid_constant__ SchedParams S, const uint32_t q0) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t W = A.W, n_words = (uint32_t)E.nk * W;
     uint4 *qquad = reinterpret_cast<uint4 *>(smem_raw);                   // [word][half][quad][NQ]
@@ -628,7 +628,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
     uint16_t *counts_all = reinterpret_cast<uint16_t *>(qtail + (size_t)n_words * 2 * NQ);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t nq = (uint32_t)B.n;
+    const uint32_t nq_all = (uint32_t)B.n;                      // this launch: queries [q0, q0 + nq)
+    const uint32_t nq = nq_all - q0 < (uint32_t)NQ ? nq_all - q0 : (uint32_t)NQ;
     const uint32_t hb0 = (uint32_t)(S.row_begin / 32), hb1 = (uint32_t)((S.row_end + 31) / 32);
     const uint32_t n_warps = gridDim.x * (STREAM_THREADS / 32);
     const uint32_t first = hb0 + blockIdx.x * (STREAM_THREADS / 32) + warp;
@@ -640,8 +641,9 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
 #pragma unroll
         for (int quad = 0; quad < 3; ++quad)
             qquad[((size_t)step * 3 + quad) * NQ + q] =
-                live ? *reinterpret_cast<const uint4 *>(slab + quad * QUAD_U32 + q * 4) : make_uint4(0, 0, 0, 0);
-        qtail[(size_t)step * NQ + q] = live ? *reinterpret_cast<const uint2 *>(slab + TAIL_U32 + q * 2) : make_uint2(0, 0);
+                live ? *reinterpret_cast<const uint4 *>(slab + quad * QUAD_U32 + (q0 + q) * 4) : make_uint4(0, 0, 0, 0);
+        qtail[(size_t)step * NQ + q] =
+            live ? *reinterpret_cast<const uint2 *>(slab + TAIL_U32 + (q0 + q) * 2) : make_uint2(0, 0);
     }
     uint16_t *counts = counts_all + (size_t)warp * 32 * NQ * E.kp;
     if (E.kp != E.nk)  // padding slots of the per-pair count words must hold a valid table index
@@ -715,17 +717,18 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
             const bool rect = S.rect_ld != 0;
             for (uint32_t q = 0; q < nq; ++q) {
                 const int pair = lane * NQ + (int)q;
+                const uint64_t gj = q0 + q;
                 if (S.mode == MODE_COUNTS) {
-                    uint32_t *o = reinterpret_cast<uint32_t *>(S.out) + ((gi - S.row_begin) * nq + q) * (uint64_t)E.nk;
+                    uint32_t *o = reinterpret_cast<uint32_t *>(S.out) + ((gi - S.row_begin) * nq_all + gj) * (uint64_t)E.nk;
                     for (int k = 0; k < E.nk; ++k) o[k] = counts[pair * E.kp + k];
                     continue;
                 }
-                const uint64_t idx = (gi - S.row_begin) * (rect ? S.rect_ld : (uint64_t)nq) + q;
+                const uint64_t idx = (gi - S.row_begin) * (rect ? S.rect_ld : (uint64_t)nq_all) + gj;
                 float d0, d1;
                 if (E.has_c)
-                    pair_epilogue<uint16_t, true>(counts, pair, E, gi, q, rect, d0, d1);
+                    pair_epilogue<uint16_t, true>(counts, pair, E, gi, gj, rect, d0, d1);
                 else
-                    pair_epilogue<uint16_t, false>(counts, pair, E, gi, q, rect, d0, d1);
+                    pair_epilogue<uint16_t, false>(counts, pair, E, gi, gj, rect, d0, d1);
                 if (rect) {  // kNN keys, read back soon by select_kernel
                     if (E.kind == KIND_CORE_ACC)
                         reinterpret_cast<float2 *>(S.out)[idx] = make_float2(d0, d1);
@@ -750,10 +753,12 @@ static size_t stream_smem(const DevDb &A, const EpiParams &E, int NQ) {
 }
 
 static bool stream_applies(const DevDb &A, const DevDb &B, const EpiParams &E, const SchedParams &S, bool count32) {
-    if (count32 || B.n == 0 || B.n > 8 || A.W != B.W) return false;
+    // up to 16 queries: one or two passes over the references still beat the narrow tile variants (B200: 16 queries
+    // 2.67 ms vs 2.86 ms per 7.2 GB of reference planes; 32 queries 5.3 ms vs 4.5 ms)
+    if (count32 || B.n == 0 || B.n > 16 || A.W != B.W) return false;
     if (S.mode != MODE_DENSE_CROSS && S.mode != MODE_COUNTS) return false;
     if (S.mode == MODE_COUNTS && S.self_mode) return false;
-    const int NQ = B.n <= 1 ? 1 : B.n <= 2 ? 2 : B.n <= 4 ? 4 : 8;
+    const int NQ = B.n <= 1 ? 1 : B.n <= 2 ? 2 : B.n <= 4 ? 4 : 8;  // more than 8 queries: passes of 8
     return stream_smem(A, E, NQ) != 0;
 }
 
@@ -774,7 +779,7 @@ static cudaError_t launch_stream(const DevDb &A, const DevDb &B, const EpiParams
     do {                                                                                                       \
         err = cudaFuncSetAttribute(stream_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
         if (err != cudaSuccess) return err;                                                                    \
-        stream_kernel<N><<<ctas, STREAM_THREADS, smem, st>>>(A, B, E, S);                                      \
+        for (uint32_t q0 = 0; q0 < B.n; q0 += N) stream_kernel<N><<<ctas, STREAM_THREADS, smem, st>>>(A, B, E, S, q0); \
     } while (0)
     if (NQ == 1) SKD_STREAM(1);
     else if (NQ == 2) SKD_STREAM(2);
@@ -876,15 +881,12 @@ void launch_knn_merge(const unsigned long long *part_key, const float *part_aux,
 // One CTA owns 64 targets (rows or columns of D), streams 64x64 sub-tiles of D through shared memory and
 // keeps, per target, the running list L[target][knn] (sorted composites) topped up through a 128-slot
 // buffer with threshold rejection, exactly like the tile kernel's kNN epilogue.
-// cross != 0 (COLS only): D is a ref-major cross matrix (rows = references g0.., columns = all n queries); every
-// row is a candidate of every column, the stored neighbour index is row + idx_offset, and blockIdx.y splits the
-// rows into slices of rows_per_split with one list set per slice (Lkey + slice * part_stride).
+// (Ref-major cross matrices with few query columns go through select_few_kernel below.)
 template <bool COLS, bool AUX>
 __global__ void __launch_bounds__(256) select_kernel(const float *__restrict__ D, uint64_t ld, uint64_t g0, uint32_t R,
                                                      uint64_t c0, uint64_t n, uint64_t t0, uint64_t t1,
                                                      unsigned long long *__restrict__ Lkey, float *__restrict__ Laux,
-                                                     uint32_t knn, int cross, uint64_t idx_offset,
-                                                     uint32_t rows_per_split, uint64_t part_stride) {
+                                                     uint32_t knn) {
     constexpr int CAP = 128;
     extern __shared__ __align__(16) unsigned char sm_raw[];
     unsigned long long *buf = reinterpret_cast<unsigned long long *>(sm_raw);           // [64][CAP]
@@ -895,16 +897,6 @@ __global__ void __launch_bounds__(256) select_kernel(const float *__restrict__ D
     uint32_t *cnt = reinterpret_cast<uint32_t *>(thr + TS);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint64_t tbase = t0 + (uint64_t)blockIdx.x * TS;  // first target (global sample index) of this CTA
-    if (cross) {  // this CTA's slice of the rows and its own list set
-        const uint64_t lo = (uint64_t)blockIdx.y * rows_per_split;
-        const uint64_t hi = lo + rows_per_split < R ? lo + rows_per_split : R;
-        Lkey += (uint64_t)blockIdx.y * part_stride;
-        if (AUX) Laux += (uint64_t)blockIdx.y * part_stride;
-        g0 += lo;
-        D += lo * ld * (AUX ? 2 : 1);
-        R = (uint32_t)(hi - lo);
-    }
-
     // start from the lists accumulated so far
     for (int e = tid; e < TS * CAP; e += 256) {
         const int t = e / CAP, s = e % CAP;
@@ -931,14 +923,14 @@ __global__ void __launch_bounds__(256) select_kernel(const float *__restrict__ D
     // ROWS: targets are rows i in [tbase, +64), candidates are columns j in (i, n)
     // COLS: targets are columns j, candidates are rows i in [g0, min(j, g0 + R))
     const uint64_t s_begin = COLS ? g0 : (tbase + 1 > c0 ? tbase + 1 : c0);
-    const uint64_t s_end = COLS ? (cross || g0 + R < tbase + TS ? g0 + R : tbase + TS) : n;
+    const uint64_t s_end = COLS ? (g0 + R < tbase + TS ? g0 + R : tbase + TS) : n;
     for (uint64_t sb = s_begin / TS * TS; sb < s_end; sb += TS) {
         // load D sub-tile: ROWS: rows = targets, cols = sb..sb+63 ; COLS: rows = sb.., cols = targets
         for (int e = tid; e < TS * TS; e += 256) {
             const int r = e / TS, c = e % TS;
             const uint64_t gi = COLS ? sb + r : tbase + r, gj = COLS ? tbase + c : sb + c;
             float k = 0.f, a = 0.f;
-            if (gi >= g0 && gi < g0 + R && gj < n && (cross || gj > gi) && gj >= c0) {
+            if (gi >= g0 && gi < g0 + R && gj < n && gj > gi && gj >= c0) {
                 const uint64_t off = (gi - g0) * ld + (gj - c0);
                 if (AUX) {
                     float2 v = __ldcs(reinterpret_cast<const float2 *>(D) + off);
@@ -962,12 +954,12 @@ __global__ void __launch_bounds__(256) select_kernel(const float *__restrict__ D
                 const int s = lane + 32 * h;
                 const uint64_t cand = sb + s;  // global index of the candidate sample
                 const uint64_t gi = COLS ? cand : tg, gj = COLS ? tg : cand;
-                bool ok = gi >= g0 && gi < g0 + R && gj < n && (cross || gj > gi) && gj >= c0;
+                bool ok = gi >= g0 && gi < g0 + R && gj < n && gj > gi && gj >= c0;
                 const int r = COLS ? s : t, cc = COLS ? t : s;
                 unsigned long long comp = 0;
                 if (ok) {
                     comp = ((unsigned long long)float_order_bits(tkey[r * (TS + 1) + cc]) << 32) |
-                           (uint32_t)(cand + idx_offset);
+                           (uint32_t)cand;
                     ok = comp < th;
                 }
                 const unsigned m = __ballot_sync(0xffffffffu, ok);
@@ -1001,10 +993,13 @@ __global__ void __launch_bounds__(256) select_kernel(const float *__restrict__ D
     }
 }
 
-// Cross-mode selection for at most 8 target columns (a handful of queries): select_kernel gives every target to one
-// warp, which leaves a single warp per CTA busy when there is one query.  Here the ROWS of a split are divided over
-// the 8 warps instead; warp w keeps one list per target (list w * 8 + q), lanes take 32 consecutive rows at a time,
-// and the 8 lists of a target are merged at the end.  D is [R][ld] keys (float2 key/aux with AUX), ld >= nq.
+// Cross-mode selection over few target columns (queries).  D is a ref-major matrix of kNN keys (rows = references
+// g0 .., columns = the nq queries; float2 key/aux with AUX; ld >= nq): every row is a candidate of every column and
+// the stored neighbour index is row + idx_offset.  A CTA takes a group of 8 targets (blockIdx.y) and one slice of
+// rows_per_split rows (blockIdx.x; one list set per slice at Lkey + slice * part_stride); the rows of the slice are
+// divided over the 8 warps, warp w keeps one list per target (list w * 8 + q), lanes take 32 consecutive rows at a
+// time, and the 8 lists of a target are merged at the end.  (Giving each target to one warp, as select_kernel does,
+// leaves one warp per CTA busy when there is a single query: 2.3 ms instead of 0.3 ms per 500 000 references.)
 template <bool AUX>
 __global__ void __launch_bounds__(256) select_few_kernel(const float *__restrict__ D, uint64_t ld, uint64_t g0, uint32_t R,
                                                          uint32_t nq, unsigned long long *__restrict__ Lkey,
@@ -1017,8 +1012,11 @@ __global__ void __launch_bounds__(256) select_few_kernel(const float *__restrict
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint64_t lo = (uint64_t)blockIdx.x * rows_per_split;
     const uint64_t hi = lo + rows_per_split < R ? lo + rows_per_split : R;
-    Lkey += (uint64_t)blockIdx.x * part_stride;
-    if (AUX) Laux += (uint64_t)blockIdx.x * part_stride;
+    const uint32_t t0 = blockIdx.y * 8;  // this CTA's group of (at most) 8 targets
+    Lkey += (uint64_t)blockIdx.x * part_stride + (uint64_t)t0 * knn;
+    if (AUX) Laux += (uint64_t)blockIdx.x * part_stride + (uint64_t)t0 * knn;
+    D += (AUX ? 2 : 1) * (size_t)t0;
+    nq = nq - t0 < 8 ? nq - t0 : 8;
     for (int e = lane; e < 8 * CAP; e += 32) buf[warp * 8 * CAP + e] = ~0ull;
     __syncwarp();
 
@@ -1100,16 +1098,17 @@ cudaError_t launch_select_few(bool aux, const float *D, uint64_t ld, uint64_t g0
                               unsigned long long *Lkey, float *Laux, uint32_t knn, cudaStream_t st, uint64_t idx_offset,
                               uint32_t n_splits, uint32_t rows_per_split, uint64_t part_stride) {
     const size_t smem = (size_t)TS * 128 * 8 + (aux ? (size_t)TS * 128 * 4 : 0);
+    const dim3 grid(n_splits, (nq + 7) / 8);
     cudaError_t err;
     if (aux) {
         err = cudaFuncSetAttribute(select_few_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
-        select_few_kernel<true><<<n_splits, 256, smem, st>>>(D, ld, g0, R, nq, Lkey, Laux, knn, idx_offset, rows_per_split,
+        select_few_kernel<true><<<grid, 256, smem, st>>>(D, ld, g0, R, nq, Lkey, Laux, knn, idx_offset, rows_per_split,
                                                              part_stride);
     } else {
         err = cudaFuncSetAttribute(select_few_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (err != cudaSuccess) return err;
-        select_few_kernel<false><<<n_splits, 256, smem, st>>>(D, ld, g0, R, nq, Lkey, Laux, knn, idx_offset, rows_per_split,
+        select_few_kernel<false><<<grid, 256, smem, st>>>(D, ld, g0, R, nq, Lkey, Laux, knn, idx_offset, rows_per_split,
                                                               part_stride);
     }
     return cudaGetLastError();
@@ -1117,10 +1116,9 @@ cudaError_t launch_select_few(bool aux, const float *D, uint64_t ld, uint64_t g0
 
 cudaError_t launch_select(bool cols, bool aux, const float *D, uint64_t ld, uint64_t g0, uint32_t R, uint64_t c0,
                           uint64_t n, uint64_t t0, uint64_t t1, unsigned long long *Lkey, float *Laux, uint32_t knn,
-                          cudaStream_t st, int cross, uint64_t idx_offset, uint32_t n_splits, uint32_t rows_per_split,
-                          uint64_t part_stride) {
+                          cudaStream_t st) {
     if (t1 <= t0) return cudaSuccess;
-    const dim3 grid((unsigned)((t1 - t0 + TS - 1) / TS), cross ? n_splits : 1u);
+    const dim3 grid((unsigned)((t1 - t0 + TS - 1) / TS));
     size_t smem = (size_t)TS * 128 * 8 + (aux ? (size_t)TS * 128 * 4 : 0) + (size_t)TS * (TS + 1) * 4 * (aux ? 2 : 1) +
                   TS * 8 + TS * 4;
     cudaError_t err;
@@ -1128,8 +1126,7 @@ cudaError_t launch_select(bool cols, bool aux, const float *D, uint64_t ld, uint
     do {                                                                                                         \
         err = cudaFuncSetAttribute(select_kernel<C, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (err != cudaSuccess) return err;                                                                      \
-        select_kernel<C, A><<<grid, 256, smem, st>>>(D, ld, g0, R, c0, n, t0, t1, Lkey, Laux, knn, cross,        \
-                                                     idx_offset, rows_per_split, part_stride);                  \
+        select_kernel<C, A><<<grid, 256, smem, st>>>(D, ld, g0, R, c0, n, t0, t1, Lkey, Laux, knn);              \
     } while (0)
     if (cols && aux) SKD_SEL(true, true);
     else if (cols) SKD_SEL(true, false);

@@ -24,10 +24,9 @@ void launch_knn_merge(const unsigned long long *part_key, const float *part_aux,
 
 cudaError_t launch_select(bool cols, bool aux, const float *D, uint64_t ld, uint64_t g0, uint32_t R, uint64_t c0,
                           uint64_t n, uint64_t t0, uint64_t t1, unsigned long long *Lkey, float *Laux, uint32_t knn,
-                          cudaStream_t st, int cross = 0, uint64_t idx_offset = 0, uint32_t n_splits = 1,
-                          uint32_t rows_per_split = 0, uint64_t part_stride = 0);
+                          cudaStream_t st);
 
-// Cross mode with at most 8 target columns: rows of every split divided over the warps (see select_few_kernel).
+// Cross mode (few query columns): 8 targets per CTA, rows of every split divided over its warps (select_few_kernel).
 cudaError_t launch_select_few(bool aux, const float *D, uint64_t ld, uint64_t g0, uint32_t R, uint32_t nq,
                               unsigned long long *Lkey, float *Laux, uint32_t knn, cudaStream_t st, uint64_t idx_offset,
                               uint32_t n_splits, uint32_t rows_per_split, uint64_t part_stride);
