@@ -183,6 +183,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-seconds", type=float, default=10.0, help="CPU seconds per reference step / baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stream-roofline", action="store_true", help="skip the HBM-bound few-queries leg (N=1 only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
@@ -348,6 +349,8 @@ def main():
             "wall_ms_per_step_incl_flush": (t_wall1 - t_wall0) / args.steps * 1e3,
             "result_checksum_rank0": checksum,
         }
+        if world == 1 and not args.no_stream_roofline:
+            line["roofline_hbm"] = stream_roofline(ctx, sk, synth, torch)
         if not args.no_cpu_baseline and world == 1:
             threads = os.cpu_count() or 1
             rate, count, passes, secs = cpu_reference_rate(pin_in.array, n, args.ref_seconds, threads)
@@ -363,6 +366,47 @@ def main():
     ctx.device_free(d_out)
     if world > 1:
         dist.destroy_process_group()
+
+
+def stream_roofline(ctx, sk, synth, torch, n_ref=200000, reps=5):
+    """Second roofline of the path: ONE query against n_ref references is HBM-bound.  Dense
+    cross core/accessory through the C ABI with the result left in HBM; algorithmic bytes = the reference planes read
+    once (K*W*14*8 B per sample).  Timed by the library's CUDA events on its own stream; the 2.9 GB input exceeds L2."""
+    per = len(KMERS) * W * 14
+    bins = torch.empty(n_ref * per, dtype=torch.int64, device="cuda")
+    for s0 in range(0, n_ref, 50000):
+        s1 = min(n_ref, s0 + 50000)
+        bins[s0 * per:s1 * per] = synth.make_bins(s1 - s0, W, KMERS, seed=1000 + s0, device="cuda")
+    refs = sk.SketchDb.upload(ctx, bins.data_ptr(), n_ref, KMERS, W, bins_loc=sk.SKD_DEVICE)
+    del bins
+    q = synth.make_bins(1, W, KMERS, seed=7, device="cuda")
+    qry = sk.SketchDb.upload(ctx, q.data_ptr(), 1, KMERS, W, bins_loc=sk.SKD_DEVICE)
+    out = ctx.device_alloc(n_ref * 8)
+    dt = sk.set_k(refs)
+    ms = []
+    for i in range(reps + 2):
+        ctx._check(ctx.lib.skd_cross_dists_all(ctx.handle, refs.handle, qry.handle, dt.c, None, None, 0.64, 0, n_ref, out,
+                                               sk.SKD_DEVICE))
+        if i >= 2:
+            ms.append(ctx.last_kernel_ms)
+    avg = sum(ms) / len(ms)
+    algorithmic = n_ref * per * 8
+    traffic = None
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_stream_kernel.json")))
+        traffic = float(prof["launches"][0]["dram__bytes_read.sum"].split()[0]) * 1e9 * n_ref / 200000
+    except Exception:
+        pass
+    ctx.device_free(out)
+    refs.free()
+    qry.free()
+    peak = measured_hbm()
+    return {"bound": "hbm", "kernel": "skd::stream_kernel<1>",
+            "workload": f"dense cross core/accessory, {n_ref} references x 1 query, 1024 bins x 8 k, results in HBM",
+            "achieved": algorithmic / (avg * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+            "frac": algorithmic / (avg * 1e-3) / 1e9 / peak, "ms_per_launch": avg,
+            "algorithmic_bytes_per_launch": algorithmic, "traffic": traffic,
+            "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy: read+write bytes); this kernel only reads, so frac can exceed 1"}
 
 
 def measured_hbm():
