@@ -601,6 +601,36 @@ def test_few_queries_knn_equals_row_owned_path(sk, ctx, n_ref, nq, knn):
         tiny.close()
 
 
+@pytest.mark.parametrize("n_ref,nq,W,kmers", [(700, 3, 160, [21]), (700, 8, 160, [21]), (450, 2, 40, list(range(13, 31, 2))),
+                                              (450, 5, 40, list(range(13, 31, 2))), (300, 1, 1, [11, 15]), (1000, 13, 16, [15, 19, 23, 27]),
+                                              (95, 16, 3, [17, 21, 25])])
+def test_stream_kernel_shapes(sk, ctx, n_ref, nq, W, kmers):
+    """The streaming few-queries kernel over its envelope: large sketches (config 5 shape), a query side that does not
+    fit in shared memory (9 k x 40 words x 5 queries: falls back to the tile kernel), K = 2, two passes (9-16
+    queries), ragged last blocks, row ranges, completeness; counts bit-exact, distances against the oracle."""
+    ref, qry = synth_pair(n_ref, nq, W, kmers, seed=123 + nq, n_families=4)
+    gr, gq = up(sk, ctx, ref), up(sk, ctx, qry)
+    K = len(kmers)
+    want = oracle.match_counts(ref, qry, all_pairs(n_ref, nq)).reshape(n_ref, nq, K)
+    assert np.array_equal(sk.match_counts(gr, gq), want)
+    mid = K // 2
+    wj = oracle.cross_dists_all(ref, qry, k_idx=mid, threads=4)
+    assert np.array_equal(sk.cross_dists_all(gr, gq, dist_type=sk.set_k(gr, kmers[mid])).distances, wj)
+    lo, hi = n_ref // 3 + 1, n_ref - 5   # a row range that starts and ends inside 32-sample half blocks
+    part = sk.cross_dists_all(gr, gq, dist_type=sk.set_k(gr, kmers[mid]), rows=(lo, hi)).distances
+    assert np.array_equal(part, wj.reshape(n_ref, nq)[lo:hi].ravel())
+    if K >= 2:
+        check_close(sk.cross_dists_all(gr, gq, dist_type=sk.set_k(gr)).distances, oracle.cross_dists_all(ref, qry, threads=4))
+        rng = np.random.default_rng(nq)
+        rc, qc = rng.uniform(0.7, 1.0, size=n_ref), rng.uniform(0.7, 1.0, size=nq)
+        got = sk.cross_dists_all(gr, gq, dist_type=sk.set_k(gr), ref_completeness_vec=rc, query_completeness_vec=qc)
+        check_close(got.distances, oracle.cross_dists_all(ref, qry, ref_c=rc, query_c=qc, threads=4))
+    knn = min(7, n_ref)
+    got = sk.cross_dists_knn(gr, gq, knn=knn, dist_type=sk.set_k(gr, kmers[mid], ani=True))
+    oidx, od0, _ = oracle.cross_dists_knn(ref, qry, knn, k_idx=mid, ani=True, threads=4)
+    assert_knn_matches(got.idx, got.d0, None, oidx, od0, None, True)
+
+
 # ------------------------------------------------------------------ randomized differential sweep
 def test_random_shapes_against_oracle(sk, ctx):
     rng = np.random.default_rng(2026)
