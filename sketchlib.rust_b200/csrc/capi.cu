@@ -474,7 +474,7 @@ skd_status run_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, bool self, 
 
 // Cross kNN with few queries: the row-owned kernel would have only a few row blocks (queries are its rows), so
 // instead the dense cross kernel (references as rows; narrow-column variant when <= 32 queries) writes the kNN
-// keys ref-major into HBM and select_kernel folds each query's column into per-slice lists, merged at the end.
+// keys ref-major into HBM and select_few_kernel folds each query's column into per-slice lists, merged at the end.
 // E is oriented for the row-owned call (a = queries, b = refs).
 constexpr uint64_t kFewQueries = 512;
 skd_status finalize_lists(skd_ctx *ctx, const unsigned long long *dkeys, const float *daux, uint32_t n_parts,
@@ -698,7 +698,7 @@ skd_status finalize_lists(skd_ctx *ctx, const unsigned long long *dkeys, const f
 
 // Symmetric self-kNN: every unordered pair is evaluated once.  Row groups of the upper triangle are computed
 // by the tile kernel into a row-major key matrix in HBM (rect mode) and folded into per-row lists twice by
-// select_kernel: along rows (candidates j for row i) and along columns (candidates i for row j).
+// select_sym_kernel: along rows (candidates j for row i) and along columns (candidates i for row j).
 // Lists: dkey[n][knn] (+ daux), device memory, covering ALL n rows; only triangle rows [row_begin, row_end)
 // are evaluated, so ranks that split the triangle produce partial lists to be merged (skd_knn_merge).
 
@@ -717,7 +717,7 @@ skd_status run_knn_symmetric(skd_ctx *ctx, const skd_db *db, const EpiParams &E,
         R = std::min<uint64_t>(R, (row_end - g0 + TS - 1) / TS * TS);
         const uint64_t g1 = std::min<uint64_t>({g0 + R, row_end, n});
         void *D;
-        skd_status st = scratch_get(ctx, "knn_rect", R * ld * elt, &D);
+        skd_status st = scratch_get(ctx, "knn_rect", R * ld * elt + 64, &D);  // + 64: 8-column vector reads of the last row
         if (st) return st;
         // tile kernel, rect mode, rows [g0, g1)
         SchedParams S{};
@@ -750,10 +750,10 @@ skd_status run_knn_symmetric(skd_ctx *ctx, const skd_db *db, const EpiParams &E,
         if (st) return st;
         CU(ctx, launch_tiles(db->dev, db->dev, E, S, off.back(), count32, smem, ctx->compute));
         // rows of the group: candidates to their right; columns right of g0: candidates from the group's rows
-        CU(ctx, launch_select(false, with_aux, (const float *)D, ld, g0, (uint32_t)(g1 - g0), g0, n, g0, g1, dkey, daux,
-                              (uint32_t)knn, ctx->compute));
-        CU(ctx, launch_select(true, with_aux, (const float *)D, ld, g0, (uint32_t)(g1 - g0), g0, n, g0, n, dkey, daux,
-                              (uint32_t)knn, ctx->compute));
+        CU(ctx, launch_select_sym(false, with_aux, (const float *)D, ld, g0, (uint32_t)(g1 - g0), n, g0, g1, dkey, daux,
+                                  (uint32_t)knn, ctx->compute));
+        CU(ctx, launch_select_sym(true, with_aux, (const float *)D, ld, g0, (uint32_t)(g1 - g0), n, g0, n, dkey, daux,
+                                  (uint32_t)knn, ctx->compute));
         ctx->launches += 3;
         st = timer_end(ctx);
         if (st) return st;

@@ -464,7 +464,7 @@ __global__ void __launch_bounds__(THREADS, 2)
                 else
                     idx = nA * gi - ((gi * (gi + 1)) >> 1) + gj - 1 - gi - S.out_base;  // square_to_condensed
             } else if (rect) {
-                idx = (gi - S.row_begin) * S.rect_ld + gj;  // ref-major kNN keys for select_kernel
+                idx = (gi - S.row_begin) * S.rect_ld + gj;  // ref-major kNN keys for select_few_kernel
             } else {
                 idx = (gi - S.row_begin) * nB + gj;  // ref-major
             }
@@ -478,7 +478,7 @@ __global__ void __launch_bounds__(THREADS, 2)
             else
                 pair_epilogue<CountT, false>(counts, pair, E, gi, gj, rect, d0, d1);
 #endif
-            if (rect) {  // read back soon by select_kernel: normal (L2-resident) stores
+            if (rect) {  // read back soon by the select kernels: normal (L2-resident) stores
                 if (E.kind == KIND_CORE_ACC)
                     reinterpret_cast<float2 *>(S.out)[idx] = make_float2(d0, d1);
                 else
@@ -729,7 +729,7 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
                     pair_epilogue<uint16_t, true>(counts, pair, E, gi, gj, rect, d0, d1);
                 else
                     pair_epilogue<uint16_t, false>(counts, pair, E, gi, gj, rect, d0, d1);
-                if (rect) {  // kNN keys, read back soon by select_kernel
+                if (rect) {  // kNN keys, read back soon by select_few_kernel
                     if (E.kind == KIND_CORE_ACC)
                         reinterpret_cast<float2 *>(S.out)[idx] = make_float2(d0, d1);
                     else
@@ -878,128 +878,18 @@ void launch_knn_merge(const unsigned long long *part_key, const float *part_aux,
 // Symmetric self-kNN, second stage.  The tile kernel (rect mode) has written the kNN keys of the pairs
 // (i, j > i) of a row group as a row-major matrix D in HBM; every such value is a candidate for row i
 // (read along rows) and for row j (read along columns), so each unordered pair is computed once.
-// One CTA owns 64 targets (rows or columns of D), streams 64x64 sub-tiles of D through shared memory and
-// keeps, per target, the running list L[target][knn] (sorted composites) topped up through a 128-slot
-// buffer with threshold rejection, exactly like the tile kernel's kNN epilogue.
-// (Ref-major cross matrices with few query columns go through select_few_kernel below.)
-template <bool COLS, bool AUX>
-__global__ void __launch_bounds__(256) select_kernel(const float *__restrict__ D, uint64_t ld, uint64_t g0, uint32_t R,
-                                                     uint64_t c0, uint64_t n, uint64_t t0, uint64_t t1,
-                                                     unsigned long long *__restrict__ Lkey, float *__restrict__ Laux,
-                                                     uint32_t knn) {
-    constexpr int CAP = 128;
-    extern __shared__ __align__(16) unsigned char sm_raw[];
-    unsigned long long *buf = reinterpret_cast<unsigned long long *>(sm_raw);           // [64][CAP]
-    float *baux = reinterpret_cast<float *>(buf + TS * CAP);                              // [64][CAP]
-    float *tkey = baux + (AUX ? TS * CAP : 0);                                            // [64][65]
-    float *taux = tkey + TS * (TS + 1);                                                   // [64][65]
-    unsigned long long *thr = reinterpret_cast<unsigned long long *>(taux + (AUX ? TS * (TS + 1) : 0));
-    uint32_t *cnt = reinterpret_cast<uint32_t *>(thr + TS);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint64_t tbase = t0 + (uint64_t)blockIdx.x * TS;  // first target (global sample index) of this CTA
-    // start from the lists accumulated so far
-    for (int e = tid; e < TS * CAP; e += 256) {
-        const int t = e / CAP, s = e % CAP;
-        const uint64_t tg = tbase + t;
-        unsigned long long v = ~0ull;
-        float a = 0.f;
-        if (tg < t1 && s < (int)knn) {
-            v = Lkey[tg * knn + s];
-            if (AUX) a = Laux[tg * knn + s];
-        }
-        buf[e] = v;
-        if (AUX) baux[e] = a;
-    }
-    __syncthreads();
-    for (int t = tid; t < TS; t += 256) {
-        uint32_t c = 0;
-        while (c < knn && buf[t * CAP + c] != ~0ull) ++c;  // lists are sorted: padding is at the end
-        cnt[t] = c;
-        thr[t] = c == knn ? buf[t * CAP + knn - 1] : ~0ull;
-    }
-    __syncthreads();
-
-    // candidate range along the streamed dimension
-    // ROWS: targets are rows i in [tbase, +64), candidates are columns j in (i, n)
-    // COLS: targets are columns j, candidates are rows i in [g0, min(j, g0 + R))
-    const uint64_t s_begin = COLS ? g0 : (tbase + 1 > c0 ? tbase + 1 : c0);
-    const uint64_t s_end = COLS ? (g0 + R < tbase + TS ? g0 + R : tbase + TS) : n;
-    for (uint64_t sb = s_begin / TS * TS; sb < s_end; sb += TS) {
-        // load D sub-tile: ROWS: rows = targets, cols = sb..sb+63 ; COLS: rows = sb.., cols = targets
-        for (int e = tid; e < TS * TS; e += 256) {
-            const int r = e / TS, c = e % TS;
-            const uint64_t gi = COLS ? sb + r : tbase + r, gj = COLS ? tbase + c : sb + c;
-            float k = 0.f, a = 0.f;
-            if (gi >= g0 && gi < g0 + R && gj < n && gj > gi && gj >= c0) {
-                const uint64_t off = (gi - g0) * ld + (gj - c0);
-                if (AUX) {
-                    float2 v = __ldcs(reinterpret_cast<const float2 *>(D) + off);
-                    k = v.x;
-                    a = v.y;
-                } else {
-                    k = __ldcs(D + off);
-                }
-            }
-            tkey[r * (TS + 1) + c] = k;
-            if (AUX) taux[r * (TS + 1) + c] = a;
-        }
-        __syncthreads();
-        for (int t = warp; t < TS; t += 8) {
-            const uint64_t tg = tbase + t;
-            if (tg >= t1) continue;
-            const unsigned long long th = thr[t];
-            uint32_t c = cnt[t];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int s = lane + 32 * h;
-                const uint64_t cand = sb + s;  // global index of the candidate sample
-                const uint64_t gi = COLS ? cand : tg, gj = COLS ? tg : cand;
-                bool ok = gi >= g0 && gi < g0 + R && gj < n && gj > gi && gj >= c0;
-                const int r = COLS ? s : t, cc = COLS ? t : s;
-                unsigned long long comp = 0;
-                if (ok) {
-                    comp = ((unsigned long long)float_order_bits(tkey[r * (TS + 1) + cc]) << 32) |
-                           (uint32_t)cand;
-                    ok = comp < th;
-                }
-                const unsigned m = __ballot_sync(0xffffffffu, ok);
-                if (ok) {
-                    const uint32_t slot = c + __popc(m & ((1u << lane) - 1u));
-                    buf[t * CAP + slot] = comp;
-                    if (AUX) baux[t * CAP + slot] = taux[r * (TS + 1) + cc];
-                }
-                c += __popc(m);
-            }
-            __syncwarp();
-            if (c + TS > CAP) {
-                warp_bitonic_sort(buf + t * CAP, AUX ? baux + t * CAP : nullptr, CAP, lane);
-                for (int e = knn + lane; e < CAP; e += 32) buf[t * CAP + e] = ~0ull;
-                __syncwarp();
-                c = knn;
-                if (lane == 0) thr[t] = buf[t * CAP + knn - 1];
-            }
-            if (lane == 0) cnt[t] = c;
-        }
-        __syncthreads();
-    }
-    for (int t = warp; t < TS; t += 8) {
-        const uint64_t tg = tbase + t;
-        if (tg >= t1) continue;
-        warp_bitonic_sort(buf + t * CAP, AUX ? baux + t * CAP : nullptr, CAP, lane);
-        for (uint32_t e = lane; e < knn; e += 32) {
-            Lkey[tg * knn + e] = buf[t * CAP + e];
-            if (AUX) Laux[tg * knn + e] = baux[t * CAP + e];
-        }
-    }
-}
+// select_sym_kernel folds D into the running per-sample lists L[sample][knn] (sorted u64 composites, ~0 padded);
+// select_few_kernel does the same for ref-major cross matrices with few query columns.  Both keep 128-slot lists
+// in shared memory with threshold rejection, exactly like the tile kernel's kNN epilogue.  (A first version streamed
+// 64x64 sub-tiles of D through shared memory with one warp per target and two CTA barriers per sub-tile: 2.7x slower.)
 
 // Cross-mode selection over few target columns (queries).  D is a ref-major matrix of kNN keys (rows = references
 // g0 .., columns = the nq queries; float2 key/aux with AUX; ld >= nq): every row is a candidate of every column and
 // the stored neighbour index is row + idx_offset.  A CTA takes a group of 8 targets (blockIdx.y) and one slice of
 // rows_per_split rows (blockIdx.x; one list set per slice at Lkey + slice * part_stride); the rows of the slice are
 // divided over the 8 warps, warp w keeps one list per target (list w * 8 + q), lanes take 32 consecutive rows at a
-// time, and the 8 lists of a target are merged at the end.  (Giving each target to one warp, as select_kernel does,
-// leaves one warp per CTA busy when there is a single query: 2.3 ms instead of 0.3 ms per 500 000 references.)
+// time, and the 8 lists of a target are merged at the end.  (Giving each target to one warp leaves one warp per CTA
+// busy when there is a single query: 2.3 ms instead of 0.3 ms per 500 000 references.)
 template <bool AUX>
 __global__ void __launch_bounds__(256) select_few_kernel(const float *__restrict__ D, uint64_t ld, uint64_t g0, uint32_t R,
                                                          uint32_t nq, unsigned long long *__restrict__ Lkey,
@@ -1114,19 +1004,163 @@ cudaError_t launch_select_few(bool aux, const float *D, uint64_t ld, uint64_t g0
     return cudaGetLastError();
 }
 
-cudaError_t launch_select(bool cols, bool aux, const float *D, uint64_t ld, uint64_t g0, uint32_t R, uint64_t c0,
-                          uint64_t n, uint64_t t0, uint64_t t1, unsigned long long *Lkey, float *Laux, uint32_t knn,
-                          cudaStream_t st) {
+// Symmetric self-kNN, second stage: a CTA takes 8 targets, its 8
+// warps take contiguous slices of the candidate range, every warp keeps one 128-slot list per target, and the 8 lists
+// of a target are merged with the list accumulated so far (Lkey / Laux, [n][knn]) at the end.
+//   ROWS: targets are rows i of the group [t0, t1) = [g0, g1), candidates are the columns j in (i, n): lanes read 32
+//         consecutive keys of row i.
+//   COLS: targets are columns j in [t0, t1) = [g0, n), candidates are the rows i in [g0, min(j, g0 + R)): a lane reads
+//         the keys of its row for the CTA's 8 consecutive columns (32 or 64 contiguous bytes).
+// Every candidate at or above a target's current knn-th key is rejected up front by all warps.
+template <bool COLS, bool AUX>
+__global__ void __launch_bounds__(256) select_sym_kernel(const float *__restrict__ D, uint64_t ld, uint64_t g0, uint32_t R,
+                                                         uint64_t n, uint64_t t0, uint64_t t1,
+                                                         unsigned long long *__restrict__ Lkey, float *__restrict__ Laux,
+                                                         uint32_t knn) {
+    constexpr int CAP = 128;
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    unsigned long long *buf = reinterpret_cast<unsigned long long *>(sm_raw);  // [8 warps][8 targets][CAP]
+    float *baux = reinterpret_cast<float *>(buf + TS * CAP);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint64_t tbase = t0 + (uint64_t)blockIdx.x * 8;
+    const uint32_t nt = (uint32_t)(t1 - tbase < 8 ? t1 - tbase : 8);
+
+    // candidate range of the CTA (union over its targets), cut into 8 warp slices of whole 32-candidate steps
+    const uint64_t s_begin = COLS ? g0 : tbase + 1;
+    const uint64_t s_end = COLS ? (tbase + nt - 1 < g0 + R ? tbase + nt - 1 : g0 + R) : n;
+    const uint64_t span = s_end > s_begin ? s_end - s_begin : 0;
+    const uint64_t per_warp = ((span + 7) / 8 + 31) / 32 * 32;
+    const uint64_t w_lo = s_begin + (uint64_t)warp * per_warp;
+    const uint64_t w_hi = w_lo + per_warp < s_end ? w_lo + per_warp : s_end;
+
+    uint32_t cnt[8];
+    unsigned long long thr[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        unsigned long long *list = buf + (warp * 8 + q) * CAP;
+        for (int e = lane; e < CAP; e += 32) list[e] = ~0ull;
+        cnt[q] = 0;
+        thr[q] = q < (int)nt ? Lkey[(tbase + q) * knn + knn - 1] : 0ull;  // ~0 while the list is not full
+    }
+    __syncwarp();
+
+    for (uint64_t c0 = w_lo; c0 < w_hi; c0 += 32) {
+        const uint64_t cand = c0 + lane;
+        const bool in = cand < w_hi;
+        float key[8], av[8];
+        if (COLS) {  // one row, 8 consecutive columns
+            const size_t off = (size_t)(cand - g0) * ld + (tbase - g0);
+            if (in) {
+                if (AUX) {
+                    const float4 *p4 = reinterpret_cast<const float4 *>(reinterpret_cast<const float2 *>(D) + off);
+#pragma unroll
+                    for (int h = 0; h < 4; ++h) {
+                        const float4 v = __ldcs(p4 + h);
+                        key[2 * h] = v.x;
+                        av[2 * h] = v.y;
+                        key[2 * h + 1] = v.z;
+                        av[2 * h + 1] = v.w;
+                    }
+                } else {
+                    const float4 *p4 = reinterpret_cast<const float4 *>(D + off);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const float4 v = __ldcs(p4 + h);
+                        key[4 * h] = v.x;
+                        key[4 * h + 1] = v.y;
+                        key[4 * h + 2] = v.z;
+                        key[4 * h + 3] = v.w;
+                    }
+                }
+            }
+        } else {  // 8 rows, one column each
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (in && q < (int)nt && cand > tbase + q) {
+                    const size_t off = (size_t)(tbase + q - g0) * ld + (cand - g0);
+                    if (AUX) {
+                        const float2 v = __ldcs(reinterpret_cast<const float2 *>(D) + off);
+                        key[q] = v.x;
+                        av[q] = v.y;
+                    } else {
+                        key[q] = __ldcs(D + off);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            if (q >= (int)nt) break;
+            const uint64_t tg = tbase + q;
+            const bool valid = in && (COLS ? cand < tg : cand > tg);
+            unsigned long long comp = 0;
+            if (valid) comp = ((unsigned long long)float_order_bits(key[q]) << 32) | (uint32_t)cand;
+            const bool ok = valid && comp < thr[q];
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (m == 0) continue;
+            unsigned long long *list = buf + (warp * 8 + q) * CAP;
+            float *la = AUX ? baux + (warp * 8 + q) * CAP : nullptr;
+            if (ok) {
+                const uint32_t slot = cnt[q] + __popc(m & ((1u << lane) - 1u));
+                list[slot] = comp;
+                if (AUX) la[slot] = av[q];
+            }
+            cnt[q] += __popc(m);
+            __syncwarp();
+            if (cnt[q] + 32 > CAP) {
+                warp_bitonic_sort(list, la, CAP, lane);
+                for (int e = knn + lane; e < CAP; e += 32) list[e] = ~0ull;
+                __syncwarp();
+                cnt[q] = knn;
+                thr[q] = list[knn - 1] < thr[q] ? list[knn - 1] : thr[q];
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+        if (q < (int)nt && cnt[q] > 0)
+            warp_bitonic_sort(buf + (warp * 8 + q) * CAP, AUX ? baux + (warp * 8 + q) * CAP : nullptr, CAP, lane);
+    __syncthreads();
+    // warp q merges: the list accumulated so far + the 8 warp lists of target q (each sorted, best knn first)
+    if (warp < (int)nt) {
+        const int q = warp;
+        const uint64_t tg = tbase + q;
+        unsigned long long *acc = buf + q * CAP;  // warp 0's list of this target doubles as the accumulator
+        float *acc_a = AUX ? baux + q * CAP : nullptr;
+        bool any = false;
+        for (int w = 0; w < 8; ++w) any |= buf[(w * 8 + q) * CAP] != ~0ull;
+        if (!any) return;  // no candidate beat the threshold: the stored list stands
+        for (int w = 0; w < 8; ++w) {
+            // source: w == 0 -> the stored list; otherwise warp w's list
+            const unsigned long long *src = w == 0 ? Lkey + tg * knn : buf + (w * 8 + q) * CAP;
+            const float *src_a = !AUX ? nullptr : (w == 0 ? Laux + tg * knn : baux + (w * 8 + q) * CAP);
+            if (src[0] == ~0ull) continue;  // empty
+            for (int e = lane; e < CAP - (int)knn; e += 32) {
+                acc[knn + e] = e < (int)knn ? src[e] : ~0ull;
+                if (AUX) acc_a[knn + e] = e < (int)knn ? src_a[e] : 0.f;
+            }
+            __syncwarp();
+            warp_bitonic_sort(acc, acc_a, CAP, lane);
+        }
+        for (uint32_t e = lane; e < knn; e += 32) {
+            Lkey[tg * knn + e] = acc[e];
+            if (AUX) Laux[tg * knn + e] = acc_a[e];
+        }
+    }
+}
+
+cudaError_t launch_select_sym(bool cols, bool aux, const float *D, uint64_t ld, uint64_t g0, uint32_t R, uint64_t n,
+                              uint64_t t0, uint64_t t1, unsigned long long *Lkey, float *Laux, uint32_t knn,
+                              cudaStream_t st) {
     if (t1 <= t0) return cudaSuccess;
-    const dim3 grid((unsigned)((t1 - t0 + TS - 1) / TS));
-    size_t smem = (size_t)TS * 128 * 8 + (aux ? (size_t)TS * 128 * 4 : 0) + (size_t)TS * (TS + 1) * 4 * (aux ? 2 : 1) +
-                  TS * 8 + TS * 4;
+    const unsigned grid = (unsigned)((t1 - t0 + 7) / 8);
+    const size_t smem = (size_t)TS * 128 * 8 + (aux ? (size_t)TS * 128 * 4 : 0);
     cudaError_t err;
-#define SKD_SEL(C, A)                                                                                            \
-    do {                                                                                                         \
-        err = cudaFuncSetAttribute(select_kernel<C, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        if (err != cudaSuccess) return err;                                                                      \
-        select_kernel<C, A><<<grid, 256, smem, st>>>(D, ld, g0, R, c0, n, t0, t1, Lkey, Laux, knn);              \
+#define SKD_SEL(C, A)                                                                                                \
+    do {                                                                                                             \
+        err = cudaFuncSetAttribute(select_sym_kernel<C, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+        if (err != cudaSuccess) return err;                                                                          \
+        select_sym_kernel<C, A><<<grid, 256, smem, st>>>(D, ld, g0, R, n, t0, t1, Lkey, Laux, knn);                   \
     } while (0)
     if (cols && aux) SKD_SEL(true, true);
     else if (cols) SKD_SEL(true, false);

@@ -22,10 +22,12 @@ void launch_knn_merge(const unsigned long long *part_key, const float *part_aux,
                       uint32_t cap, uint64_t first_lrow, uint64_t n_rows, int kind, unsigned long long *idx_out, float *d0_out,
                       float *d1_out, unsigned long long *key_out, float *aux_out, cudaStream_t st);
 
-cudaError_t launch_select(bool cols, bool aux, const float *D, uint64_t ld, uint64_t g0, uint32_t R, uint64_t c0,
-                          uint64_t n, uint64_t t0, uint64_t t1, unsigned long long *Lkey, float *Laux, uint32_t knn,
-                          cudaStream_t st);
-
+// Symmetric self-kNN second stage: folds the rect key matrix D of row group [g0, g0 + R) (leading dimension ld,
+// first column g0) into the per-sample lists Lkey/Laux [n][knn].  cols = false: targets are the rows [t0, t1) of the
+// group; cols = true: targets are the columns [t0, t1).
+cudaError_t launch_select_sym(bool cols, bool aux, const float *D, uint64_t ld, uint64_t g0, uint32_t R, uint64_t n,
+                              uint64_t t0, uint64_t t1, unsigned long long *Lkey, float *Laux, uint32_t knn,
+                              cudaStream_t st);
 // Cross mode (few query columns): 8 targets per CTA, rows of every split divided over its warps (select_few_kernel).
 cudaError_t launch_select_few(bool aux, const float *D, uint64_t ld, uint64_t g0, uint32_t R, uint32_t nq,
                               unsigned long long *Lkey, float *Laux, uint32_t knn, cudaStream_t st, uint64_t idx_offset,
