@@ -98,33 +98,30 @@ def main():
         total = 0.0
     ctx.last_kernel_ms_total = 0.0
 
-    if 3 in want:
-        n = int(100_000 * args.scale)
-        g, gen_s, up_s = make_db(ctx, n, 16, KMERS8, 3, dev)
-        dt = sk.set_k(g)
-        knn = 50
-        # symmetric: each unordered pair once; ranks take equal-pair triangle row blocks and produce partial
-        # lists for all n rows, exchanged with ONE NCCL all-gather and merged on every rank
+    def symmetric_knn(g, n, dt, knn, with_aux):
+        """Symmetric self kNN over all ranks: each unordered pair once; ranks take equal-pair triangle row blocks and
+        produce partial lists for all n rows, exchanged with ONE NCCL all-to-all and merged by the rank that owns the
+        rows; final rows are all-gathered.  Returns (ms, exchange+merge ms, checksum of d0)."""
         r0, r1 = sk.triangle_row_partition(n, rank, world)
-        # rows padded to a multiple of the world size so that the all-to-all has equal splits
-        n_pad = (n + world - 1) // world * world
+        n_pad = (n + world - 1) // world * world   # equal splits for the all-to-all
         rows_mine = n_pad // world
         keys = torch.full((n_pad, knn), -1, dtype=torch.int64, device=dev)   # -1 = UINT64_MAX padding
-        aux = torch.zeros((n_pad, knn), dtype=torch.float32, device=dev)
+        aux = torch.zeros((n_pad, knn), dtype=torch.float32, device=dev) if with_aux else None
         idx_o = torch.empty((rows_mine, knn), dtype=torch.int64, device=dev)
         d0_o = torch.empty((rows_mine, knn), dtype=torch.float32, device=dev)
-        d1_o = torch.empty((rows_mine, knn), dtype=torch.float32, device=dev)
+        d1_o = torch.empty((rows_mine, knn), dtype=torch.float32, device=dev) if with_aux else None
+        ptr = lambda t: t.data_ptr() if t is not None else None
         if world > 1:
             recv_keys = torch.empty((world, rows_mine, knn), dtype=torch.int64, device=dev)
-            recv_aux = torch.empty((world, rows_mine, knn), dtype=torch.float32, device=dev)
+            recv_aux = torch.empty((world, rows_mine, knn), dtype=torch.float32, device=dev) if with_aux else None
             all_idx = torch.empty((n_pad, knn), dtype=torch.int64, device=dev)
             all_d0 = torch.empty((n_pad, knn), dtype=torch.float32, device=dev)
-            all_d1 = torch.empty((n_pad, knn), dtype=torch.float32, device=dev)
+            all_d1 = torch.empty((n_pad, knn), dtype=torch.float32, device=dev) if with_aux else None
         xchg = {"ms": 0.0}
 
         def run():
             ctx._check(ctx.lib.skd_self_knn_partial(ctx.handle, g.handle, knn, dt.c, None, 0.64, r0, r1, keys.data_ptr(),
-                                                    aux.data_ptr(), sk.SKD_DEVICE))
+                                                    ptr(aux), sk.SKD_DEVICE))
             ms = ctx.last_kernel_ms
             e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
             torch.cuda.synchronize()
@@ -132,37 +129,45 @@ def main():
             if world > 1:
                 # rank r receives, from every rank, the partial lists of ITS rows [r*rows_mine, (r+1)*rows_mine)
                 dist.all_to_all_single(recv_keys.view(-1), keys.view(-1))
-                dist.all_to_all_single(recv_aux.view(-1), aux.view(-1))
-                kp, ap, parts = recv_keys.data_ptr(), recv_aux.data_ptr(), world
+                if with_aux:
+                    dist.all_to_all_single(recv_aux.view(-1), aux.view(-1))
+                kp, ap, parts = recv_keys.data_ptr(), ptr(recv_aux), world
             else:
-                kp, ap, parts = keys.data_ptr(), aux.data_ptr(), 1
+                kp, ap, parts = keys.data_ptr(), ptr(aux), 1
             e1.record()
             torch.cuda.synchronize()
             ctx._check(ctx.lib.skd_knn_merge(ctx.handle, kp, ap, parts, rows_mine, knn, dt.c, sk.SKD_DEVICE,
-                                             idx_o.data_ptr(), d0_o.data_ptr(), d1_o.data_ptr(), sk.SKD_DEVICE))
+                                             idx_o.data_ptr(), d0_o.data_ptr(), ptr(d1_o), sk.SKD_DEVICE))
             merge_ms = ctx.last_kernel_ms
             e2.record()
             if world > 1:  # final sparse rows to every rank (rank 0 would write the text)
                 dist.all_gather_into_tensor(all_idx, idx_o)
                 dist.all_gather_into_tensor(all_d0, d0_o)
-                dist.all_gather_into_tensor(all_d1, d1_o)
+                if with_aux:
+                    dist.all_gather_into_tensor(all_d1, d1_o)
             e3 = torch.cuda.Event(enable_timing=True)
             e3.record()
             torch.cuda.synchronize()
             xchg["ms"] = e0.elapsed_time(e1) + merge_ms + e2.elapsed_time(e3)
             ctx.last_kernel_ms_total = ms + xchg["ms"]
         ms = timed(run)
+        checksum = float((all_d0 if world > 1 else d0_o)[:n].double().sum().item())
+        return ms, maxr(xchg["ms"]), checksum
+
+    if 3 in want:
+        n = int(100_000 * args.scale)
+        g, gen_s, up_s = make_db(ctx, n, 16, KMERS8, 3, dev)
+        ms, xms, checksum = symmetric_knn(g, n, sk.set_k(g), 50, True)
         emit({"config": 3, "what": "self kNN 50 core/acc, 1024 bins, K=8 (symmetric: each unordered pair once)", "n": n,
-              "kernel_ms": ms, "exchange_and_merge_ms": maxr(xchg["ms"]),
+              "kernel_ms": ms, "exchange_and_merge_ms": xms,
               "unique_pairs_per_s": n * (n - 1) / 2 / (ms * 1e-3),
               "reference_equivalent_ordered_pairs_per_s": n * (n - 1) / (ms * 1e-3),
               "lop3_T_per_s": n * (n - 1) / 2 * 3584 / (ms * 1e-3) / 1e12 / world, "db_hbm_bytes": g.hbm_bytes,
-              "checksum": float((all_d0 if world > 1 else d0_o)[:n].double().sum().item()),
+              "checksum": checksum,
               "note": "the reference evaluates every ordered pair (i, j != i); here each unordered pair is evaluated once "
                       "and credited to both rows; ranks own equal-pair triangle row blocks; partial lists are exchanged "
                       "with one NCCL all-to-all, each rank merges its rows, final rows are all-gathered; "
                       "lop3_T_per_s is per GPU"})
-        del keys, aux, idx_o, d0_o, d1_o
         g.free()
 
     if 4 in want:
@@ -262,15 +267,12 @@ def main():
               "kernel_ms": ms, "pairs_per_s": pairs / (ms * 1e-3), "lop3_T_per_s": pairs * lop3_pair / (ms * 1e-3) / 1e12 / world,
               "db_hbm_bytes": g.hbm_bytes, "note": "equal-pair triangle row blocks over ranks"})
         ctx.device_free(dbuf)
-        k0, k1 = sk.row_partition(n, rank, world)
         dta = sk.set_k(g, 21, ani=True)
-
-        def run_knn():
-            sk.self_dists_knn(g, knn=50, dist_type=dta, rows=(k0, k1))
-            ctx.last_kernel_ms_total = ctx.last_kernel_ms
-        ms = timed(run_knn)
-        emit({"config": 5, "what": "self kNN 50 ANI k=21, 10240 bins", "n": n, "kernel_ms": ms,
-              "ordered_pairs_per_s": n * (n - 1) / (ms * 1e-3), "lop3_T_per_s": n * (n - 1) * lop3_pair / (ms * 1e-3) / 1e12})
+        ms, xms, checksum = symmetric_knn(g, n, dta, 50, False)
+        emit({"config": 5, "what": "self kNN 50 ANI k=21, 10240 bins (symmetric: each unordered pair once)", "n": n,
+              "kernel_ms": ms, "exchange_and_merge_ms": xms, "unique_pairs_per_s": n * (n - 1) / 2 / (ms * 1e-3),
+              "reference_equivalent_ordered_pairs_per_s": n * (n - 1) / (ms * 1e-3),
+              "lop3_T_per_s": n * (n - 1) / 2 * lop3_pair / (ms * 1e-3) / 1e12 / world, "checksum": checksum})
         g.free()
 
     if rank == 0 and args.out:
