@@ -198,7 +198,7 @@ class SketchDb:
 
     def __init__(self, ctx, handle, names, kmer_lengths, sketchsize64, sketch_size):
         self.ctx, self.handle = ctx, handle
-        self.names = list(names)
+        self._names = None if names is None else list(names)
         self.kmer_lengths = [int(k) for k in kmer_lengths]
         self.sketchsize64, self.sketch_size = int(sketchsize64), int(sketch_size)
 
@@ -224,7 +224,6 @@ class SketchDb:
         else:
             ctx._check(ctx.lib.skd_db_upload(ctx.handle, _ptr(bins), bins_loc, int(n_samples), sample_stride,
                                              kmer_stride, W, sketch_size, _ptr(kmers), len(kmers), C.byref(h)))
-        names = names if names is not None else [f"s{i}" for i in range(int(n_samples))]
         return cls(ctx, h, names, kmers.tolist(), W, sketch_size)
 
     @classmethod
@@ -239,8 +238,14 @@ class SketchDb:
         h = C.c_void_p()
         ctx._check(ctx.lib.skd_db_load_skd(ctx.handle, os.fsencode(skd_path), _ptr(idx), int(n_samples), sample_stride,
                                            kmer_stride, W, sketch_size, _ptr(kmers), len(kmers), C.byref(h)))
-        names = names if names is not None else [f"s{i}" for i in range(int(n_samples))]
         return cls(ctx, h, names, kmers.tolist(), W, sketch_size)
+
+    @property
+    def names(self):
+        """Sample names; default names s0, s1, ... are made on first use (10 000 f-strings cost more than a launch)."""
+        if self._names is None:
+            self._names = [f"s{i}" for i in range(self.number_samples_loaded())]
+        return self._names
 
     def number_samples_loaded(self):
         return int(self.ctx.lib.skd_db_n_samples(self.handle))

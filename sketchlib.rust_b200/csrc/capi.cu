@@ -33,6 +33,7 @@ constexpr uint32_t kSymKnnMax = 64;           // symmetric self-kNN keeps 128-sl
 struct skd_ctx {
     int device = 0;
     cudaStream_t compute = nullptr, copy = nullptr;
+    cudaStream_t aux[2] = {nullptr, nullptr};  // async-upload dense runs: re-tiling / every other column band
     std::string err;
     uint64_t launches = 0;
     float last_ms = 0.f;
@@ -121,18 +122,18 @@ skd_status pinned_get(skd_ctx *ctx, size_t bytes) {
 }
 
 void timers_reset(skd_ctx *ctx) { ctx->timers_used = 0; }
-skd_status timer_begin(skd_ctx *ctx) {
+skd_status timer_begin(skd_ctx *ctx, cudaStream_t stream = nullptr) {
     if (ctx->timers_used == ctx->timers.size()) {
         cudaEvent_t a, b;
         CU(ctx, cudaEventCreate(&a));
         CU(ctx, cudaEventCreate(&b));
         ctx->timers.push_back({a, b});
     }
-    CU(ctx, cudaEventRecord(ctx->timers[ctx->timers_used].first, ctx->compute));
+    CU(ctx, cudaEventRecord(ctx->timers[ctx->timers_used].first, stream ? stream : ctx->compute));
     return SKD_OK;
 }
-skd_status timer_end(skd_ctx *ctx) {
-    CU(ctx, cudaEventRecord(ctx->timers[ctx->timers_used].second, ctx->compute));
+skd_status timer_end(skd_ctx *ctx, cudaStream_t stream = nullptr) {
+    CU(ctx, cudaEventRecord(ctx->timers[ctx->timers_used].second, stream ? stream : ctx->compute));
     ctx->timers_used++;
     return SKD_OK;
 }
@@ -272,13 +273,14 @@ void build_groups(uint32_t group, bool self, uint32_t rb0, uint32_t n_rb, uint32
 }
 
 // Re-tile chunk c of an asynchronously uploaded database (compute stream waits for its arrival).
-skd_status retile_chunk(skd_ctx *ctx, skd_db *db, size_t c) {
+skd_status retile_chunk(skd_ctx *ctx, skd_db *db, size_t c, cudaStream_t stream = nullptr) {
     auto &p = db->pending;
+    if (!stream) stream = ctx->compute;
     const uint32_t b0 = c ? p.block_end[c - 1] : 0, b1 = p.block_end[c];
     const uint64_t s0 = (uint64_t)b0 * TS, s1 = std::min<uint64_t>(db->n, (uint64_t)b1 * TS);
-    CU(ctx, cudaStreamWaitEvent(ctx->compute, p.ready[c], 0));
+    CU(ctx, cudaStreamWaitEvent(stream, p.ready[c], 0));
     launch_repack(p.raw + s0 * p.sample_stride, s1 - s0, p.sample_stride, p.kmer_stride, db->tiled, db->dev, b0, b1 - b0,
-                  ctx->compute);
+                  stream);
     CU(ctx, cudaGetLastError());
     ctx->launches++;
     return SKD_OK;
@@ -307,7 +309,9 @@ skd_status materialize(skd_ctx *ctx, const skd_db *cdb) {
 // of `off` (group offsets built by build_groups for exactly this row range).
 skd_status launch_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, const EpiParams &E, int mode, uint64_t r0,
                         uint64_t r1, float *dout, const std::vector<uint64_t> &off, const uint64_t *d_grp_off,
-                        uint64_t rect_ld = 0, uint32_t cb_lo = 0, uint32_t cb_hi = 0, uint64_t out_row_begin = ~0ull) {
+                        uint64_t rect_ld = 0, uint32_t cb_lo = 0, uint32_t cb_hi = 0, uint64_t out_row_begin = ~0ull,
+                        cudaStream_t stream = nullptr) {
+    if (!stream) stream = ctx->compute;
     SchedParams S{};
     S.mode = mode;
     S.one = 1;
@@ -331,11 +335,11 @@ skd_status launch_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, const Ep
     if (smem > kMaxSmem)
         return fail(ctx, SKD_ERR_UNSUPPORTED, "%d k-mer lengths at %u bins need %zu B of shared memory per tile", E.nk,
                     E.nbins, smem);
-    skd_status st = timer_begin(ctx);
+    skd_status st = timer_begin(ctx, stream);
     if (st) return st;
-    CU(ctx, launch_tiles(A->dev, B->dev, E, S, off.back(), count32, smem, ctx->compute));
+    CU(ctx, launch_tiles(A->dev, B->dev, E, S, off.back(), count32, smem, stream));
     ctx->launches++;
-    return timer_end(ctx);
+    return timer_end(ctx, stream);
 }
 
 // Rows [row_begin, row_end) of a dense matrix, streamed to host in chunks or written in place on the device.
@@ -421,16 +425,49 @@ skd_status run_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, bool self, 
             if (st) return st;
             CU(ctx, cudaMemcpyAsync(dband, flat.data(), flat.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->compute));
             CU(ctx, cudaStreamSynchronize(ctx->compute));  // flat is pageable
+            // Streams: aux[0] re-tiles the chunks in arrival order; the column bands alternate between the compute
+            // stream and aux[1], each waiting only for "its" chunk to be re-tiled, so that the tiles of band c + 1 fill
+            // the SMs while band c drains (on one stream every band boundary costs a partial wave).
+            std::vector<cudaEvent_t> retiled(nc, nullptr);
+            auto drop_events = [&] {
+                for (auto e : retiled)
+                    if (e) cudaEventDestroy(e);
+            };
+            CU(ctx, cudaEventRecord(ctx->ev_a[0], ctx->compute));  // database buffers exist, offsets uploaded
+            CU(ctx, cudaStreamWaitEvent(ctx->aux[0], ctx->ev_a[0], 0));
+            CU(ctx, cudaStreamWaitEvent(ctx->aux[1], ctx->ev_a[0], 0));
             for (size_t c = 0; c < nc; ++c) {
-                st = retile_chunk(ctx, pa, c);
-                if (st) return st;
+                st = retile_chunk(ctx, pa, c, ctx->aux[0]);
+                if (st == SKD_OK && cudaEventCreateWithFlags(&retiled[c], cudaEventDisableTiming) != cudaSuccess)
+                    st = fail(ctx, SKD_ERR_CUDA, "cudaEventCreate failed");
+                if (st == SKD_OK && cudaEventRecord(retiled[c], ctx->aux[0]) != cudaSuccess)
+                    st = fail(ctx, SKD_ERR_CUDA, "cudaEventRecord failed");
+                if (st) {
+                    cudaDeviceSynchronize();
+                    drop_events();
+                    return st;
+                }
+            }
+            for (size_t c = 0; c < nc; ++c) {
+                cudaStream_t band = (c & 1) ? ctx->aux[1] : ctx->compute;
+                cudaStreamWaitEvent(band, retiled[c], 0);
                 if (offs[c].empty() || offs[c].back() == 0) continue;
                 const uint32_t b0 = c ? pa->pending.block_end[c - 1] : 0, b1 = pa->pending.block_end[c];
                 const uint64_t r1 = std::min<uint64_t>(row_end, (uint64_t)b1 * TS);
                 st = launch_dense(ctx, A, B, E, mode, row_begin, r1, out, offs[c], (const uint64_t *)dband + pos[c], 0, b0, b1,
-                                  row_begin);
-                if (st) return st;
+                                  row_begin, band);
+                if (st) {
+                    cudaDeviceSynchronize();
+                    drop_events();
+                    return st;
+                }
             }
+            for (int i = 0; i < 2; ++i) {  // join: the compute stream continues after both helpers
+                cudaEventRecord(ctx->ev_b[i], ctx->aux[i]);
+                cudaStreamWaitEvent(ctx->compute, ctx->ev_b[i], 0);
+            }
+            CU(ctx, cudaStreamSynchronize(ctx->compute));
+            drop_events();
             st = finish_pending(ctx, pa);
             if (st) return st;
             CU(ctx, cudaStreamSynchronize(ctx->compute));
@@ -958,13 +995,17 @@ skd_status skd_ctx_create(int device, skd_ctx **out) {
     cudaDeviceProp prop;
     if ((e = cudaSetDevice(device)) != cudaSuccess || (e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess ||
         (e = cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking)) != cudaSuccess ||
-        (e = cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking)) != cudaSuccess) {
+        (e = cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->aux[0], cudaStreamNonBlocking)) != cudaSuccess ||
+        (e = cudaStreamCreateWithFlags(&ctx->aux[1], cudaStreamNonBlocking)) != cudaSuccess) {
         delete ctx;
         return fail(nullptr, SKD_ERR_CUDA, "context setup failed: %s", cudaGetErrorString(e));
     }
     if (prop.major != 10) {
         cudaStreamDestroy(ctx->compute);
         cudaStreamDestroy(ctx->copy);
+        cudaStreamDestroy(ctx->aux[0]);
+        cudaStreamDestroy(ctx->aux[1]);
         delete ctx;
         return fail(nullptr, SKD_ERR_UNSUPPORTED, "device %d is sm_%d%d; libsketchdist is built for sm_100a only", device,
                     prop.major, prop.minor);
@@ -1008,6 +1049,8 @@ void skd_ctx_destroy(skd_ctx *ctx) {
     }
     if (ctx->compute) cudaStreamDestroy(ctx->compute);
     if (ctx->copy) cudaStreamDestroy(ctx->copy);
+    for (int i = 0; i < 2; ++i)
+        if (ctx->aux[i]) cudaStreamDestroy(ctx->aux[i]);
     delete ctx;
 }
 
