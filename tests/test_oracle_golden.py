@@ -135,3 +135,94 @@ def test_precluster_driver_goldens():
     nidx, d0 = oracle.self_dists_knn_precluster(db, none_off, none_idx, 2, 0, retain=2)
     kidx, kd0, _ = oracle.self_dists_knn(db, 2, k_idx=0)
     assert np.array_equal(nidx, kidx) and np.array_equal(d0, kd0)
+
+
+# ---------------------------------------------------------------- second opinion: an independent restatement
+def _py_bins(db, s, k_idx):
+    """14-bit bin values of sample s at k index k_idx, rebuilt from the bit planes (inverse of fill_usigs,
+    src/sketch/mod.rs:215-223)."""
+    sl = db.bins[s * db.sample_stride + k_idx * db.kmer_stride:][:db.W * 14].reshape(db.W, 14)
+    bits = (sl[:, :, None] >> np.arange(64, dtype=np.uint64)[None, None, :]) & np.uint64(1)    # [w][plane][bin]
+    return (bits * (np.uint64(1) << np.arange(14, dtype=np.uint64))[None, :, None]).sum(axis=1).reshape(-1)
+
+
+def _py_jaccard(a_bins, b_bins, W, c1=None, c2=None, cutoff=0.64):
+    """jaccard.rs:6-45 on bin VALUES (equal bins <=> all 14 planes equal)."""
+    samebits = int((a_bins == b_bins).sum())
+    maxnbits = 64 * W
+    expected = maxnbits >> 14
+    diff = max(0, samebits - expected)
+    intersize = diff * maxnbits / (maxnbits - expected)
+    j = intersize / (64 * W)
+    if c1 is not None and c2 is not None and c1 * c2 >= cutoff:
+        j = min(1.0, j / (c1 * c2 / (c1 + c2 - c1 * c2)))
+    return j
+
+
+def _py_core_acc(db, i, j, comp=None):
+    """core_acc_dist + simple_linear_regression, jaccard.rs:61-142, in Python floats (IEEE double, same libm)."""
+    import math
+    tol = math.log(2.0 / (db.sketch_size * 64.0))
+    xsum = ysum = xysum = xsq = ysq = 0.0
+    n = 0.0
+    for k_idx, k in enumerate(db.kmers.tolist()):
+        c1, c2 = (None, None) if comp is None else (comp[i], comp[j])
+        jac = _py_jaccard(_py_bins(db, i, k_idx), _py_bins(db, j, k_idx), db.W, c1, c2)
+        y = math.log(jac) if jac > 0 else -math.inf
+        if y < tol:
+            break
+        x = float(k)
+        xsum += x
+        ysum += y
+        xysum += x * y
+        xsq += x * x
+        ysq += y * y
+        n += 1.0
+    if math.isnan(ysum) or ysum == -math.inf or n < 3:
+        return 1.0, 1.0
+    xbar, ybar = xsum / n, ysum / n
+    x_diff, y_diff = xsq - xsum * xsum / n, ysq - ysum * ysum / n
+    xstddev, ystddev = math.sqrt(x_diff / n), math.sqrt(y_diff / n)
+    den = math.sqrt(x_diff * y_diff)
+    num = xysum - xsum * ysum / n
+    r = num / den if den != 0 else (math.nan if num == 0 else math.copysign(math.inf, num))
+    beta = r * ystddev / xstddev
+    alpha = -beta * xbar + ybar
+    if math.isnan(r):
+        core = 0.0          # `beta < 0` and `r > 0` are both false for NaN
+    else:
+        core = 1.0 - math.exp(beta) if beta < 0 else (1.0 if r > 0 else 0.0)
+    acc = 1.0 - math.exp(alpha) if alpha < 0 else 0.0
+    return core, acc
+
+
+@pytest.mark.parametrize("n,W,kmers,seed", [(9, 2, [13, 17, 21, 25, 29], 1), (6, 16, [15, 19, 23], 2), (4, 256, [17, 21, 25, 29], 3),
+                                            (7, 1, [11, 13, 15, 17], 4)])
+def test_oracle_agrees_with_independent_python_restatement(n, W, kmers, seed):
+    """The C oracle against a second, structurally different restatement (bin values rebuilt from the planes, Python
+    float arithmetic): bit-identical f32 distances for core/accessory, Jaccard, ANI and completeness, including
+    >= 16 384 bins (expected_samebits = 1), early breaks, n < 3 and constant-y pairs."""
+    import math
+    from helpers import synth_db
+    db = synth_db(n, W, kmers, seed=seed, n_families=2)
+    rows = db.bins.reshape(n, -1).copy()
+    rows[1] = rows[0]                       # identical pair: y = 0 at every k -> NaN r -> (0, 0)
+    rows[2, :W * 14] ^= np.uint64(0xFFFFFFFFFFFFFFFF)   # sample 2 shares nothing at the first k -> break at once -> (1, 1)
+    db = oracle.Db(rows.reshape(-1), n, kmers, W)
+    comp = np.linspace(0.7, 1.0, n)
+    got = oracle.self_dists_all(db).reshape(-1, 2)
+    gotc = oracle.self_dists_all(db, completeness=comp, cutoff=0.64).reshape(-1, 2)
+    mid = len(kmers) // 2
+    gotj = oracle.self_dists_all(db, k_idx=mid)
+    gota = oracle.self_dists_all(db, k_idx=mid, ani=True)
+    d = 0
+    for i in range(n):
+        for j in range(i + 1, n):
+            assert tuple(got[d]) == tuple(np.float32(v) for v in _py_core_acc(db, i, j)), (i, j)
+            assert tuple(gotc[d]) == tuple(np.float32(v) for v in _py_core_acc(db, i, j, comp)), (i, j)
+            jac = _py_jaccard(_py_bins(db, i, mid), _py_bins(db, j, mid), W)
+            assert gotj[d] == np.float32(1.0 - jac)
+            ani = max(0.0, 1.0 + (1.0 / kmers[mid]) * math.log(2.0 * jac / (1.0 + jac))) if jac > 0 else 0.0
+            assert gota[d] == np.float32(ani)
+            d += 1
+    assert tuple(got[0]) == (0.0, 0.0) and tuple(got[1]) == (1.0, 1.0)
