@@ -763,12 +763,10 @@ static bool stream_applies(const DevDb &A, const DevDb &B, const EpiParams &E, c
 }
 
 static cudaError_t launch_stream(const DevDb &A, const DevDb &B, const EpiParams &E, const SchedParams &S, cudaStream_t st) {
-    static int sm_count = 0;
-    if (sm_count == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-    }
+    int dev = 0, sm_count = 148;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0)
+        sm_count = 148;
     const int NQ = B.n <= 1 ? 1 : B.n <= 2 ? 2 : B.n <= 4 ? 4 : 8;
     const size_t smem = stream_smem(A, E, NQ);
     const uint64_t units = (S.row_end + 31) / 32 - S.row_begin / 32;
