@@ -106,6 +106,11 @@ skd_status skd_db_load_skd(skd_ctx *ctx, const char *skd_path, const uint64_t *s
                            uint64_t sketchsize64, uint64_t sketch_size, const uint64_t *kmer_lengths,
                            uint32_t n_kmers, skd_db **out);
 void skd_db_free(skd_db *db);
+/* Hands a completely loaded database to another context of the SAME device.  A loader thread with its own context
+ * can then fill the next shard of a large reference file (skd_db_load_skd is synchronous) while this context
+ * compares the previous one: the out-of-core / overlapped form of read_sketch_data + cross_dists_knn
+ * (multisketch.rs:167-184, src/distances/mod.rs:306-395).  The previous owner must not use `db` afterwards. */
+skd_status skd_db_adopt(skd_ctx *ctx, skd_db *db);
 uint64_t skd_db_n_samples(const skd_db *db);       /* number_samples_loaded, multisketch.rs:106-111 */
 uint32_t skd_db_n_kmers(const skd_db *db);
 uint64_t skd_db_sketch_size(const skd_db *db);     /* bins */

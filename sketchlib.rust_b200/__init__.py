@@ -74,6 +74,7 @@ def load_library(build=True):
         "skd_db_upload_async": (C.c_int, [vp, vp, u64, u64, u64, u64, u64, vp, u32, C.POINTER(vp)]),
         "skd_db_load_skd": (C.c_int, [vp, C.c_char_p, vp, u64, u64, u64, u64, u64, vp, u32, C.POINTER(vp)]),
         "skd_db_free": (None, [vp]),
+        "skd_db_adopt": (C.c_int, [vp, vp]),
         "skd_db_n_samples": (u64, [vp]),
         "skd_db_n_kmers": (u32, [vp]),
         "skd_db_sketch_size": (u64, [vp]),

@@ -1164,6 +1164,18 @@ void skd_db_free(skd_db *db) {
     if (db->lny_dev) cudaFreeAsync(db->lny_dev, st);
     delete db;
 }
+skd_status skd_db_adopt(skd_ctx *ctx, skd_db *db) {
+    if (!ctx || !db || !db->ctx) return fail(ctx, SKD_ERR_INVALID, "null context or database");
+    if (db->ctx == ctx) return SKD_OK;
+    if (db->ctx->device != ctx->device)
+        return fail(ctx, SKD_ERR_INVALID, "database lives on device %d, context on device %d", db->ctx->device, ctx->device);
+    CU(ctx, cudaSetDevice(ctx->device));
+    skd_status st = materialize(db->ctx, db);  // an upload still in flight is completed by its own context
+    if (st) return fail(ctx, st, "%s", db->ctx->err.c_str());
+    CU(ctx, cudaStreamSynchronize(db->ctx->compute));
+    db->ctx = ctx;
+    return SKD_OK;
+}
 uint64_t skd_db_n_samples(const skd_db *db) { return db ? db->n : 0; }
 uint32_t skd_db_n_kmers(const skd_db *db) { return db ? (uint32_t)db->kmers.size() : 0; }
 uint64_t skd_db_sketch_size(const skd_db *db) { return db ? db->sketch_size : 0; }

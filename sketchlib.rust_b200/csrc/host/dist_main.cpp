@@ -66,6 +66,7 @@ struct DistArgs {
     double completeness_cutoff = 0.64;
     int gpu = 0;
     int gpus = 1;
+    long long ref_shard_mb = 4096;  // cross --knn: references are loaded and compared in shards of this size
     bool verbose = false, quiet = false;
 };
 
@@ -86,6 +87,8 @@ const char *USAGE =
     "      --completeness-cutoff <X>      Minimum c1*c2 for the completeness correction [default: 0.64]\n"
     "      --gpu <ID>                     CUDA device [default: 0]\n"
     "      --gpus <N>                     Use devices 0..N-1 for --knn runs (one host thread and context per device)\n"
+    "      --ref-shard-mb <MB>            Cross --knn: load and compare the references in shards of this size, the next\n"
+    "                                     shard loading while the previous one is compared [default: 4096]\n"
     "  -v, --verbose                      Show progress messages\n"
     "      --quiet                        Don't show any messages\n";
 
@@ -138,6 +141,9 @@ DistArgs parse_args(int argc, char **argv) {
             a.completeness_cutoff = strtod(v.c_str(), &end);
             if (v.empty() || end != v.c_str() + v.size())
                 throw UsageError("invalid value '" + v + "' for '--completeness-cutoff <COMPLETENESS_CUTOFF>'");
+        } else if (is("--ref-shard-mb")) {
+            a.ref_shard_mb = parse_uint(value("--ref-shard-mb <MB>"), "--ref-shard-mb <MB>");
+            if (a.ref_shard_mb < 1) throw UsageError("invalid value for '--ref-shard-mb <MB>': at least 1");
         } else if (is("--gpus")) {
             a.gpus = (int)parse_uint(value("--gpus <N>"), "--gpus <N>");
             if (a.gpus < 1) throw UsageError("invalid value for '--gpus <N>': at least one device is needed");
@@ -333,23 +339,19 @@ KnnOut multi_gpu_knn(const DistArgs &a, const MultiSketch &refs, const std::stri
         auto fail = [&](const char *what) {
             errs[d] = std::string(what) + ": " + skd_last_error(ctx);
         };
-        if (skd_ctx_create(d, &ctx) != SKD_OK) {
-            errs[d] = std::string("device ") + std::to_string(d) + ": " + skd_last_error(nullptr);
+        const int dev = world == 1 ? a.gpu : d;
+        if (skd_ctx_create(dev, &ctx) != SKD_OK) {
+            errs[d] = std::string("device ") + std::to_string(dev) + ": " + skd_last_error(nullptr);
             return;
         }
         do {
-            uint64_t lo = 0, hi = n;  // reference samples this device loads
-            if (cross) {
-                lo = n * d / world;
-                hi = n * (d + 1) / world;
-            }
-            std::vector<uint64_t> fi = file_indices(lo, hi);
-            if (skd_db_load_skd(ctx, (ref_prefix + ".skd").c_str(), fi.data(), hi - lo, refs.sample_stride, refs.kmer_stride,
-                                refs.sketchsize64, refs.sketch_size, refs.kmer_lengths.data(),
-                                (uint32_t)refs.kmer_lengths.size(), &rdb) != SKD_OK) {
-                fail("loading references");
-                break;
-            }
+            const uint64_t lo = cross ? n * d / world : 0, hi = cross ? n * (d + 1) / world : n;  // references of this device
+            auto load_refs = [&](skd_ctx *c, uint64_t s0, uint64_t s1, skd_db **out) {
+                std::vector<uint64_t> fi = file_indices(s0, s1);
+                return skd_db_load_skd(c, (ref_prefix + ".skd").c_str(), fi.data(), s1 - s0, refs.sample_stride,
+                                       refs.kmer_stride, refs.sketchsize64, refs.sketch_size, refs.kmer_lengths.data(),
+                                       (uint32_t)refs.kmer_lengths.size(), out) == SKD_OK;
+            };
             if (cross) {
                 if (skd_db_load_skd(ctx, (q_prefix + ".skd").c_str(), nullptr, rows, queries->sample_stride,
                                     queries->kmer_stride, queries->sketchsize64, queries->sketch_size,
@@ -357,12 +359,54 @@ KnnOut multi_gpu_knn(const DistArgs &a, const MultiSketch &refs, const std::stri
                     fail("loading queries");
                     break;
                 }
-                keys[d].resize(rows * nn);
-                if (with_aux) aux[d].resize(rows * nn);
-                if (skd_cross_knn_partial(ctx, rdb, qdb, nn, dt, ref_c ? ref_c + lo : nullptr, query_c, a.completeness_cutoff,
-                                          lo, keys[d].data(), with_aux ? aux[d].data() : nullptr, SKD_HOST) != SKD_OK)
-                    fail("cross kNN");
-            } else if (partial) {
+                // Reference shards of this device: shard i + 1 is read by a loader thread with its own context while
+                // shard i is compared, so file I/O + PCIe overlap the kernels and the references never have to fit
+                // in HBM at once.  Every shard yields one partial list set (merged at the end with the other devices').
+                uint64_t per_shard = std::max<uint64_t>(64, ((uint64_t)a.ref_shard_mb << 20) / (refs.sample_stride * 8) / 64 * 64);
+                const uint64_t max_parts = std::max<uint64_t>(1, 64 / (uint64_t)world);  // the final merge handles 64 lists
+                per_shard = std::max(per_shard, ((hi - lo + max_parts - 1) / max_parts + 63) / 64 * 64);
+                const uint64_t ns = hi > lo ? (hi - lo + per_shard - 1) / per_shard : 0;
+                keys[d].resize(ns * rows * nn);
+                if (with_aux) aux[d].resize(ns * rows * nn);
+                skd_ctx *lctx = nullptr;
+                if (ns > 1 && skd_ctx_create(dev, &lctx) != SKD_OK) {
+                    errs[d] = std::string("device ") + std::to_string(dev) + ": " + skd_last_error(nullptr);
+                    break;
+                }
+                skd_db *next = nullptr;
+                bool next_ok = ns == 0 || load_refs(ctx, lo, std::min(hi, lo + per_shard), &next);
+                if (!next_ok) fail("loading references");
+                for (uint64_t i = 0; i < ns && errs[d].empty(); ++i) {
+                    rdb = next;
+                    next = nullptr;
+                    const uint64_t s0 = lo + i * per_shard;
+                    std::thread loader;
+                    std::string load_err;
+                    if (i + 1 < ns)
+                        loader = std::thread([&, i] {
+                            const uint64_t n0 = lo + (i + 1) * per_shard;
+                            if (!load_refs(lctx, n0, std::min(hi, n0 + per_shard), &next))
+                                load_err = std::string("loading references: ") + skd_last_error(lctx);
+                        });
+                    if (skd_cross_knn_partial(ctx, rdb, qdb, nn, dt, ref_c ? ref_c + s0 : nullptr, query_c,
+                                              a.completeness_cutoff, s0, keys[d].data() + i * rows * nn,
+                                              with_aux ? aux[d].data() + i * rows * nn : nullptr, SKD_HOST) != SKD_OK)
+                        fail("cross kNN");
+                    skd_db_free(rdb);
+                    rdb = nullptr;
+                    if (loader.joinable()) loader.join();
+                    if (!load_err.empty()) errs[d] = load_err;
+                    if (next && skd_db_adopt(ctx, next) != SKD_OK) fail("adopting a reference shard");
+                }
+                if (next) skd_db_free(next);
+                if (lctx) skd_ctx_destroy(lctx);
+                break;
+            }
+            if (!load_refs(ctx, 0, n, &rdb)) {
+                fail("loading references");
+                break;
+            }
+            if (partial) {
                 const uint64_t r0 = triangle_bound(n, d, world), r1 = triangle_bound(n, d + 1, world);
                 keys[d].resize(n * nn);
                 if (with_aux) aux[d].resize(n * nn);
@@ -403,15 +447,16 @@ KnnOut multi_gpu_knn(const DistArgs &a, const MultiSketch &refs, const std::stri
         }
         return out;
     }
-    std::vector<uint64_t> all_keys((size_t)world * rows * nn);
-    std::vector<float> all_aux(with_aux ? (size_t)world * rows * nn : 0);
-    for (int d = 0; d < world; ++d) {
-        std::copy(keys[d].begin(), keys[d].end(), all_keys.begin() + (size_t)d * rows * nn);
-        if (with_aux) std::copy(aux[d].begin(), aux[d].end(), all_aux.begin() + (size_t)d * rows * nn);
+    std::vector<uint64_t> all_keys;
+    std::vector<float> all_aux;
+    for (int d = 0; d < world; ++d) {  // every device contributes one list set (self) or one per reference shard (cross)
+        all_keys.insert(all_keys.end(), keys[d].begin(), keys[d].end());
+        if (with_aux) all_aux.insert(all_aux.end(), aux[d].begin(), aux[d].end());
     }
+    const uint32_t n_parts = (uint32_t)(all_keys.size() / std::max<uint64_t>(1, rows * nn));
     Gpu g0;
-    if (skd_ctx_create(0, &g0.ctx) != SKD_OK) throw std::runtime_error(skd_last_error(nullptr));
-    g0.check(skd_knn_merge(g0.ctx, all_keys.data(), with_aux ? all_aux.data() : nullptr, (uint32_t)world, rows, nn, dt,
+    if (skd_ctx_create(world == 1 ? a.gpu : 0, &g0.ctx) != SKD_OK) throw std::runtime_error(skd_last_error(nullptr));
+    g0.check(skd_knn_merge(g0.ctx, all_keys.data(), with_aux ? all_aux.data() : nullptr, n_parts, rows, nn, dt,
                            SKD_HOST, out.idx.data(), out.d0.data(), with_aux ? out.d1.data() : nullptr, SKD_HOST));
     return out;
 }
@@ -465,8 +510,12 @@ int run(const DistArgs &a) {
         }
     }
 
-    // ---- several devices: sparse outputs only (for dense outputs the text tail, not the GPU, is the bottleneck)
-    if (a.gpus > 1 && a.knn >= 0) {
+    // ---- several devices: sparse outputs only (for dense outputs the text tail, not the GPU, is the bottleneck).
+    // The same driver runs a single device when a cross --knn run has more reference data than one shard: the
+    // references are then streamed through HBM shard by shard, each loaded while the previous one is compared.
+    const bool sharded_refs = a.has_query && a.knn >= 0 &&
+                              n * refs.meta.sample_stride * 8 > ((uint64_t)a.ref_shard_mb << 20);
+    if ((a.gpus > 1 || sharded_refs) && a.knn >= 0) {
         Out out(a);
         skd_dist_type dt;
         dt.kind = a.kmer < 0 ? SKD_CORE_ACC : (a.ani ? SKD_ANI : SKD_JACCARD);
@@ -492,7 +541,7 @@ int run(const DistArgs &a) {
         }
         if (nn == 0) throw std::runtime_error("knn must be at least 1");
         log_info("Calculating sparse distances with " + std::to_string(nn) + " nearest neighbours on " +
-                 std::to_string(a.gpus) + " devices");
+                 std::to_string(a.gpus) + " device(s)" + (sharded_refs ? ", references in shards" : ""));
         KnnOut r = multi_gpu_knn(a, refs.meta, ref_name, a.subset.empty() ? nullptr : &subset_idx,
                                  a.has_query ? &queries.meta : nullptr, qname, dt, nn, has_ref_c ? ref_c.data() : nullptr,
                                  has_query_c ? query_c.data() : nullptr);

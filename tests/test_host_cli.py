@@ -182,6 +182,36 @@ def test_cli_dense_and_cross_modes(tools, tmp_path):
     assert len(r.stdout.splitlines()) == 9 * 8 and "knn=50 is higher than number of samples=9" in r.stderr
 
 
+@pytest.mark.gpu
+def test_cli_cross_knn_streams_reference_shards(tools, tmp_path):
+    """Cross --knn with the references loaded and compared shard by shard (loader thread + second context, the
+    shard handed over with skd_db_adopt): same text as the run that loads the whole reference database at once,
+    with and without completeness files, single-k and core/accessory, and in --subset order."""
+    cli, _ = tools
+    ref, qry = synth_pair(1500, 23, 16, [17, 21, 25, 29], seed=61, n_families=12)
+    rp, qp = write_skm_skd(str(tmp_path / "ref"), ref), write_skm_skd(str(tmp_path / "qry"), qry)
+    comp = tmp_path / "c.txt"
+    rng = np.random.default_rng(4)
+    comp.write_text("".join(f"ref{i}\t{c:.3f}\n" for i, c in enumerate(rng.uniform(0.7, 1.0, size=1500))))
+    qc = tmp_path / "qc.txt"
+    qc.write_text("".join(f"qry{i}\t0.9\n" for i in range(23)))
+    sub = tmp_path / "subset.txt"
+    sub.write_text("".join(f"ref{i}\n" for i in range(1499, 200, -2)))
+    for extra in (["--knn", "10"], ["--knn", "10", "-k", "21", "--ani"], ["--knn", "64", "-k", "25"],
+                  ["--knn", "7", "--ref-completeness-file", str(comp), "--query-completeness-file", str(qc)],
+                  ["--knn", "5", "--subset", str(sub)]):
+        whole = run([cli, "dist", rp, qp] + extra)
+        assert whole.returncode == 0, whole.stderr
+        shard = run([cli, "dist", rp, qp, "-v", "--ref-shard-mb", "1"] + extra)   # 1 MB = 128 references per shard
+        assert shard.returncode == 0, shard.stderr
+        assert "references in shards" in shard.stderr and "references in shards" not in whole.stderr
+        assert shard.stdout == whole.stdout and len(whole.stdout.splitlines()) == 23 * int(extra[1])
+    # the oracle agrees with the sharded run (values; neighbours apart from exact ties)
+    r = run([cli, "dist", rp, qp, "--knn", "10", "-k", "21", "--ref-shard-mb", "2"])
+    oidx, od0, _ = oracle.cross_dists_knn(ref, qry, 10, k_idx=1, threads=4)
+    assert [l.split("\t")[2] for l in r.stdout.splitlines()] == [oracle.fmt_f32(v) for v in od0.ravel()]
+
+
 # ---------------------------------------------------------------- `sketchlib sketch` (CPU tool, DNA FASTA)
 def _write_fasta(path, records, gz=False, width=60):
     import gzip
