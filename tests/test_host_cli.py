@@ -343,6 +343,10 @@ def test_cli_multi_gpu_knn_equals_single_gpu(tools, tmp_path):
         two = run([cli, "dist", rp] + args + ["--gpus", "2"])
         assert one.returncode == 0 and two.returncode == 0, (args, one.stderr, two.stderr)
         assert one.stdout == two.stdout and len(one.stdout) > 0, args
+    # both devices stream their half of the references in several shards (700 refs, 1 MB = 128 refs per shard)
+    one = run([cli, "dist", rp, qp, "--knn", "9"])
+    two = run([cli, "dist", rp, qp, "--knn", "9", "--gpus", "2", "--ref-shard-mb", "1", "-v"])
+    assert two.returncode == 0 and two.stdout == one.stdout and "references in shards" in two.stderr
 
 
 # ---------------------------------------------------------------- inverted index (.ski / .skq) and precluster
