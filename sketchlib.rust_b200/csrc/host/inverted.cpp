@@ -135,18 +135,24 @@ struct Unpacker {
         for (size_t i = 0; i < n; ++i) s.push_back((char)uint());
         return s;
     }
+    // every element / entry takes at least one byte: a declared length beyond the bytes left is corrupt (and must
+    // not reach a resize)
+    size_t bounded(size_t n, size_t min_bytes_each) const {
+        if (n > (size_t)(end - p) / min_bytes_each) bad("declared length exceeds the data");
+        return n;
+    }
     size_t array() {
         unsigned char t = (unsigned char)be(1);
-        if ((t & 0xf0) == 0x90) return t & 0x0f;
-        if (t == 0xdc) return be(2);
-        if (t == 0xdd) return be(4);
+        if ((t & 0xf0) == 0x90) return bounded(t & 0x0f, 1);
+        if (t == 0xdc) return bounded(be(2), 1);
+        if (t == 0xdd) return bounded(be(4), 1);
         bad("expected an array");
     }
     size_t map() {
         unsigned char t = (unsigned char)be(1);
-        if ((t & 0xf0) == 0x80) return t & 0x0f;
-        if (t == 0xde) return be(2);
-        if (t == 0xdf) return be(4);
+        if ((t & 0xf0) == 0x80) return bounded(t & 0x0f, 2);
+        if (t == 0xde) return bounded(be(2), 2);
+        if (t == 0xdf) return bounded(be(4), 2);
         bad("expected a map");
     }
 };
@@ -219,6 +225,7 @@ std::vector<uint32_t> roaring_deserialise(const std::string &s) {
         }
     } else if (cookie == kCookieNoRun) {
         n = rd(4);
+        if (n > (size_t)(end - p) / 4) throw std::runtime_error("invalid .ski: bitmap container count exceeds the data");
         is_run.assign(n, false);
     } else {
         throw std::runtime_error("invalid .ski: unknown bitmap cookie");
@@ -456,6 +463,11 @@ Inverted Inverted::deserialise(const std::string &buf) {
     inv.sample_names.resize(u.array());
     for (auto &s : inv.sample_names) s = u.str();
     if (n != inv.sample_names.size()) Unpacker::bad("n_samples does not match the sample names");
+    for (auto &bin : inv.index)
+        for (auto &kv : bin) {
+            if (!std::is_sorted(kv.second.begin(), kv.second.end())) Unpacker::bad("unsorted bitmap");
+            if (!kv.second.empty() && kv.second.back() >= n) Unpacker::bad("sample index beyond n_samples in a bitmap");
+        }
     for (auto *opt : {&inv.metadata, &inv.labels}) {
         if (u.try_nil()) continue;
         opt->emplace(u.array());

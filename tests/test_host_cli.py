@@ -550,3 +550,34 @@ def test_cli_inverted_precluster_unmatched_and_mismatched_inputs(tools, tmp_path
     assert run([cli, "inverted", "build", "-o", "three", "-k", "21", "-s", "4", "-f", "r3.txt", "--write-skq"], cwd=tmp_path).returncode == 0
     r = run([cli, "inverted", "precluster", "--skd", "standard", "three.ski"], cwd=tmp_path)
     assert r.returncode == 101 and "could not be found in the .ski" in r.stderr and names[3] in r.stderr
+
+
+def test_container_decoders_survive_corrupt_files(tools, tmp_path):
+    """Byte flips, truncations and insertions in a .ski (snappy frame + MessagePack + roaring) and a .skm (snappy frame +
+    CBOR): the C++ readers must reject or accept them cleanly -- no crash, no hang, no giant allocation from a
+    corrupted length field."""
+    import shutil
+    cli, skm_info = tools
+    rng = np.random.default_rng(0)
+    for name, cmd in (("inverted.ski", lambda p: [cli, "inverted", "precluster", "--count", p]),
+                      ("sketches3.skm", lambda p: [skm_info, p[:-4]])):
+        raw = bytearray(open(os.path.join(FIXTURES, name), "rb").read())
+        p = str(tmp_path / ("f" + os.path.splitext(name)[1]))
+        if name.endswith(".skm"):
+            shutil.copyfile(os.path.join(FIXTURES, "sketches3.skd"), p[:-4] + ".skd")
+        codes = set()
+        for it in range(150):
+            m = bytearray(raw)
+            if it % 3 == 0:
+                for _ in range(int(rng.integers(1, 4))):
+                    m[int(rng.integers(10, len(m)))] = int(rng.integers(0, 256))
+            elif it % 3 == 1:
+                m = m[: int(rng.integers(1, len(m)))]
+            else:
+                pos = int(rng.integers(10, len(m)))
+                m[pos:pos] = bytes(rng.integers(0, 256, size=int(rng.integers(1, 9))).tolist())
+            open(p, "wb").write(m)
+            r = subprocess.run(cmd(p), capture_output=True, timeout=20)
+            assert r.returncode in (0, 1, 2, 101), (name, it, r.returncode, r.stderr[-300:])
+            codes.add(r.returncode)
+        assert 1 in codes or 101 in codes     # most corruptions are detected
