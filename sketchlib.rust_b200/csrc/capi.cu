@@ -51,6 +51,7 @@ struct skd_ctx {
     size_t result_chunk_bytes = 64ull << 20;  // SKD_RESULT_CHUNK_MB: staged D2H chunk of dense results
     uint32_t group = 8;                       // SKD_GROUP: row blocks per L2 group of the tile scheduler
     size_t sym_chunk_bytes = 2ull << 30;      // SKD_SYM_CHUNK_MB: HBM key buffer of one symmetric-kNN row group
+    uint64_t few_queries = 1ull << 20;        // SKD_FEW_QUERIES: cross kNN up to this many queries goes dense keys + select
     size_t read_threads = 8;                  // SKD_READ_THREADS: host threads copying an .skd chunk into pinned staging
                                               // (default: the host's hardware threads, at most 16)
 };
@@ -511,11 +512,13 @@ skd_status run_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, bool self, 
     return timers_collect(ctx);
 }
 
-// Cross kNN with few queries: the row-owned kernel would have only a few row blocks (queries are its rows), so
-// instead the dense cross kernel (references as rows; narrow-column variant when <= 32 queries) writes the kNN
-// keys ref-major into HBM and select_few_kernel folds each query's column into per-slice lists, merged at the end.
+// Whole-range cross kNN (knn <= 64): the dense cross kernel (references as rows; stream kernel up to 16 queries,
+// narrow-column tile variants up to 32) writes the kNN keys ref-major into HBM, one chunk of references at a time, and
+// select_few_kernel folds each query's column into per-slice lists that are carried from chunk to chunk and merged at
+// the end.  With few queries the row-owned kernel would have only a few row blocks (queries are its rows); with many
+// it still loses 5 % to its in-kernel candidate lists.
 // E is oriented for the row-owned call (a = queries, b = refs).
-constexpr uint64_t kFewQueries = 512;
+
 skd_status finalize_lists(skd_ctx *ctx, const unsigned long long *dkeys, const float *daux, uint32_t n_parts,
                           uint64_t part_stride, uint64_t n_rows, uint64_t knn, int kind, uint64_t *idx_out, float *d0_out,
                           float *d1_out, skd_loc out_loc);
@@ -532,11 +535,11 @@ skd_status run_knn_few_queries(skd_ctx *ctx, const skd_db *R, const skd_db *Q, c
     rows_chunk = std::min<uint64_t>(rows_chunk, (n_ref + TS - 1) / TS * TS);
     const uint32_t n_chunks = (uint32_t)((n_ref + rows_chunk - 1) / rows_chunk);
     const uint32_t tgt_groups = (uint32_t)((nq + 7) / 8);  // select_few_kernel: 8 queries per CTA
-    uint32_t n_splits = (uint32_t)std::max<uint64_t>(1, (4ull * ctx->sm_count) / ((uint64_t)tgt_groups * n_chunks));
+    uint32_t n_splits = (uint32_t)std::max<uint64_t>(1, (4ull * ctx->sm_count) / (uint64_t)tgt_groups);
     // at most 16 row splits: few, long lists, since the final merge is O(parts^2) per query
     n_splits = std::max(1u, std::min<uint32_t>({n_splits, 16u, (uint32_t)(rows_chunk / TS)}));
     const uint32_t rows_per_split = (uint32_t)(((rows_chunk + n_splits - 1) / n_splits + TS - 1) / TS * TS);
-    const uint32_t parts = n_chunks * n_splits;
+    const uint32_t parts = n_splits;  // slice s of every chunk continues the lists of slice s of the chunk before
     const uint64_t part_stride = nq * knn;
     void *D, *pk, *pa = nullptr;
     skd_status st = scratch_get(ctx, "knn_rect", rows_chunk * nq * elt, &D);
@@ -564,9 +567,8 @@ skd_status run_knn_few_queries(skd_ctx *ctx, const skd_db *R, const skd_db *Q, c
         st = timer_begin(ctx);
         if (st) return st;
         CU(ctx, launch_select_few(with_aux, (const float *)D, nq, g0, (uint32_t)(g1 - g0), (uint32_t)nq,
-                                  (unsigned long long *)pk + (uint64_t)c * n_splits * part_stride,
-                                  with_aux ? (float *)pa + (uint64_t)c * n_splits * part_stride : nullptr, (uint32_t)knn,
-                                  ctx->compute, idx_offset, n_splits, rows_per_split, part_stride));
+                                  (unsigned long long *)pk, with_aux ? (float *)pa : nullptr, (uint32_t)knn, ctx->compute,
+                                  idx_offset, n_splits, rows_per_split, part_stride));
         ctx->launches++;
         st = timer_end(ctx);
         if (st) return st;
@@ -612,7 +614,7 @@ skd_status run_knn(skd_ctx *ctx, const skd_db *R, const skd_db *Q, bool self, co
     const uint64_t n_rows = row_end - row_begin;
     timers_reset(ctx);
     if (n_rows == 0) return SKD_OK;
-    if (!self && ctx->knn_symmetric && Q->n <= kFewQueries && knn <= kSymKnnMax && row_begin == 0 && row_end == Q->n)
+    if (!self && ctx->knn_symmetric && Q->n <= ctx->few_queries && knn <= kSymKnnMax && row_begin == 0 && row_end == Q->n)
         return run_knn_few_queries(ctx, R, Q, E, knn, idx_out, d0_out, d1_out, out_loc, key_out, aux_out, idx_offset);
     const bool with_aux = E.kind == KIND_CORE_ACC;
     const bool partial = key_out != nullptr;
@@ -1027,6 +1029,7 @@ skd_status skd_ctx_create(int device, skd_ctx **out) {
     if (const char *e = getenv("SKD_KNN_SYMMETRIC")) ctx->knn_symmetric = atoi(e) != 0;
     if (const char *e = getenv("SKD_SYM_CHUNK_MB")) ctx->sym_chunk_bytes = (size_t)std::max(1, atoi(e)) << 20;
     ctx->read_threads = std::min<size_t>(16, std::max<size_t>(1, std::thread::hardware_concurrency()));
+    if (const char *e = getenv("SKD_FEW_QUERIES")) ctx->few_queries = (uint64_t)std::max(0ll, atoll(e));
     if (const char *e = getenv("SKD_READ_THREADS")) ctx->read_threads = (size_t)std::max(1, atoi(e));
     if (const char *e = getenv("SKD_RESULT_CHUNK_MB")) ctx->result_chunk_bytes = (size_t)std::max(1, atoi(e)) << 20;
     for (int i = 0; i < 2; ++i) {

@@ -884,7 +884,8 @@ void launch_knn_merge(const unsigned long long *part_key, const float *part_aux,
 // Cross-mode selection over few target columns (queries).  D is a ref-major matrix of kNN keys (rows = references
 // g0 .., columns = the nq queries; float2 key/aux with AUX; ld >= nq): every row is a candidate of every column and
 // the stored neighbour index is row + idx_offset.  A CTA takes a group of 8 targets (blockIdx.y) and one slice of
-// rows_per_split rows (blockIdx.x; one list set per slice at Lkey + slice * part_stride); the rows of the slice are
+// rows_per_split rows (blockIdx.x; one list set per slice at Lkey + slice * part_stride, carried over from the same
+// slice of earlier reference chunks, so thresholds are tight from the second chunk on); the rows of the slice are
 // divided over the 8 warps, warp w keeps one list per target (list w * 8 + q), lanes take 32 consecutive rows at a
 // time, and the 8 lists of a target are merged at the end.  (Giving each target to one warp leaves one warp per CTA
 // busy when there is a single query: 2.3 ms instead of 0.3 ms per 500 000 references.)
@@ -917,7 +918,8 @@ __global__ void __launch_bounds__(256) select_few_kernel(const float *__restrict
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         cnt[q] = 0;
-        thr[q] = ~0ull;
+        // the slice's list from earlier reference chunks (~0 padded): nothing at or above its knn-th key can enter
+        thr[q] = q < (int)nq ? Lkey[(uint64_t)q * knn + knn - 1] : 0ull;
     }
     for (uint64_t r0 = w_lo; r0 < w_hi; r0 += 32) {
         const uint64_t row = r0 + lane;
@@ -953,24 +955,30 @@ __global__ void __launch_bounds__(256) select_few_kernel(const float *__restrict
                 for (int e = knn + lane; e < CAP; e += 32) list[e] = ~0ull;
                 __syncwarp();
                 cnt[q] = knn;
-                thr[q] = list[knn - 1];
+                thr[q] = list[knn - 1] < thr[q] ? list[knn - 1] : thr[q];
             }
         }
     }
 #pragma unroll
     for (int q = 0; q < 8; ++q)
-        if (q < (int)nq) warp_bitonic_sort(buf + (warp * 8 + q) * CAP, AUX ? baux + (warp * 8 + q) * CAP : nullptr, CAP, lane);
+        if (q < (int)nq && cnt[q] > 0)
+            warp_bitonic_sort(buf + (warp * 8 + q) * CAP, AUX ? baux + (warp * 8 + q) * CAP : nullptr, CAP, lane);
     __syncthreads();
-    // warp q merges the 8 lists of target q (each sorted, best knn <= 64 first) into list q of warp 0
+    // warp q merges the stored list of target q and the 8 warp lists (each sorted, best knn <= 64 first)
     if (warp < (int)nq) {
         const int q = warp;
-        unsigned long long *acc = buf + q * CAP;
+        unsigned long long *acc = buf + q * CAP;  // warp 0's list of this target doubles as the accumulator
         float *acc_a = AUX ? baux + q * CAP : nullptr;
-        for (int w = 1; w < 8; ++w) {
-            const unsigned long long *src = buf + (w * 8 + q) * CAP;
+        bool any = false;
+        for (int w = 0; w < 8; ++w) any |= buf[(w * 8 + q) * CAP] != ~0ull;
+        if (!any) return;  // no candidate of this chunk beat the threshold: the stored list stands
+        for (int w = 0; w < 8; ++w) {
+            const unsigned long long *src = w == 0 ? Lkey + (uint64_t)q * knn : buf + (w * 8 + q) * CAP;
+            const float *src_a = !AUX ? nullptr : (w == 0 ? Laux + (uint64_t)q * knn : baux + (w * 8 + q) * CAP);
+            if (src[0] == ~0ull) continue;  // empty
             for (int e = lane; e < CAP - (int)knn; e += 32) {
                 acc[knn + e] = e < (int)knn ? src[e] : ~0ull;
-                if (AUX) acc_a[knn + e] = e < (int)knn ? baux[(w * 8 + q) * CAP + e] : 0.f;
+                if (AUX) acc_a[knn + e] = e < (int)knn ? src_a[e] : 0.f;
             }
             __syncwarp();
             warp_bitonic_sort(acc, acc_a, CAP, lane);

@@ -578,9 +578,12 @@ def test_cross_with_few_queries(sk, ctx, nq):
     assert_knn_matches(gotc.idx, gotc.d0, gotc.d1, oidx, od0, od1, False)
 
 
-@pytest.mark.parametrize("n_ref,nq,knn", [(900, 40, 25), (20000, 3, 64), (5000, 8, 1), (3000, 1, 50)])
+@pytest.mark.parametrize("n_ref,nq,knn", [(900, 40, 25), (20000, 3, 64), (5000, 8, 1), (3000, 1, 50), (6000, 70, 25),
+                                          (3000, 600, 10)])
 def test_few_queries_knn_equals_row_owned_path(sk, ctx, n_ref, nq, knn):
-    """nq <= 8 runs the streaming kernel + select_few_kernel, larger nq the narrow tile variants + select_kernel."""
+    """Whole-range cross kNN (knn <= 64) = dense keys in HBM + select_few_kernel (stream kernel up to 16 queries, tile
+    kernel above) against the row-owned kernel; the 1 MB key buffer of the `tiny` context cuts the last two cases into
+    4 and 14 reference chunks whose lists continue from chunk to chunk."""
     ref, qry = synth_pair(n_ref, nq, 16, [17, 21, 25, 29], seed=91, n_families=12)
     plain = fresh_ctx(sk, SKD_KNN_SYMMETRIC=0)  # also disables the few-queries route
     tiny = fresh_ctx(sk, SKD_SYM_CHUNK_MB=1)    # several reference chunks and row slices
