@@ -17,7 +17,8 @@
  *   - "loc" arguments say where a caller buffer lives: SKD_HOST (pageable or pinned host memory)
  *     or SKD_DEVICE (memory of the context's GPU);
  *   - one context per GPU per process (one process per GPU for multi-GPU runs; rows are sharded by
- *     the row/ref/query ranges every compute call takes); a context is not thread-safe.
+ *     the row/ref/query ranges every compute call takes); a context is not thread-safe, but a thread may
+ *     create a second context on the same GPU (a loader filling the next shard: skd_db_adopt).
  *   - there is no CPU fallback: without a CUDA device skd_ctx_create fails.
  */
 #ifndef SKETCHDIST_H
