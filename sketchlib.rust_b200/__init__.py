@@ -541,3 +541,8 @@ def match_counts(ref_sketches, query_sketches, pairs=None, rows=None):
     ctx._check(ctx.lib.skd_match_counts_dense(ctx.handle, ref_sketches.handle, query_sketches.handle, r0, r1,
                                               _ptr(out)))
     return out
+
+
+# host-side mirrors of the reference's file-level types (.skm / .skd / .ski / .skq), bound to the C++ readers
+from .host import (HostError, Inverted, MultiSketch, precluster_from_files, read_completeness_file,  # noqa: E402,F401
+                   read_subset_names)

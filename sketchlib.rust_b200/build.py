@@ -43,9 +43,25 @@ HOST = os.path.join(CSRC, "host")
 HOST_FLAGS = ["-O2", "-std=c++17", "-Wall", "-Wextra", "-ffp-contract=off"]
 
 
+HOSTLIB = os.path.join(HERE, "lib", "libsketchhost.so")
+
+
+def build_hostlib(force=False):
+    """Host-only shared library over the C++ readers (.skm / .ski / completeness files) for the Python layer."""
+    srcs = ["host_capi.cpp", "multisketch.cpp", "inverted.cpp", "sketcher.cpp"]
+    deps = [os.path.join(HOST, f) for f in srcs + ["multisketch.hpp", "inverted.hpp"]]
+    newest = max(os.path.getmtime(d) for d in deps)
+    if force or not os.path.exists(HOSTLIB) or os.path.getmtime(HOSTLIB) < newest:
+        os.makedirs(os.path.dirname(HOSTLIB), exist_ok=True)
+        subprocess.check_call(["g++"] + HOST_FLAGS + ["-shared", "-fPIC", "-o", HOSTLIB] + srcs + ["-lz", "-lpthread"], cwd=HOST)
+    return HOSTLIB
+
+
 def build_host(force=False):
-    """Host-only C++: the drop-in `sketchlib dist` CLI (links libsketchdist.so) and the skm_info test tool."""
+    """Host-only C++: the drop-in `sketchlib dist` CLI (links libsketchdist.so), the skm_info test tool and
+    libsketchhost.so."""
     os.makedirs(BIN, exist_ok=True)
+    build_hostlib(force)
     cli, info = os.path.join(BIN, "sketchlib"), os.path.join(BIN, "skm_info")
     srcs = [os.path.join(HOST, f) for f in ("dist_main.cpp", "multisketch.cpp", "multisketch.hpp", "skm_info.cpp",
                                             "sketcher.cpp", "inverted.cpp", "inverted.hpp")]

@@ -733,3 +733,25 @@ def test_async_upload_overlapped_dense_and_other_calls(sk, ctx):
     g = sk.SketchDb.upload(ctx, db.bins, db.n, db.kmers, db.W, async_upload=True)
     assert np.array_equal(sk.self_dists_all(g, dist_type=sk.set_k(g), pinned=False).distances, want)
     pin.free()
+
+
+def test_python_file_level_api_reproduces_goldens(sk, ctx, tmp_path):
+    """The reference's flow in Python: MultiSketch.load_metadata -> read_sketch_data[_block] -> distances -> Display,
+    and Inverted.load -> precluster, on files, against the reference's golden stdout files."""
+    from helpers import write_skm_skd
+    prefix = write_skm_skd(str(tmp_path / "db"), load_json_db("s10048"))
+    ms = sk.MultiSketch.load_metadata(prefix + ".skm")
+    g = ms.read_sketch_data(ctx)
+    assert g.names == ms.names() and g.number_samples_loaded() == 4
+    assert str(sk.self_dists_knn(g, knn=1, dist_type=sk.set_k(g))) == golden("dists_knn_ca")
+    assert str(sk.self_dists_knn(g, knn=1, dist_type=sk.set_k(g, 21))) == golden("dists_knn_jaccard")
+    sub = sk.MultiSketch(prefix)
+    gs = sub.read_sketch_data_block(ctx, sk.read_subset_names(os.path.join(FIXTURES, "subset.txt")))
+    assert str(sk.self_dists_all(gs, dist_type=sk.set_k(gs))) == golden("dists_subset")
+    for ski in ("inverted", "reordered_inv"):
+        for ani, gold in ((False, "inverted_precluster"), (True, "inverted_precluster_ani")):
+            got = sk.precluster_from_files(ctx, os.path.join(FIXTURES, ski + ".ski"), os.path.join(FIXTURES, "sketches3"),
+                                           knn=1, ani=ani)
+            assert sorted(str(got).splitlines()) == sorted(golden(gold).splitlines())
+    with pytest.raises(sk.HostError, match="could not find|Could not find"):
+        sk.MultiSketch(prefix).read_sketch_data_block(ctx, ["not_a_sample"])

@@ -136,3 +136,46 @@ def test_bench_workload_sizes():
     for g in (2, 4, 8):
         n = bench.n_for_gpus(g)
         assert n % 64 == 0 and abs(n * (n - 1) / 2 / g - 49995000) / 49995000 < 0.02
+
+
+def test_python_multisketch_and_inverted_mirror_the_reference_types(tmp_path):
+    """sketchlib.rust_b200.MultiSketch / Inverted (libsketchhost.so: the CLI's C++ readers behind ctypes) against the
+    oracle's independent Python reader on the reference's fixtures: metadata, legacy fix-up, subset order, completeness
+    files, index queries.  No GPU involved."""
+    import oracle
+    import sketchlib.rust_b200 as sk
+    from helpers import FIXTURES
+    for name in ("sketches1", "sketches2", "sketches3", "legacy_db"):
+        ms = sk.MultiSketch.load_metadata(os.path.join(FIXTURES, name + ".skm"))
+        want = oracle.MultiSketch(os.path.join(FIXTURES, name))
+        assert ms.kmer_lengths == list(want.kmer_lengths) and ms.sketch_size == want.sketch_size
+        assert (ms.sketchsize64, ms.sample_stride, ms.kmer_stride) == (want.sketchsize64, want.sample_stride, want.kmer_stride)
+        assert ms.names() == want.names() and ms.number_samples_loaded() == len(want.names())
+        assert ms.file_indices().tolist() == [m["index"] for m in want.sketch_metadata]
+        assert ms.hash_type == "DNA" and ms.get_k_idx(ms.kmer_lengths[-1]) == len(ms.kmer_lengths) - 1 and ms.get_k_idx(4) is None
+    # --subset: loaded order = list order (read_sketch_data_block), unknown names are the reference's panic
+    ms = sk.MultiSketch(os.path.join(FIXTURES, "sketches3"))
+    names = sk.read_subset_names(os.path.join(FIXTURES, "subset.txt"))
+    ms.select_subset(names)
+    assert ms.names() == names and ms.number_samples_loaded() == len(names)
+    all_names = sk.MultiSketch(os.path.join(FIXTURES, "sketches3")).names()
+    assert ms.file_indices().tolist() == [all_names.index(n) for n in names]
+    with pytest.raises(sk.HostError, match="Could not find requested sample"):
+        ms.select_subset(["nope"])
+    with pytest.raises(sk.HostError):
+        sk.MultiSketch(str(tmp_path / "missing"))
+    # completeness file of the reference's tests: values by sample name, default 1.0 with a warning
+    full = sk.MultiSketch(os.path.join(FIXTURES, "sketches3"))
+    vals, warns = sk.read_completeness_file(os.path.join(FIXTURES, "completeness.txt"), full)
+    listed = dict(l.split("\t") for l in open(os.path.join(FIXTURES, "completeness.txt")).read().splitlines() if "\t" in l)
+    assert [v for v in vals] == [float(listed.get(n, 1.0)) for n in full.names()]
+    # .ski: candidates and match counts equal the definition on the .skq bins
+    inv = sk.Inverted.load(os.path.join(FIXTURES, "reordered_inv.ski"))
+    skq = inv.read_skq()
+    assert (inv.n, inv.stride, inv.kmer, inv.rc) == (4, 10, 21, True)
+    assert inv.sample_names == ["TIGR4.fa.gz", "R6.fa.gz", "14412_3#82.contigs_velvet.fa.gz", "14412_3#84.contigs_velvet.fa.gz"]
+    for s in range(4):
+        counts = (skq == skq[s][None, :]).sum(axis=1)
+        assert inv.query_against_inverted_index(skq[s]).tolist() == counts.tolist()
+        assert inv.any_shared_bins(skq[s]).tolist() == np.flatnonzero(counts > 0).tolist()
+    assert inv.any_shared_bin_pairs() == 2
