@@ -159,7 +159,7 @@ DistArgs parse_args(int argc, char **argv) {
         } else if (!saw_dist) {
             if (t != "dist")
                 throw UsageError("unrecognized subcommand '" + t +
-                                 "': this build implements only `dist`, `inverted` (the B200-accelerated paths) and `sketch` (DNA)");
+                                 "': this build implements only `dist`, `inverted` (the B200-accelerated paths), `sketch` (DNA) and `info`");
             saw_dist = true;
         } else {
             pos.push_back(t);
@@ -706,10 +706,20 @@ InputList get_input_list(const std::string &file_list, const std::vector<std::st
             if (f.size() == 1) inputs.push_back({f[0], {f[0]}});
             else inputs.push_back({f[0], std::vector<std::string>(f.begin() + 1, f.end())});
         }
-    } else {  // name = file name without directories
+    } else {
+        // read_input_fastas (src/io.rs:20-38): the file name without directories when the extension is one of
+        // fa, fasta, fastq, fq (optionally .gz); any other argument names its sample by the whole string
+        auto known_ext = [](const std::string &f) {
+            for (const char *e : {".fa", ".fasta", ".fa.gz", ".fasta.gz", ".fastq", ".fastq.gz", ".fq", ".fq.gz"}) {
+                const size_t n = strlen(e);
+                if (f.size() > n && f.compare(f.size() - n, n, e) == 0) return true;
+            }
+            return false;
+        };
         for (auto &file : seq_files) {
             size_t slash = file.rfind('/');
-            inputs.push_back({slash == std::string::npos ? file : file.substr(slash + 1), {file}});
+            const bool base = known_ext(file) && slash != std::string::npos && slash > 0 && slash + 1 < file.size();
+            inputs.push_back({base ? file.substr(slash + 1) : file, {file}});
         }
     }
     return inputs;
@@ -1153,19 +1163,87 @@ int run_inverted(int argc, char **argv) {
     return inverted_precluster(a);
 }
 
+
+// ---- `sketchlib info <db|.skm|.ski> [--sample-info]`: src/lib.rs:910-947 (Debug / Display of MultiSketch and Inverted)
+int run_info(int argc, char **argv) {
+    std::string file;
+    bool sample_info = false, verbose = false, quiet = false;
+    int words = 0;
+    for (int i = 1; i < argc; ++i) {
+        std::string t = argv[i];
+        if (t == "--sample-info") sample_info = true;
+        else if (t == "-v" || t == "--verbose") verbose = true;
+        else if (t == "--quiet") quiet = true;
+        else if (t.size() > 1 && t[0] == '-') throw UsageError("unexpected argument '" + t + "' found");
+        else if (words++ == 0) continue;  // "info"
+        else if (file.empty()) file = t;
+        else throw UsageError("unexpected argument '" + t + "' found");
+    }
+    g_level = quiet ? 0 : (verbose ? 2 : 1);
+    if (file.empty()) throw UsageError("the following required arguments were not provided:\n  <SKM_FILE>");
+    auto ends_with = [&](const char *e) { return file.size() >= 4 && file.compare(file.size() - 4, 4, e) == 0; };
+    if (ends_with(".ski")) {
+        const std::string prefix = file.substr(0, file.size() - 4);
+        Inverted inv;
+        try {
+            inv = Inverted::load(prefix);
+        } catch (const std::exception &e) {
+            printf("Read error: %s\n", e.what());
+            throw Panic("Could not read inverted index from " + prefix + ".ski");
+        }
+        if (sample_info) {
+            log_info("Printing sample info");
+            std::string text = "Name\n";
+            for (auto &n : inv.sample_names) text += n + "\n";
+            printf("%s\n", text.c_str());
+        } else {
+            log_info("Printing inverted index info");
+            printf("%s\n", inv.debug_info().c_str());
+        }
+        return 0;
+    }
+    const std::string prefix = (ends_with(".skm") || ends_with(".skd")) ? file.substr(0, file.size() - 4) : file;
+    MultiSketch m;
+    try {
+        m = MultiSketch::load_metadata(prefix);
+    } catch (const std::exception &) {
+        throw Panic("Could not read sketch metadata from " + prefix + ".skm");
+    }
+    if (sample_info) {
+        log_info("Printing sample info");
+        std::string text = "Name\tSequence length\tBase frequencies\tMissing/ambig bases\tFrom reads\tSingle strand\tDensified\n";
+        for (auto &s : m.sketch_metadata)  // impl Display for Sketch, src/sketch/mod.rs:261-277 (A, C, G, T order)
+            text += s.name + "\t" + std::to_string(s.seq_length) + "\t[" + std::to_string(s.acgt[0]) + ", " +
+                    std::to_string(s.acgt[1]) + ", " + std::to_string(s.acgt[3]) + ", " + std::to_string(s.acgt[2]) + "]\t" +
+                    std::to_string(s.non_acgt) + "\t" + (s.reads ? "true" : "false") + "\t" + (!s.rc ? "true" : "false") +
+                    "\t" + (s.densified ? "true" : "false") + "\n";
+        printf("%s\n", text.c_str());
+    } else {
+        log_info("Printing database info");
+        std::string kmers;
+        for (size_t i = 0; i < m.kmer_lengths.size(); ++i) kmers += (i ? ", " : "") + std::to_string(m.kmer_lengths[i]);
+        printf("sketch_version=%s\nsequence_type=%s\nsketch_size=%llu\nn_samples=%zu\nkmers=[%s]\ninverted=false\n",
+               m.sketch_version.c_str(), m.hash_type.c_str(), (unsigned long long)m.sketch_size, m.sketch_metadata.size(),
+               kmers.c_str());
+    }
+    return 0;
+}
+
 int main(int argc, char **argv) {
     auto start = std::chrono::steady_clock::now();
-    bool is_sketch = false, is_inverted = false;
+    bool is_sketch = false, is_inverted = false, is_info = false;
     for (int i = 1; i < argc; ++i) {
         if (argv[i][0] == '-') continue;
         is_sketch = std::string(argv[i]) == "sketch";
         is_inverted = std::string(argv[i]) == "inverted";
+        is_info = std::string(argv[i]) == "info";
         break;
     }
-    if (is_sketch || is_inverted) {
+    if (is_sketch || is_inverted || is_info) {
         try {
             if (is_sketch) run_sketch(argc, argv);
-            else run_inverted(argc, argv);
+            else if (is_inverted) run_inverted(argc, argv);
+            else run_info(argc, argv);
         } catch (const UsageError &e) {
             fprintf(stderr, "error: %s\n", e.what());
             return 2;
@@ -1176,7 +1254,7 @@ int main(int argc, char **argv) {
             fprintf(stderr, "Error: %s\n", e.what());
             return 1;
         }
-        if (g_level >= 1) {
+        if (g_level >= 1 && !is_info) {  // info turns the final message off (src/lib.rs:945)
             auto secs = std::chrono::duration_cast<std::chrono::seconds>(std::chrono::steady_clock::now() - start).count();
             fprintf(stderr, "\xF0\x9F\xA7\xAC\xF0\x9F\x96\x8B\xEF\xB8\x8F sketchlib done in %llds\n", (long long)secs);
         }

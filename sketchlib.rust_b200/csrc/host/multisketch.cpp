@@ -266,6 +266,9 @@ MultiSketch MultiSketch::load_metadata(const std::string &file_prefix) {
         if (const CborValue *v = e->get("reads")) s.reads = v->b;
         if (const CborValue *v = e->get("densified")) s.densified = v->b;
         if (const CborValue *v = e->get("seq_length")) s.seq_length = v->u;
+        if (const CborValue *v = e->get("non_acgt")) s.non_acgt = v->u;
+        if (const CborValue *v = e->get("acgt"); v && v->kind == CborValue::ARRAY)
+            for (size_t b = 0; b < 4 && b < v->arr.size(); ++b) s.acgt[b] = v->arr[b]->u;
         m.sketch_metadata.push_back(std::move(s));
     }
     if (const CborValue *nmap = root->get("name_map"); nmap && nmap->kind == CborValue::MAP) {

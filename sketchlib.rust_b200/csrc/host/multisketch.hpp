@@ -38,6 +38,8 @@ struct SketchMeta {  // src/sketch/mod.rs:57-70 (serialised fields of Sketch)
     uint64_t index = 0;
     bool rc = true, reads = false, densified = false;
     uint64_t seq_length = 0;
+    uint64_t acgt[4] = {0, 0, 0, 0};  // indexed by (ascii >> 1) & 3: A, C, T, G
+    uint64_t non_acgt = 0;
 };
 
 class MultiSketch {

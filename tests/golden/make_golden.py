@@ -40,7 +40,9 @@ def main():
     for f in ("subset.txt", "rfile.txt", "completeness.txt"):
         shutil.copyfile(os.path.join(IN, f), os.path.join(fx, f))
     for f in ("dists_knn_ca", "dists_knn_jaccard", "dists_knn_ani", "dists_subset", "inverted_precluster",
-              "inverted_precluster_ani", "inverted_query_count", "inverted_query_any", "inverted_query_all"):
+              "inverted_precluster_ani", "inverted_query_count", "inverted_query_any", "inverted_query_all",
+              "assembly_sketch_info", "assembly_sketch_full_info", "inverted_sketch_info", "inverted_sketch_full_info",
+              "inverted_sketch_info_reorder"):
         shutil.copyfile(os.path.join(OUT, f + ".stdout"), os.path.join(fx, f + ".stdout"))
     shutil.copyfile(os.path.join(OUT, "inverted.skq"), os.path.join(fx, "inverted.skq"))  # 4 samples x 10 u16 bins
 

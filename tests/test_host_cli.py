@@ -581,3 +581,51 @@ def test_container_decoders_survive_corrupt_files(tools, tmp_path):
             assert r.returncode in (0, 1, 2, 101), (name, it, r.returncode, r.stderr[-300:])
             codes.add(r.returncode)
         assert 1 in codes or 101 in codes     # most corruptions are detected
+
+
+def _matches_snapbox(got, want):
+    """snapbox `[..]` matches any run of characters inside a line."""
+    import re
+    g, w = got.splitlines(), want.splitlines()
+    return len(g) == len(w) and all(re.fullmatch(".*".join(re.escape(p) for p in wl.split("[..]")), gl) for gl, wl in zip(g, w))
+
+
+def test_info_goldens_pin_sketch_metadata_and_index_statistics(tools, tmp_path):
+    """`sketchlib info` (src/lib.rs:910-947) on databases made by this build's `sketch` / `inverted build` from the
+    reference's genomes, against the reference's golden stdout files (tests/sketch.rs:10-44, tests/inverted.rs:14-50,
+    131-166): sequence lengths, base counts, ambiguous bases, strand / read flags, and the index's hashes-per-bin
+    statistics over 1000 bins."""
+    ref_in = "/root/reference/tests/test_files_in"
+    if not os.path.exists(os.path.join(ref_in, "rfile.txt")):
+        pytest.skip("reference checkout not present (GPU box)")
+    cli, _ = tools
+    g82, g84 = (os.path.join(ref_in, f) for f in ("14412_3#82.contigs_velvet.fa.gz", "14412_3#84.contigs_velvet.fa.gz"))
+    out = str(tmp_path / "assembly")
+    assert run([cli, "sketch", "-o", out, "-v", "-k", "31", g82, g84]).returncode == 0
+    r = run([cli, "info", out])
+    assert r.returncode == 0 and _matches_snapbox(r.stdout, golden("assembly_sketch_info")), r.stdout
+    r = run([cli, "info", "--sample-info", out, "-v"])
+    assert _matches_snapbox(r.stdout, golden("assembly_sketch_full_info")), r.stdout
+    assert "done in" not in r.stderr                                     # info turns the final message off
+    inv = str(tmp_path / "inverted")
+    assert run([cli, "inverted", "build", "-o", inv, "-v", "-k", "31", g82, g84]).returncode == 0
+    r = run([cli, "info", inv + ".ski", "-v"])
+    assert _matches_snapbox(r.stdout, golden("inverted_sketch_info")), r.stdout
+    r = run([cli, "info", "--sample-info", inv + ".ski", "-v"])
+    assert _matches_snapbox(r.stdout, golden("inverted_sketch_full_info")), r.stdout
+    files = [g82, g84, os.path.join(ref_in, "R6.fa.gz"), os.path.join(ref_in, "TIGR4.fa.gz")]
+    assert run([cli, "inverted", "build", "-o", inv, "-k", "61", "-s", "63", "--species-names",
+                os.path.join(ref_in, "species_names.txt")] + files).returncode == 0
+    r = run([cli, "info", inv + ".ski", "--sample-info", "-v"])
+    assert _matches_snapbox(r.stdout, golden("inverted_sketch_info_reorder")), r.stdout
+    # sample names of positional inputs (read_input_fastas, src/io.rs:20-38): basename for FASTA/FASTQ extensions,
+    # the whole argument otherwise
+    import shutil, gzip
+    odd = tmp_path / "genome.fna"
+    with gzip.open(g82, "rb") as fh:
+        odd.write_bytes(fh.read())
+    assert run([cli, "sketch", "-o", out + "2", "-k", "21", str(odd), g84, "--quiet"]).returncode == 0
+    names = [l.split("\t")[0] for l in run([cli, "info", "--sample-info", out + "2"]).stdout.splitlines()[1:3]]
+    assert names == [str(odd), "14412_3#84.contigs_velvet.fa.gz"]
+    assert run([cli, "info", str(tmp_path / "missing")]).returncode == 101
+    assert run([cli, "info"]).returncode == 2
