@@ -340,6 +340,12 @@ class DistanceMatrix:
                 d += 1
         return "".join(out)
 
+    def write(self, path, threads=1, append=False):
+        """The same text as str(self), formatted by `threads` host threads in C++ (large matrices)."""
+        from . import host
+        host.write_dense(path, self.ref_names, self.query_names, self.distances, self.dist_type.n_dist_cols, self.row_range,
+                         threads, append)
+
 
 class SparseDistanceMatrix:
     """kNN rows: src/distances/distance_matrix.rs:285-401."""
@@ -361,6 +367,13 @@ class SparseDistanceMatrix:
                 elif self.d0[r, t] < 1.0 or cn != rn:  # padding entries skipped, :376-381
                     out.append(f"{rn}\t{cn}\t{fmt_f32(self.d0[r, t])}\n")
         return "".join(out)
+
+    def write(self, path, threads=1, append=False):
+        """The same text as str(self), formatted in C++."""
+        from . import host
+        rows = self.query_names if self.query_names is not None else self.ref_names
+        host.write_sparse(path, rows, self.ref_names, self.row_range[0], self.idx, self.d0,
+                          self.d1 if self.dist_type.kind == CORE_ACC else None, threads, append)
 
 
 # ---- multi-GPU partitioning (one process per GPU; no data-path collective) ---------------------------

@@ -401,9 +401,36 @@ std::vector<double> read_completeness_file(const std::string &file, const MultiS
 }
 
 std::string fmt_f32(float v) {
-    char buf[128];
-    auto r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::fixed);  // shortest round-trip, no exponent
-    return std::string(buf, r.ptr);
+    // Rust's `{}`: the shortest digits that round-trip, written positionally (zeros pad a large or a small exponent).
+    // to_chars(fixed) alone would print the exact integer digits of large values (3.4e38 -> 339999995214...).
+    if (std::isnan(v)) return "NaN";
+    if (std::isinf(v)) return v < 0 ? "-inf" : "inf";
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::scientific);  // d[.ddd]e[+-]xx, shortest
+    std::string sci(buf, r.ptr), out;
+    size_t pos = 0;
+    if (sci[0] == '-') {
+        out = "-";
+        pos = 1;
+    }
+    const size_t e = sci.find('e');
+    std::string digits;
+    for (size_t i = pos; i < e; ++i)
+        if (sci[i] != '.') digits.push_back(sci[i]);
+    const int exp10 = atoi(sci.c_str() + e + 1);  // value = d.ddd * 10^exp10
+    if (digits == "0") return out + "0";
+    const int point = exp10 + 1;  // digits before the decimal point
+    if (point <= 0) {
+        out += "0.";
+        out.append((size_t)(-point), '0');
+        out += digits;
+    } else if ((size_t)point >= digits.size()) {
+        out += digits;
+        out.append((size_t)point - digits.size(), '0');
+    } else {
+        out += digits.substr(0, (size_t)point) + "." + digits.substr((size_t)point);
+    }
+    return out;
 }
 
 }  // namespace skdhost

@@ -47,6 +47,10 @@ def load_library():
             "skh_ski_any_shared_bins": (u64, [vp, vp, vp, u64]),
             "skh_ski_match_counts": (None, [vp, vp, vp]),
             "skh_ski_any_shared_bin_pairs": (u64, [vp]),
+            "skh_write_dense": (C.c_int, [cp, C.c_int, C.POINTER(cp), u64, C.POINTER(cp), u64, vp, C.c_int, u64, u64, C.c_int,
+                                          cp, C.c_size_t]),
+            "skh_write_sparse": (C.c_int, [cp, C.c_int, C.POINTER(cp), C.POINTER(cp), u64, u64, u64, vp, vp, vp, C.c_int, cp,
+                                           C.c_size_t]),
         }
         for name, (res, args) in sigs.items():
             fn = getattr(lib, name)
@@ -218,3 +222,29 @@ def precluster_from_files(ctx, ski_prefix, skd_prefix, knn, ani=False, retain_un
     if ref_completeness_file:
         comp, _ = read_completeness_file(ref_completeness_file, refs)
     return sk.self_dists_knn_precluster(db, skq, inv.sample_names, knn, dt, retain_unmatched, comp, completeness_cutoff)
+
+
+def _names(names):
+    return (C.c_char_p * len(names))(*[n.encode() for n in names])
+
+
+def write_dense(path, ref_names, query_names, distances, ncols, row_range, threads=1, append=False):
+    """Display of DistanceMatrix (distance_matrix.rs:175-209) written to `path` by `threads` host threads."""
+    lib = load_library()
+    d = np.ascontiguousarray(distances, dtype=np.float32)
+    q = None if query_names is None else _names(query_names)
+    _call(lib.skh_write_dense, os.fsencode(path), int(append), _names(ref_names), len(ref_names), q,
+          0 if query_names is None else len(query_names), d.ctypes.data_as(C.c_void_p), int(ncols), int(row_range[0]),
+          int(row_range[1]), int(threads))
+
+
+def write_sparse(path, row_names, col_names, row_begin, idx, d0, d1, threads=1, append=False):
+    """Display of SparseDistanceMatrix (distance_matrix.rs:360-401) written to `path`."""
+    lib = load_library()
+    idx = np.ascontiguousarray(idx, dtype=np.uint64)
+    d0 = np.ascontiguousarray(d0, dtype=np.float32)
+    d1 = None if d1 is None else np.ascontiguousarray(d1, dtype=np.float32)
+    n_rows, knn = idx.shape
+    _call(lib.skh_write_sparse, os.fsencode(path), int(append), _names(row_names), _names(col_names), int(row_begin), n_rows,
+          knn, idx.ctypes.data_as(C.c_void_p), d0.ctypes.data_as(C.c_void_p),
+          None if d1 is None else d1.ctypes.data_as(C.c_void_p), int(threads))

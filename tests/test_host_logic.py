@@ -179,3 +179,41 @@ def test_python_multisketch_and_inverted_mirror_the_reference_types(tmp_path):
         assert inv.query_against_inverted_index(skq[s]).tolist() == counts.tolist()
         assert inv.any_shared_bins(skq[s]).tolist() == np.flatnonzero(counts > 0).tolist()
     assert inv.any_shared_bin_pairs() == 2
+
+
+def test_matrix_writers_match_python_display(tmp_path):
+    """DistanceMatrix.write / SparseDistanceMatrix.write (C++, threaded) produce exactly str(matrix): self / cross / row
+    shards, one and two columns, sparse rows with padding entries, tricky floats."""
+    import sketchlib.rust_b200 as sk
+    rng = np.random.default_rng(3)
+    n, nq = 77, 5
+    names, qnames = [f"s{i}#x" for i in range(n)], [f"q{i}" for i in range(nq)]
+    tricky = np.array([0.0, 1.0, 1e-7, 0.1, 1 / 3, 0.008820182, 123456.7, 3.4e38, 1e-45, 0.99999994], dtype=np.float32)
+    for ncols, kind in ((2, sk.CORE_ACC), (1, sk.JACCARD)):
+        dt = sk.DistType(kind, 0)
+        for r0, r1 in ((0, n), (13, 50), (76, 77)):
+            cnt = sum(n - 1 - i for i in range(r0, r1))
+            d = rng.random(cnt * ncols).astype(np.float32)
+            d[: min(d.size, tricky.size)] = tricky[: min(d.size, tricky.size)]
+            m = sk.DistanceMatrix(names, None, dt, d, (r0, r1))
+            m.write(str(tmp_path / "a.tsv"), threads=3)
+            assert open(tmp_path / "a.tsv").read() == str(m)
+        d = rng.random((40 - 7) * nq * ncols).astype(np.float32)
+        m = sk.DistanceMatrix(names, qnames, dt, d, (7, 40))
+        m.write(str(tmp_path / "b.tsv"), threads=2)
+        assert open(tmp_path / "b.tsv").read() == str(m)
+        m.write(str(tmp_path / "b.tsv"), append=True)
+        assert open(tmp_path / "b.tsv").read() == str(m) * 2
+        knn = 4
+        idx = rng.integers(0, n, size=(30, knn)).astype(np.uint64)
+        d0 = rng.random((30, knn)).astype(np.float32)
+        idx[3, 2:], d0[3, 2:] = 10 + 3, 1.0          # padding entries of row 3 (its own index, distance 1)
+        d1 = rng.random((30, knn)).astype(np.float32) if ncols == 2 else None
+        sp = sk.SparseDistanceMatrix(names, None, dt, knn, idx, d0, d1, (10, 40))
+        sp.write(str(tmp_path / "c.tsv"), threads=4)
+        assert open(tmp_path / "c.tsv").read() == str(sp)
+        spx = sk.SparseDistanceMatrix(names, qnames, dt, knn, idx[:5], d0[:5], None if d1 is None else d1[:5], (0, 5))
+        spx.write(str(tmp_path / "d.tsv"))
+        assert open(tmp_path / "d.tsv").read() == str(spx)
+    with pytest.raises(sk.HostError):
+        sp.write(str(tmp_path / "no_such_dir" / "x.tsv"))
