@@ -453,7 +453,11 @@ skd_status run_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, bool self, 
             }
             for (size_t c = 0; c < nc; ++c) {
                 cudaStream_t band = (c & 1) ? ctx->aux[1] : ctx->compute;
-                cudaStreamWaitEvent(band, retiled[c], 0);
+                if (cudaError_t e = cudaStreamWaitEvent(band, retiled[c], 0); e != cudaSuccess) {
+                    cudaDeviceSynchronize();
+                    drop_events();
+                    return fail(ctx, SKD_ERR_CUDA, "cudaStreamWaitEvent failed: %s", cudaGetErrorString(e));
+                }
                 if (offs[c].empty() || offs[c].back() == 0) continue;
                 const uint32_t b0 = c ? pa->pending.block_end[c - 1] : 0, b1 = pa->pending.block_end[c];
                 const uint64_t r1 = std::min<uint64_t>(row_end, (uint64_t)b1 * TS);
@@ -466,8 +470,13 @@ skd_status run_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, bool self, 
                 }
             }
             for (int i = 0; i < 2; ++i) {  // join: the compute stream continues after both helpers
-                cudaEventRecord(ctx->ev_b[i], ctx->aux[i]);
-                cudaStreamWaitEvent(ctx->compute, ctx->ev_b[i], 0);
+                cudaError_t e = cudaEventRecord(ctx->ev_b[i], ctx->aux[i]);
+                if (e == cudaSuccess) e = cudaStreamWaitEvent(ctx->compute, ctx->ev_b[i], 0);
+                if (e != cudaSuccess) {
+                    cudaDeviceSynchronize();
+                    drop_events();
+                    return fail(ctx, SKD_ERR_CUDA, "joining the band streams failed: %s", cudaGetErrorString(e));
+                }
             }
             CU(ctx, cudaStreamSynchronize(ctx->compute));
             drop_events();
@@ -934,8 +943,12 @@ skd_status db_build(skd_ctx *ctx, const ChunkSource &src, uint64_t n, uint64_t s
                     auto work = [&](int t) {
                         const uint64_t cnt = s1 - s0, a = s0 + cnt * t / n_thr, b = s0 + cnt * (t + 1) / n_thr;
                         for (uint64_t s = a; s < b;) {
-                            // contiguous file range when there is no subset list, else one sample at a time
-                            const uint64_t run = src.indices ? 1 : b - s;
+                            // contiguous file range when there is no subset list, else runs of consecutive positions
+                            uint64_t run = b - s;
+                            if (src.indices) {
+                                run = 1;
+                                while (s + run < b && src.indices[s + run] == src.indices[s] + run) ++run;
+                            }
                             const uint64_t fpos = (src.indices ? src.indices[s] : s) * sbytes;
                             size_t want = (size_t)run * sbytes, got = 0;
                             while (got < want) {

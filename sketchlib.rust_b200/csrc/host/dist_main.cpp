@@ -329,8 +329,9 @@ KnnOut multi_gpu_knn(const DistArgs &a, const MultiSketch &refs, const std::stri
     std::vector<std::pair<uint64_t, uint64_t>> ranges(world);
     auto file_indices = [&](uint64_t lo, uint64_t hi) {
         std::vector<uint64_t> v(hi - lo);
-        for (uint64_t s = lo; s < hi; ++s)
-            v[s - lo] = subset_idx ? (*subset_idx)[s] : refs.sketch_metadata[s].index;
+        // no subset: file POSITION, like the reference's read_sketch_data (multisketch.rs:167-184); after `delete`
+        // Sketch::index keeps the old numbering while the .skd is rewritten, so index != position
+        for (uint64_t s = lo; s < hi; ++s) v[s - lo] = subset_idx ? (*subset_idx)[s] : s;
         return v;
     };
     auto worker = [&](int d) {

@@ -108,8 +108,9 @@ const char *skh_skm_sketch_name(const skh_multisketch *h, uint64_t idx) {
 // positions in the .skd file (Sketch::index) of the loaded samples, in loaded order: what skd_db_load_skd takes
 void skh_skm_file_indices(const skh_multisketch *h, uint64_t *out) {
     const MultiSketch &m = h->m;
+    // full load: file POSITION like read_sketch_data (multisketch.rs:167-184); Sketch::index only after a subset
     for (size_t i = 0; i < m.number_samples_loaded(); ++i)
-        out[i] = m.sketch_metadata[m.block_reindex ? (*m.block_reindex)[i] : i].index;
+        out[i] = m.block_reindex ? m.sketch_metadata[(*m.block_reindex)[i]].index : (uint64_t)i;
 }
 // read_sketch_data_block's name lookup (multisketch.rs:187-200): afterwards the loaded samples are `names`, in order
 int skh_skm_select_subset(skh_multisketch *h, const char *const *names, uint64_t n, char *err, size_t errlen) {

@@ -1,6 +1,7 @@
 // See multisketch.hpp.  Host-only C++17.
 #include "multisketch.hpp"
 
+#include <algorithm>
 #include <charconv>
 #include <cmath>
 #include <cstdlib>
@@ -23,9 +24,12 @@ static std::string snappy_block(const unsigned char *p, size_t n) {
         want |= (uint64_t)(b & 0x7f) << shift;
         shift += 7;
         if (!(b & 0x80)) break;
+        if (shift >= 35) throw err("snappy: length varint longer than 5 bytes");  // the format caps it at 32 bits
     }
+    if (want > 0xffffffffull) throw err("snappy: uncompressed length exceeds 32 bits");
     std::string out;
-    out.reserve(want);
+    // a copy element expands at most 64 bytes from 2 input bytes: never trust a declared length beyond that bound
+    out.reserve((size_t)std::min<uint64_t>(want, (uint64_t)n * 32 + 64));
     auto need = [&](size_t k) {
         if (pos + k > n) throw err("snappy: truncated block");
     };
@@ -276,6 +280,9 @@ MultiSketch MultiSketch::load_metadata(const std::string &file_prefix) {
             if (kv.first->kind == CborValue::TEXT && kv.second->kind == CborValue::UINT)
                 m.name_map[kv.first->s] = (size_t)kv.second->u;
     }
+    // The reference's `delete` (remove_metadata) shrinks sketch_metadata but leaves name_map stale, so entries that
+    // point past the end occur in files the reference itself wrote; Rust panics on the indexing, here every use
+    // is bounds-checked (select_subset / get_sample_index) and such entries never reach an array access.
     m.bin_stride = as_u64(root->get("bin_stride"), "bin_stride");
     m.kmer_stride = as_u64(root->get("kmer_stride"), "kmer_stride");
     m.sample_stride = as_u64(root->get("sample_stride"), "sample_stride");
@@ -296,6 +303,9 @@ std::vector<uint64_t> MultiSketch::select_subset(const std::vector<std::string> 
     for (auto &name : names) {
         auto it = name_map.find(name);
         if (it == name_map.end()) throw err("Could not find requested sample " + name + " in sketch metadata");
+        if (it->second >= sketch_metadata.size())  // stale name_map entry: the reference panics on this index
+            throw err("index out of bounds: the len is " + std::to_string(sketch_metadata.size()) + " but the index is " +
+                      std::to_string(it->second) + " (name_map entry of " + name + ")");
         read_indices.push_back(sketch_metadata[it->second].index);
         reindex.push_back(it->second);
     }
@@ -312,11 +322,14 @@ std::optional<size_t> MultiSketch::get_k_idx(uint64_t k) const {
 std::optional<size_t> MultiSketch::get_sample_index(const std::string &name) const {
     if (block_reindex) {
         for (size_t l = 0; l < block_reindex->size(); ++l)
-            if (sketch_metadata[(*block_reindex)[l]].name == name) return l;
+            if ((*block_reindex)[l] < sketch_metadata.size() && sketch_metadata[(*block_reindex)[l]].name == name) return l;
         return std::nullopt;
     }
     auto it = name_map.find(name);
     if (it == name_map.end()) return std::nullopt;
+    if (it->second >= sketch_metadata.size())  // stale name_map entry (see load_metadata)
+        throw err("index out of bounds: the len is " + std::to_string(sketch_metadata.size()) + " but the index is " +
+                  std::to_string(it->second) + " (name_map entry of " + name + ")");
     return it->second;
 }
 
@@ -332,7 +345,49 @@ std::vector<std::string> read_subset_names(const std::string &subset_file) {
     return names;
 }
 
+// Rust's f64::from_str (src/io.rs:268): decimal digits with optional sign, fraction and exponent, or
+// inf / infinity / nan in any case; no hex floats, no locale (strtod accepts both), no surrounding garbage.
+static bool parse_rust_f64(const std::string &s, double *out) {
+    if (s.empty()) return false;
+    size_t p = 0;
+    bool neg = false;
+    if (s[0] == '+' || s[0] == '-') {
+        neg = s[0] == '-';
+        p = 1;
+    }
+    std::string low;
+    for (size_t i = p; i < s.size(); ++i) low.push_back((char)tolower((unsigned char)s[i]));
+    if (low == "inf" || low == "infinity") {
+        *out = neg ? -INFINITY : INFINITY;
+        return true;
+    }
+    if (low == "nan") {
+        *out = NAN;
+        return true;
+    }
+    if (low.empty()) return false;
+    for (char ch : low)
+        if (!(isdigit((unsigned char)ch) || ch == '.' || ch == 'e' || ch == '+' || ch == '-')) return false;
+    const char *b = s.data() + p, *e = s.data() + s.size();
+    double v = 0.0;
+    auto r = std::from_chars(b, e, v, std::chars_format::general);
+    if (r.ptr != e) return false;
+    if (r.ec == std::errc::result_out_of_range) {  // Rust saturates: huge -> inf, tiny -> 0
+        bool big = false;
+        size_t epos = low.find('e');
+        if (epos != std::string::npos) big = low.find('-', epos) == std::string::npos;
+        else big = true;
+        v = big ? INFINITY : 0.0;
+    } else if (r.ec != std::errc()) {
+        return false;
+    }
+    *out = neg ? -v : v;
+    return true;
+}
+
 static std::string fmt_f64(double v) {
+    if (std::isnan(v)) return "NaN";  // Rust Display
+    if (std::isinf(v)) return v < 0 ? "-inf" : "inf";
     char buf[512];
     auto r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::fixed);
     return std::string(buf, r.ptr);
@@ -367,9 +422,8 @@ std::vector<double> read_completeness_file(const std::string &file, const MultiS
         size_t tab = line.find('\t');
         if (tab == std::string::npos) continue;  // split_once('\t')? -> skipped
         std::string id = line.substr(0, tab), val = trim(line.substr(tab + 1));
-        char *end = nullptr;
-        double c = val.empty() ? 0.0 : strtod(val.c_str(), &end);
-        if (val.empty() || end != val.c_str() + val.size()) {
+        double c = 0.0;
+        if (!parse_rust_f64(val, &c)) {
             if (warn) warn->push_back("Could not parse completeness value for '" + id + "': '" + line.substr(tab + 1) + "' — skipping");
             continue;
         }

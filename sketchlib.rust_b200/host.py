@@ -110,6 +110,8 @@ class MultiSketch:
         return self.kmer_lengths.index(k) if k in self.kmer_lengths else None
 
     def file_indices(self):
+        """File positions of the loaded samples: 0..n-1 for a full load (read_sketch_data reads by position,
+        multisketch.rs:167-184), Sketch::index of the selected samples after select_subset."""
         out = np.zeros(self.number_samples_loaded(), dtype=np.uint64)
         self.lib.skh_skm_file_indices(self.handle, out.ctypes.data_as(C.c_void_p))
         return out
@@ -118,17 +120,20 @@ class MultiSketch:
         from . import SketchDb
         return SketchDb.load_skd(ctx, self.prefix + ".skd", self.number_samples_loaded(), self.kmer_lengths,
                                  self.sketchsize64, self.sketch_size, self.sample_stride, self.kmer_stride, self.names(),
-                                 sample_indices=self.file_indices())
+                                 sample_indices=self.file_indices() if self.has_subset else None)
 
     def read_sketch_data(self, ctx):
         """multisketch.rs:167-184: every sample of the file, into HBM."""
         return self._to_device(ctx)
+
+    has_subset = False
 
     def select_subset(self, names):
         """The name lookup of read_sketch_data_block (multisketch.rs:187-200): afterwards the loaded samples are
         `names`, in that order.  Raises HostError("Could not find requested sample ...") like the reference panics."""
         arr = (C.c_char_p * len(names))(*[n.encode() for n in names])
         _call(self.lib.skh_skm_select_subset, self.handle, arr, len(names))
+        self.has_subset = True
 
     def read_sketch_data_block(self, ctx, names):
         """multisketch.rs:187-210: only `names`, in that order (the --subset list)."""
@@ -137,9 +142,13 @@ class MultiSketch:
 
 
 def read_subset_names(subset_file):
-    """src/io.rs:227-236: first whitespace-separated field of every line."""
-    with open(subset_file) as fh:
-        return [line.split()[0] for line in fh if line.split()]
+    """src/io.rs:227-236: every line verbatim (BufRead::lines: the trailing "\n" / "\r\n" is stripped, nothing else),
+    so names may contain spaces and a blank line is a name that will not be found -- like the C++ reader."""
+    with open(subset_file, newline="") as fh:
+        lines = fh.read().split("\n")
+    if lines and lines[-1] == "":
+        lines.pop()
+    return [ln[:-1] if ln.endswith("\r") else ln for ln in lines]
 
 
 def read_completeness_file(path, sketches: MultiSketch):

@@ -129,15 +129,15 @@ def _crc32c(data: bytes) -> int:
     return crc ^ 0xFFFFFFFF
 
 
-def write_skm_skd(prefix, db, version="0.3.0"):
+def write_skm_skd(prefix, db, version="0.3.0", name_map=None, indices=None):
     """Writes <prefix>.skm/.skd for an oracle.Db in the reference's container format (snappy frame with
     uncompressed chunks + CBOR map with the serde field names of MultiSketch / Sketch)."""
     meta = {
         "sketch_size": db.sketch_size, "sketchsize64": db.W, "kmer_lengths": [int(k) for k in db.kmers],
         "sketch_metadata": [
-            {"name": nm, "index": i, "rc": True, "reads": False, "seq_length": 2000000, "densified": False,
+            {"name": nm, "index": i if indices is None else int(indices[i]), "rc": True, "reads": False, "seq_length": 2000000, "densified": False,
              "acgt": [1, 1, 1, 1], "non_acgt": 0} for i, nm in enumerate(db.names)],
-        "name_map": {nm: i for i, nm in enumerate(db.names)},
+        "name_map": name_map if name_map is not None else {nm: i for i, nm in enumerate(db.names)},
         "bin_stride": 1, "kmer_stride": db.kmer_stride, "sample_stride": db.sample_stride,
         "sketch_version": version, "hash_type": "DNA",
     }

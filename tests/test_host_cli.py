@@ -106,6 +106,54 @@ def test_cli_host_side_errors(tools, tmp_path):
     assert r.returncode == 2
 
 
+def test_stale_name_map_entries_are_bounds_checked(tools, tmp_path):
+    """The reference's `delete` shrinks sketch_metadata but leaves name_map stale (remove_metadata); Rust panics with
+    an index-out-of-bounds on such an entry.  Here: a clean error, never an out-of-bounds access."""
+    cli, skm_info = tools
+    db = synth_db(6, 2, [15, 19], seed=3)
+    nm = {n: i for i, n in enumerate(db.names)}
+    nm[db.names[2]] = 1048575           # stale: points far past sketch_metadata
+    nm["ghost"] = 6                     # deleted sample still in the map, one past the end
+    prefix = write_skm_skd(str(tmp_path / "stale"), db, name_map=nm)
+    sub = tmp_path / "sub.txt"
+    sub.write_text(f"{db.names[0]}\n{db.names[2]}\n")
+    comp = tmp_path / "comp.txt"
+    comp.write_text(f"{db.names[2]}\t0.9\nghost\t0.5\n")
+    for args in ([skm_info, prefix, "--subset", str(sub)], [skm_info, prefix, "--completeness", str(comp)],
+                 [cli, "dist", prefix, "--subset", str(sub)], [cli, "dist", prefix, "--ref-completeness-file", str(comp)]):
+        r = run(args)
+        assert r.returncode in (1, 101), (args, r.returncode, r.stderr)
+        assert "index out of bounds" in r.stderr, r.stderr
+    # entries that are in range keep working next to the stale ones
+    ok = tmp_path / "ok.txt"
+    ok.write_text(f"{db.names[4]}\n{db.names[0]}\n")
+    got = parse_info(run([skm_info, prefix, "--subset", str(ok)]).stdout)
+    assert got["samples"] == [(db.names[4], 4), (db.names[0], 0)]
+
+
+def test_completeness_values_parse_like_rust(tools, tmp_path):
+    """f64::from_str accepts decimal floats, inf and nan; not hex floats or trailing garbage (strtod took both)."""
+    _, skm_info = tools
+    db = os.path.join(FIXTURES, "sketches1")
+    comp = tmp_path / "c.txt"
+    comp.write_text("R6.fa.gz\t0x1p-1\nTIGR4.fa.gz\t5e-1\n14412_3#82.contigs_velvet.fa.gz\t.25\n"
+                    "14412_3#84.contigs_velvet.fa.gz\t0.5x\n")
+    got = parse_info(run([skm_info, db, "--completeness", str(comp)]).stdout)
+    assert got["completeness"] == [0.25, 1.0, 1.0, 0.5]
+    assert sum("Could not parse completeness value" in w for w in got["warn"]) == 2
+    bad = tmp_path / "nan.txt"
+    bad.write_text("R6.fa.gz\tnan\n")
+    r = run([skm_info, db, "--completeness", str(bad)])
+    assert r.returncode == 1 and "R6.fa.gz: NaN" in r.stderr
+
+
+def test_python_subset_names_are_whole_lines(tmp_path):
+    import sketchlib.rust_b200.host as host
+    f = tmp_path / "names.txt"
+    f.write_bytes(b"a b\r\n\nlast")
+    assert host.read_subset_names(str(f)) == ["a b", "", "last"]
+
+
 # ---------------------------------------------------------------- GPU: end-to-end CLI
 def golden(name):
     return open(os.path.join(FIXTURES, name + ".stdout")).read()
