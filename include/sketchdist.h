@@ -57,6 +57,8 @@ typedef struct skd_ctx skd_ctx;
 typedef struct skd_db skd_db; /* a MultiSketch resident in HBM (src/sketch/multisketch.rs:23-43) */
 
 /* ---- context ---------------------------------------------------------------------------- */
+/* Number of CUDA devices visible to the process (0 without a driver or GPU). */
+int skd_device_count(void);
 skd_status skd_ctx_create(int device, skd_ctx **out);
 void skd_ctx_destroy(skd_ctx *ctx);
 /* Message of the last failing call on this context (or of a failed skd_ctx_create when ctx == NULL). */
@@ -67,6 +69,9 @@ uint64_t skd_ctx_launch_count(const skd_ctx *ctx);
 /* Device time in ms of the distance kernels of the last compute call, measured with CUDA events on
  * the context's compute stream (the stream the kernels are launched on). */
 float skd_ctx_last_kernel_ms(const skd_ctx *ctx);
+/* The part of it spent in the match-count kernels (tile_kernel / stream_kernel launches), the path's dominant
+ * kernels: what bench.py's roofline is computed from. */
+float skd_ctx_last_tile_kernel_ms(const skd_ctx *ctx);
 /* Block until all work queued by this context is complete. */
 skd_status skd_ctx_synchronize(skd_ctx *ctx);
 /* The context's compute stream as a cudaStream_t (for callers that time with their own events). */
@@ -185,6 +190,87 @@ skd_status skd_cross_knn_partial(skd_ctx *ctx, const skd_db *ref_shard, const sk
 skd_status skd_knn_merge(skd_ctx *ctx, const uint64_t *keys, const float *aux, uint32_t n_parts, uint64_t n_rows,
                          uint64_t knn, skd_dist_type dist, skd_loc in_loc, uint64_t *idx_out, float *d0_out,
                          float *d1_out, skd_loc out_loc);
+
+/* ---- peer groups: the GPUs of one box working on ONE distance problem -------------------------------------------
+ * The reference has a single shared-memory thread pool (rayon, src/cli.rs:75-86); its multi-GPU counterpart is a
+ * group of `world` contexts, one per GPU -- one process per GPU (handles exchanged by the launcher, memory mapped
+ * with CUDA IPC) or several host threads of one process (direct peer access).  Every rank owns a window of device
+ * memory that its peers can read over NVLink; the library's own kernels do the exchange (the merge kernel pulls the
+ * partial kNN lists it needs straight from the peers' windows, the loader pulls the peers' re-tiled sample slices),
+ * synchronised by flag barriers in peer memory.  There is no NCCL or MPI dependency.
+ *
+ * All skd_comm_* compute calls are COLLECTIVE: every rank of the group calls them in the same order with the same
+ * arguments (except where noted); a rank that never arrives makes the others fail with SKD_ERR_CUDA after the
+ * barrier timeout (SKD_PEER_TIMEOUT_S, default 60 s) instead of hanging. */
+typedef struct skd_comm skd_comm;
+#define SKD_COMM_HANDLE_BYTES 128
+#define SKD_COMM_MAX_WORLD 16
+
+skd_status skd_comm_create(skd_ctx *ctx, int rank, int world, size_t window_bytes, skd_comm **out);
+void skd_comm_destroy(skd_comm *comm);
+/* handle_out: SKD_COMM_HANDLE_BYTES bytes describing this rank's window, to be sent to every peer. */
+skd_status skd_comm_export(const skd_comm *comm, void *handle_out);
+/* handles: world x SKD_COMM_HANDLE_BYTES bytes in rank order (the own entry is ignored). */
+skd_status skd_comm_connect(skd_comm *comm, const void *handles);
+int skd_comm_rank(const skd_comm *comm);
+int skd_comm_world(const skd_comm *comm);
+/* Device time in ms of the last collective call on this rank (CUDA events on the context's compute stream, from
+ * the entry barrier to the last kernel or copy of the call). */
+float skd_comm_last_op_ms(const skd_comm *comm);
+/* The part of it spent after the local distance kernels: barriers + peer merge + gather of the final rows. */
+float skd_comm_last_exchange_ms(const skd_comm *comm);
+/* Window sizes the collective calls need (the window must hold the largest one used). */
+size_t skd_comm_window_bytes_knn(uint64_t n_rows, uint64_t knn, int world);
+size_t skd_comm_window_bytes_db(uint64_t n_samples, uint64_t sketchsize64, uint32_t n_kmers, int world);
+
+/* The partitions the collective calls use (exported so that every host layer derives them from one rule):
+ * skd_triangle_rows: upper-triangle row block of `rank` with about 1/world of the n(n-1)/2 pairs (boundaries at
+ *   n(1 - sqrt(1 - r/world)), rounded to the 64-sample tile) -- dense self outputs and symmetric self kNN;
+ * skd_slice_rows: contiguous slices of ceil(n/world) items rounded up to `align` -- sample slices of the
+ *   distributed loader (align 64), reference shards (align 64), owned result rows (align 1). */
+void skd_triangle_rows(uint64_t n, int rank, int world, uint64_t *row_begin, uint64_t *row_end);
+void skd_slice_rows(uint64_t n, int rank, int world, uint64_t align, uint64_t *begin, uint64_t *end);
+
+/* Distributed form of read_sketch_data (multisketch.rs:167-184): every rank ends up with the WHOLE database in its
+ * HBM, but moves only its own slice skd_slice_rows(n_total, rank, world, 64) over PCIe: `bins_slice` points at the
+ * first sample of that slice (reference layout, host or device memory).  The slice is re-tiled locally into the
+ * window and every rank pulls the other slices from its peers over NVLink. */
+skd_status skd_comm_db_upload(skd_comm *comm, const uint64_t *bins_slice, skd_loc bins_loc, uint64_t n_total,
+                              uint64_t sample_stride, uint64_t kmer_stride, uint64_t sketchsize64,
+                              uint64_t sketch_size, const uint64_t *kmer_lengths, uint32_t n_kmers, skd_db **out);
+/* Same from an .skd file: `sample_indices` (nullable) lists the file positions of all n_total samples in load order
+ * (the --subset order); every rank reads only the entries of its slice. */
+skd_status skd_comm_db_load_skd(skd_comm *comm, const char *skd_path, const uint64_t *sample_indices,
+                                uint64_t n_total, uint64_t sample_stride, uint64_t kmer_stride,
+                                uint64_t sketchsize64, uint64_t sketch_size, const uint64_t *kmer_lengths,
+                                uint32_t n_kmers, skd_db **out);
+
+/* self_dists_knn (src/distances/mod.rs:133-224) over the group, database replicated on every rank.  knn <= 64:
+ * every rank evaluates its skd_triangle_rows block once per unordered pair (skd_self_knn_partial), the owner of a
+ * row (skd_slice_rows(n, rank, world, 1)) merges the partial lists of that row straight out of its peers' windows;
+ * larger knn: every rank computes its owned rows against all columns.  The final n x knn rows are gathered on rank
+ * `root` (every rank if root < 0) into idx_out / d0_out / d1_out (ignored on the other ranks, may be NULL there). */
+skd_status skd_comm_self_dists_knn(skd_comm *comm, const skd_db *db, uint64_t knn, skd_dist_type dist,
+                                   const double *completeness, double completeness_cutoff, int root,
+                                   uint64_t *idx_out, float *d0_out, float *d1_out, skd_loc out_loc);
+/* cross_dists_knn (src/distances/mod.rs:306-395) with the REFERENCES sharded: rank r holds the references
+ * [ref_index_offset, ref_index_offset + n(ref_shard)) of n_ref_total (`ref_completeness` covers the shard) and all
+ * queries; per-shard partial lists are merged by the owners of the query rows and gathered on `root`.  knn is
+ * clamped to n_ref_total (:325), *knn_used is the row pitch of the outputs. */
+skd_status skd_comm_cross_dists_knn(skd_comm *comm, const skd_db *ref_shard, const skd_db *query, uint64_t knn,
+                                    skd_dist_type dist, const double *ref_completeness,
+                                    const double *query_completeness, double completeness_cutoff,
+                                    uint64_t ref_index_offset, uint64_t n_ref_total, int root, uint64_t *idx_out,
+                                    float *d0_out, float *d1_out, skd_loc out_loc, uint64_t *knn_used);
+/* The exchange half alone, for callers that produce the partial lists themselves (skd_self_knn_partial /
+ * skd_cross_knn_partial; e.g. one list set per reference shard streamed through HBM): `keys` holds n_parts_local
+ * list sets [n_parts_local][n_rows][knn] of this rank (aux likewise, NULL unless core/accessory); they are folded
+ * into one, merged across the group by the rows' owners out of peer memory and gathered on `root`. */
+skd_status skd_comm_knn_merge(skd_comm *comm, const uint64_t *keys, const float *aux, uint32_t n_parts_local,
+                              skd_loc in_loc, uint64_t n_rows, uint64_t knn, skd_dist_type dist, int root,
+                              uint64_t *idx_out, float *d0_out, float *d1_out, skd_loc out_loc);
+/* Flag barrier over the peers' windows on the compute stream, then a stream synchronise (a collective no-op). */
+skd_status skd_comm_barrier(skd_comm *comm);
 
 /* The distance half of self_dists_knn_precluster (src/distances/mod.rs:399-553): per row i the candidates
  * cand_idx[cand_offsets[i] .. cand_offsets[i+1]) (.skd sample indices; what Inverted::any_shared_bins returned,

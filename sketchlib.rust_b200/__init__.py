@@ -19,7 +19,7 @@ __all__ = [
     "Context", "SketchDb", "DistType", "DistanceMatrix", "SparseDistanceMatrix", "SketchDistError", "set_k",
     "self_dists_all", "self_dists_knn", "cross_dists_all", "cross_dists_knn", "pair_dists", "match_counts",
     "self_knn_partial", "cross_knn_partial", "knn_merge", "self_dists_knn_precluster",
-    "row_partition", "triangle_row_partition", "load_library", "library_path",
+    "row_partition", "triangle_row_partition", "slice_rows", "PeerGroup", "load_library", "library_path",
 ]
 
 SKD_HOST, SKD_DEVICE = 0, 1
@@ -57,12 +57,14 @@ def load_library(build=True):
     L = C.CDLL(os.environ.get("SKD_LIB_OVERRIDE", _build.LIB))  # override: ablation builds (tools/)
     vp, u64, u32, i64, dbl, f32p = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int64, C.c_double, C.c_void_p
     sig = {
+        "skd_device_count": (C.c_int, []),
         "skd_ctx_create": (C.c_int, [C.c_int, C.POINTER(vp)]),
         "skd_ctx_destroy": (None, [vp]),
         "skd_last_error": (C.c_char_p, [vp]),
         "skd_ctx_device": (C.c_int, [vp]),
         "skd_ctx_launch_count": (u64, [vp]),
         "skd_ctx_last_kernel_ms": (C.c_float, [vp]),
+        "skd_ctx_last_tile_kernel_ms": (C.c_float, [vp]),
         "skd_ctx_synchronize": (C.c_int, [vp]),
         "skd_ctx_stream": (vp, [vp]),
         "skd_host_alloc": (C.c_int, [vp, C.c_size_t, C.POINTER(vp)]),
@@ -94,6 +96,25 @@ def load_library(build=True):
         "skd_pair_dists": (C.c_int, [vp, vp, vp, _DistType, vp, vp, dbl, vp, u64, vp]),
         "skd_match_counts": (C.c_int, [vp, vp, vp, vp, u64, vp]),
         "skd_match_counts_dense": (C.c_int, [vp, vp, vp, u64, u64, vp]),
+        "skd_comm_create": (C.c_int, [vp, C.c_int, C.c_int, C.c_size_t, C.POINTER(vp)]),
+        "skd_comm_destroy": (None, [vp]),
+        "skd_comm_export": (C.c_int, [vp, vp]),
+        "skd_comm_connect": (C.c_int, [vp, vp]),
+        "skd_comm_rank": (C.c_int, [vp]),
+        "skd_comm_world": (C.c_int, [vp]),
+        "skd_comm_last_op_ms": (C.c_float, [vp]),
+        "skd_comm_last_exchange_ms": (C.c_float, [vp]),
+        "skd_comm_window_bytes_knn": (C.c_size_t, [u64, u64, C.c_int]),
+        "skd_comm_window_bytes_db": (C.c_size_t, [u64, u64, u32, C.c_int]),
+        "skd_triangle_rows": (None, [u64, C.c_int, C.c_int, C.POINTER(u64), C.POINTER(u64)]),
+        "skd_slice_rows": (None, [u64, C.c_int, C.c_int, u64, C.POINTER(u64), C.POINTER(u64)]),
+        "skd_comm_db_upload": (C.c_int, [vp, vp, C.c_int, u64, u64, u64, u64, u64, vp, u32, C.POINTER(vp)]),
+        "skd_comm_db_load_skd": (C.c_int, [vp, C.c_char_p, vp, u64, u64, u64, u64, u64, vp, u32, C.POINTER(vp)]),
+        "skd_comm_self_dists_knn": (C.c_int, [vp, vp, u64, _DistType, vp, dbl, C.c_int, vp, vp, vp, C.c_int]),
+        "skd_comm_cross_dists_knn": (C.c_int, [vp, vp, vp, u64, _DistType, vp, vp, dbl, u64, u64, C.c_int, vp, vp, vp,
+                                               C.c_int, C.POINTER(u64)]),
+        "skd_comm_knn_merge": (C.c_int, [vp, vp, vp, u32, C.c_int, u64, u64, _DistType, C.c_int, vp, vp, vp, C.c_int]),
+        "skd_comm_barrier": (C.c_int, [vp]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -170,6 +191,10 @@ class Context:
     @property
     def last_kernel_ms(self):
         return float(self.lib.skd_ctx_last_kernel_ms(self.handle))
+
+    @property
+    def last_tile_kernel_ms(self):
+        return float(self.lib.skd_ctx_last_tile_kernel_ms(self.handle))
 
     @property
     def stream(self):
@@ -386,15 +411,167 @@ def row_partition(n_rows, rank, world):
 
 def triangle_row_partition(n, rank, world, align=64):
     """Row blocks of the upper triangle with about equal pair counts: row i holds n-1-i pairs, so the
-    boundary after a fraction f of the pairs is n * (1 - sqrt(1 - f)); rounded to the 64-sample tile."""
+    boundary after a fraction f of the pairs is n * (1 - sqrt(1 - f)); rounded to the 64-sample tile.
+    Same rule as the library's skd_triangle_rows (which the peer-group calls use)."""
     def bound(r):
         if r <= 0:
             return 0
         if r >= world:
             return n
         x = n * (1.0 - (1.0 - r / world) ** 0.5)
-        return min(n, int(round(x / align)) * align)
+        return min(n, int(x / align + 0.5) * align)   # llround: halves away from zero, like the C library
     return bound(rank), bound(rank + 1)
+
+
+def slice_rows(n, rank, world, align=1):
+    """skd_slice_rows: contiguous slices of ceil(n / world) items rounded up to `align` (sample slices of the
+    distributed loader and reference shards: align 64; owned result rows: align 1)."""
+    per = -(-(-(-n // world)) // align) * align
+    a = min(n, per * rank)
+    return a, min(n, a + per)
+
+
+class PeerGroup:
+    """skd_comm: this rank's membership in a group of `world` GPUs of one box working on one problem (one process
+    per GPU, or several threads of one process).  Create on every rank, exchange the `export()` blobs with whatever
+    the launcher offers (torch.distributed.all_gather_object, a file, a pipe), `connect()` with all of them in rank
+    order, then call the collective methods on every rank in the same order."""
+
+    def __init__(self, ctx, rank, world, window_bytes):
+        self.ctx, self.rank, self.world = ctx, int(rank), int(world)
+        h = C.c_void_p()
+        ctx._check(ctx.lib.skd_comm_create(ctx.handle, self.rank, self.world, int(window_bytes), C.byref(h)))
+        self.handle = h
+
+    @staticmethod
+    def window_bytes_knn(n_rows, knn, world):
+        return int(load_library().skd_comm_window_bytes_knn(int(n_rows), int(knn), int(world)))
+
+    @staticmethod
+    def window_bytes_db(n_samples, sketchsize64, n_kmers, world):
+        return int(load_library().skd_comm_window_bytes_db(int(n_samples), int(sketchsize64), int(n_kmers), int(world)))
+
+    def export(self):
+        buf = C.create_string_buffer(128)
+        self.ctx._check(self.ctx.lib.skd_comm_export(self.handle, buf))
+        return buf.raw
+
+    def connect(self, handles):
+        blob = b"".join(handles) if not isinstance(handles, (bytes, bytearray)) else bytes(handles)
+        if len(blob) != 128 * self.world:
+            raise ValueError(f"need {self.world} handles of 128 bytes")
+        self.ctx._check(self.ctx.lib.skd_comm_connect(self.handle, blob))
+
+    def close(self):
+        if getattr(self, "handle", None) and self.ctx.handle:
+            self.ctx.lib.skd_comm_destroy(self.handle)
+        self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def last_op_ms(self):
+        return float(self.ctx.lib.skd_comm_last_op_ms(self.handle))
+
+    @property
+    def last_exchange_ms(self):
+        return float(self.ctx.lib.skd_comm_last_exchange_ms(self.handle))
+
+    def barrier(self):
+        self.ctx._check(self.ctx.lib.skd_comm_barrier(self.handle))
+
+    def my_sample_slice(self, n_total):
+        return slice_rows(n_total, self.rank, self.world, 64)
+
+    def upload(self, bins_slice, n_total, kmer_lengths, sketchsize64, sketch_size=None, names=None, bins_loc=SKD_HOST):
+        """Distributed loader (skd_comm_db_upload): `bins_slice` = the reference-layout planes of this rank's sample
+        slice `my_sample_slice(n_total)` (numpy u64 array or device pointer); returns the WHOLE database in HBM."""
+        ctx = self.ctx
+        kmers = np.ascontiguousarray(kmer_lengths, dtype=np.uint64)
+        W = int(sketchsize64)
+        kmer_stride, sample_stride = W * 14, W * 14 * len(kmers)
+        sketch_size = int(sketch_size if sketch_size is not None else 64 * W)
+        h = C.c_void_p()
+        ctx._check(ctx.lib.skd_comm_db_upload(self.handle, _ptr(bins_slice), bins_loc, int(n_total), sample_stride,
+                                              kmer_stride, W, sketch_size, _ptr(kmers), len(kmers), C.byref(h)))
+        return SketchDb(ctx, h, names, kmers.tolist(), W, sketch_size)
+
+    def load_skd(self, skd_path, n_total, kmer_lengths, sketchsize64, sketch_size=None, sample_stride=None,
+                 kmer_stride=None, names=None, sample_indices=None):
+        ctx = self.ctx
+        kmers = np.ascontiguousarray(kmer_lengths, dtype=np.uint64)
+        W = int(sketchsize64)
+        kmer_stride = int(kmer_stride if kmer_stride is not None else W * 14)
+        sample_stride = int(sample_stride if sample_stride is not None else kmer_stride * len(kmers))
+        sketch_size = int(sketch_size if sketch_size is not None else 64 * W)
+        idx = None if sample_indices is None else np.ascontiguousarray(sample_indices, dtype=np.uint64)
+        h = C.c_void_p()
+        ctx._check(ctx.lib.skd_comm_db_load_skd(self.handle, os.fsencode(skd_path), _ptr(idx), int(n_total),
+                                                sample_stride, kmer_stride, W, sketch_size, _ptr(kmers), len(kmers),
+                                                C.byref(h)))
+        return SketchDb(ctx, h, names, kmers.tolist(), W, sketch_size)
+
+    def _outputs(self, n_rows, knn, dist_type, root, out):
+        mine = root < 0 or root == self.rank
+        if out is not None:
+            return out
+        if not mine:
+            return None, None, None
+        idx = np.zeros((n_rows, knn), dtype=np.uint64)
+        d0 = np.zeros((n_rows, knn), dtype=np.float32)
+        d1 = np.zeros((n_rows, knn), dtype=np.float32) if dist_type.kind == CORE_ACC else None
+        return idx, d0, d1
+
+    def self_dists_knn(self, sketches, knn=50, dist_type=None, completeness_vec=None, completeness_cutoff=0.64, root=0,
+                       out=None, out_loc=SKD_HOST):
+        """self_dists_knn (src/distances/mod.rs:133-224) over the group; the SparseDistanceMatrix on `root` (every
+        rank if root < 0), None elsewhere.  `out` = (idx, d0, d1) preallocated arrays / device pointers."""
+        ctx = self.ctx
+        n = sketches.number_samples_loaded()
+        dist_type = dist_type or DistType(CORE_ACC)
+        idx, d0, d1 = self._outputs(n, knn, dist_type, root, out)
+        ctx._check(ctx.lib.skd_comm_self_dists_knn(self.handle, sketches.handle, int(knn), dist_type.c,
+                                                   _ptr(_f64(completeness_vec)), float(completeness_cutoff), int(root),
+                                                   _ptr(idx), _ptr(d0), _ptr(d1), out_loc))
+        if idx is None or out is not None:
+            return None
+        return SparseDistanceMatrix(sketches.names, None, dist_type, knn, idx, d0, d1, (0, n))
+
+    def knn_merge(self, keys_parts, aux_parts, dist_type, ref_names, query_names=None, root=0):
+        """skd_comm_knn_merge: this rank's partial lists (one or several [n_rows, knn] sets from self_knn_partial /
+        cross_knn_partial) merged across the group; the SparseDistanceMatrix on `root`."""
+        ctx = self.ctx
+        keys = np.ascontiguousarray(np.stack(keys_parts), dtype=np.uint64)
+        n_parts, n_rows, knn = keys.shape
+        aux = np.ascontiguousarray(np.stack(aux_parts), dtype=np.float32) if dist_type.kind == CORE_ACC else None
+        idx, d0, d1 = self._outputs(n_rows, knn, dist_type, root, None)
+        ctx._check(ctx.lib.skd_comm_knn_merge(self.handle, _ptr(keys), _ptr(aux), n_parts, SKD_HOST, n_rows, knn,
+                                              dist_type.c, int(root), _ptr(idx), _ptr(d0), _ptr(d1), SKD_HOST))
+        if idx is None:
+            return None
+        return SparseDistanceMatrix(ref_names, query_names, dist_type, knn, idx, d0, d1, (0, n_rows))
+
+    def cross_dists_knn(self, ref_shard, query_sketches, knn, dist_type, ref_index_offset, n_ref_total, ref_names=None,
+                        ref_completeness_vec=None, query_completeness_vec=None, completeness_cutoff=0.64, root=0,
+                        out=None, out_loc=SKD_HOST):
+        """cross_dists_knn (src/distances/mod.rs:306-395) with the references sharded over the group."""
+        ctx = self.ctx
+        nq = query_sketches.number_samples_loaded()
+        knn_c = max(1, min(int(knn), int(n_ref_total)))
+        idx, d0, d1 = self._outputs(nq, knn_c, dist_type, root, out)
+        used = C.c_uint64()
+        ctx._check(ctx.lib.skd_comm_cross_dists_knn(self.handle, ref_shard.handle, query_sketches.handle, int(knn),
+                                                    dist_type.c, _ptr(_f64(ref_completeness_vec)),
+                                                    _ptr(_f64(query_completeness_vec)), float(completeness_cutoff),
+                                                    int(ref_index_offset), int(n_ref_total), int(root), _ptr(idx),
+                                                    _ptr(d0), _ptr(d1), out_loc, C.byref(used)))
+        if idx is None or out is not None:
+            return None
+        return SparseDistanceMatrix(ref_names, query_sketches.names, dist_type, int(used.value), idx, d0, d1, (0, nq))
 
 
 # ---- the reference's distance drivers ------------------------------------------------------------------

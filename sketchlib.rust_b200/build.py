@@ -6,8 +6,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libsketchdist.so")
-SOURCES = ["kernels.cu", "capi.cu"]
-HEADERS = ["kernels.h", "layout.h", os.path.join("..", "..", "include", "sketchdist.h")]
+SOURCES = ["kernels.cu", "capi.cu", "peer.cu"]
+HEADERS = ["kernels.h", "layout.h", "internal.h", os.path.join("..", "..", "include", "sketchdist.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-ffp-contract=off,-fno-fast-math", "-shared", "-cudart", "static",

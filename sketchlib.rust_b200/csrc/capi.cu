@@ -18,65 +18,15 @@
 #include <thread>
 #include <vector>
 
-#include "../../include/sketchdist.h"
-#include "kernels.h"
-#include "layout.h"
+#include "internal.h"
 
 using namespace skd;
 
 namespace {
 thread_local std::string g_create_error;
-constexpr size_t kMaxSmem = 232448;           // 227 KB opt-in dynamic shared memory per CTA on sm_100
-constexpr uint32_t kSymKnnMax = 64;           // symmetric self-kNN keeps 128-slot lists: knn + 64 candidates per step
 }  // namespace
 
-struct skd_ctx {
-    int device = 0;
-    cudaStream_t compute = nullptr, copy = nullptr;
-    cudaStream_t aux[2] = {nullptr, nullptr};  // async-upload dense runs: re-tiling / every other column band
-    std::string err;
-    uint64_t launches = 0;
-    float last_ms = 0.f;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timers;  // event pairs around kernel launches of a call
-    size_t timers_used = 0;
-    cudaEvent_t ev_a[2] = {nullptr, nullptr}, ev_b[2] = {nullptr, nullptr};
-    std::map<std::string, std::pair<void *, size_t>> scratch;  // named device buffers reused across calls
-    void *pinned[2] = {nullptr, nullptr};
-    size_t pinned_bytes = 0;
-    int sm_count = 148;
-    bool knn_symmetric = true;  // SKD_KNN_SYMMETRIC=0: whole-matrix self kNN evaluates both (i,j) and (j,i)
-    bool zero_copy = true;   // dense kernels store straight into pinned host results (SKD_ZEROCOPY=0 disables)
-    // Tunables, read once from the environment when the context is created.
-    size_t upload_chunk_bytes = 64ull << 20;  // SKD_UPLOAD_CHUNK_MB: staging chunk of a pageable/file upload
-    size_t result_chunk_bytes = 64ull << 20;  // SKD_RESULT_CHUNK_MB: staged D2H chunk of dense results
-    uint32_t group = 8;                       // SKD_GROUP: row blocks per L2 group of the tile scheduler
-    size_t sym_chunk_bytes = 2ull << 30;      // SKD_SYM_CHUNK_MB: HBM key buffer of one symmetric-kNN row group
-    uint64_t few_queries = 1ull << 20;        // SKD_FEW_QUERIES: cross kNN up to this many queries goes dense keys + select
-    size_t read_threads = 8;                  // SKD_READ_THREADS: host threads copying an .skd chunk into pinned staging
-                                              // (default: the host's hardware threads, at most 16)
-};
-
-struct skd_db {
-    skd_ctx *ctx = nullptr;
-    DevDb dev{};
-    uint32_t *tiled = nullptr;
-    size_t tiled_bytes = 0;
-    std::vector<uint64_t> kmers;
-    uint64_t sketch_size = 0, W = 0, n = 0;
-    double *lny_dev = nullptr;  // [nbins + 1]
-    // skd_db_upload_async: the raw planes are still arriving (copy stream, one event per chunk of whole sample
-    // blocks); they are re-tiled by the first compute call -- band by band, interleaved with the tile kernel, when
-    // that call is a dense self run, so that the PCIe transfer overlaps the distance computation.
-    struct Pending {
-        uint64_t *raw = nullptr;                 // device copy in the reference layout
-        uint64_t sample_stride = 0, kmer_stride = 0;
-        std::vector<cudaEvent_t> ready;          // chunk c has arrived
-        std::vector<uint32_t> block_end;         // chunk c covers sample blocks [block_end[c-1], block_end[c])
-    } pending;
-    bool is_pending() const { return pending.raw != nullptr; }
-};
-
-namespace {
+namespace skdi {
 
 skd_status fail(skd_ctx *ctx, skd_status st, const char *fmt, ...) {
     char buf[512];
@@ -91,21 +41,16 @@ skd_status fail(skd_ctx *ctx, skd_status st, const char *fmt, ...) {
     return st;
 }
 
-#define CU(ctx, expr)                                                                                   \
-    do {                                                                                                \
-        cudaError_t e__ = (expr);                                                                       \
-        if (e__ != cudaSuccess)                                                                         \
-            return fail(ctx, SKD_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
-                        __LINE__);                                                                      \
-    } while (0)
-
+// Named device buffers reused across calls.  Stream-ordered allocation (cudaMallocAsync / cudaFreeAsync on the
+// compute stream): growing a buffer never synchronises the device, which matters when several contexts share a GPU
+// and one of them sits in a peer barrier (peer.cu) -- a cudaFree there would wait for the spinning kernel.
 skd_status scratch_get(skd_ctx *ctx, const char *name, size_t bytes, void **out) {
     auto &slot = ctx->scratch[name];
     if (slot.second < bytes) {
-        if (slot.first) cudaFree(slot.first);
+        if (slot.first) CU(ctx, cudaFreeAsync(slot.first, ctx->compute));
         slot = {nullptr, 0};
         size_t want = std::max<size_t>(bytes, 256);
-        CU(ctx, cudaMalloc(&slot.first, want));
+        CU(ctx, cudaMallocAsync(&slot.first, want, ctx->compute));
         slot.second = want;
     }
     *out = slot.first;
@@ -125,30 +70,34 @@ skd_status pinned_get(skd_ctx *ctx, size_t bytes) {
 }
 
 void timers_reset(skd_ctx *ctx) { ctx->timers_used = 0; }
-skd_status timer_begin(skd_ctx *ctx, cudaStream_t stream = nullptr) {
+skd_status timer_begin(skd_ctx *ctx, cudaStream_t stream, int tag) {
     if (ctx->timers_used == ctx->timers.size()) {
         cudaEvent_t a, b;
         CU(ctx, cudaEventCreate(&a));
         CU(ctx, cudaEventCreate(&b));
         ctx->timers.push_back({a, b});
+        ctx->timer_tags.push_back(0);
     }
+    ctx->timer_tags[ctx->timers_used] = tag;
     CU(ctx, cudaEventRecord(ctx->timers[ctx->timers_used].first, stream ? stream : ctx->compute));
     return SKD_OK;
 }
-skd_status timer_end(skd_ctx *ctx, cudaStream_t stream = nullptr) {
+skd_status timer_end(skd_ctx *ctx, cudaStream_t stream) {
     CU(ctx, cudaEventRecord(ctx->timers[ctx->timers_used].second, stream ? stream : ctx->compute));
     ctx->timers_used++;
     return SKD_OK;
 }
 // Call after the compute stream is idle.
 skd_status timers_collect(skd_ctx *ctx) {
-    float total = 0.f;
+    float total = 0.f, tile = 0.f;
     for (size_t i = 0; i < ctx->timers_used; ++i) {
         float ms = 0.f;
         CU(ctx, cudaEventElapsedTime(&ms, ctx->timers[i].first, ctx->timers[i].second));
         total += ms;
+        if (ctx->timer_tags[i] == 1) tile += ms;
     }
     ctx->last_ms = total;
+    ctx->last_tile_ms = tile;
     return SKD_OK;
 }
 
@@ -247,7 +196,7 @@ skd_status build_epi(skd_ctx *ctx, const skd_db *A, const skd_db *B, skd_dist_ty
 
 skd_status materialize(skd_ctx *ctx, const skd_db *cdb);
 
-skd_status check_pair(skd_ctx *ctx, const skd_db *A, const skd_db *B, bool keep_pending = false) {
+skd_status check_pair(skd_ctx *ctx, const skd_db *A, const skd_db *B, bool keep_pending) {
     if (!ctx || !A || !B) return fail(ctx, SKD_ERR_INVALID, "null context or database");
     if (A->ctx != ctx || B->ctx != ctx) return fail(ctx, SKD_ERR_INVALID, "database belongs to another context");
     if (A != B && !skd_db_compatible(A, B))
@@ -338,7 +287,7 @@ skd_status launch_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, const Ep
     if (smem > kMaxSmem)
         return fail(ctx, SKD_ERR_UNSUPPORTED, "%d k-mer lengths at %u bins need %zu B of shared memory per tile", E.nk,
                     E.nbins, smem);
-    skd_status st = timer_begin(ctx, stream);
+    skd_status st = timer_begin(ctx, stream, 1);
     if (st) return st;
     CU(ctx, launch_tiles(A->dev, B->dev, E, S, off.back(), count32, smem, stream));
     ctx->launches++;
@@ -617,7 +566,7 @@ skd_status run_knn_few_queries(skd_ctx *ctx, const skd_db *R, const skd_db *Q, c
 // merge across column shards; idx_offset is added to the stored neighbour indices).
 skd_status run_knn(skd_ctx *ctx, const skd_db *R, const skd_db *Q, bool self, const EpiParams &E, uint64_t knn,
                    uint64_t row_begin, uint64_t row_end, uint64_t *idx_out, float *d0_out, float *d1_out,
-                   skd_loc out_loc, uint64_t *key_out = nullptr, float *aux_out = nullptr, uint64_t idx_offset = 0) {
+                   skd_loc out_loc, uint64_t *key_out, float *aux_out, uint64_t idx_offset) {
     // Rows are the A side of the tile kernel (self: the database; cross: queries), columns the refs.
     const skd_db *A = self ? R : Q, *B = R;
     const uint64_t n_rows = row_end - row_begin;
@@ -682,10 +631,14 @@ skd_status run_knn(skd_ctx *ctx, const skd_db *R, const skd_db *Q, bool self, co
             dd1 = (float *)p;
         }
     }
+    if (partial) launch_fill_u64(dkey, n_rows * knn, ~0ull, ctx->compute);
+    st = timer_begin(ctx, nullptr, 1);
+    if (st) return st;
+    CU(ctx, launch_tiles(A->dev, B->dev, E, S, (uint64_t)S.n_rb * S.n_split, count32, smem, ctx->compute));
+    st = timer_end(ctx);
+    if (st) return st;
     st = timer_begin(ctx);
     if (st) return st;
-    if (partial) launch_fill_u64(dkey, n_rows * knn, ~0ull, ctx->compute);
-    CU(ctx, launch_tiles(A->dev, B->dev, E, S, (uint64_t)S.n_rb * S.n_split, count32, smem, ctx->compute));
     launch_knn_merge(S.part_key, S.part_aux, S.n_split, S.knn, S.cap, row_begin - (uint64_t)S.rb0 * TS, n_rows, E.kind,
                      partial ? nullptr : didx, partial ? nullptr : dd0, partial ? nullptr : dd1, partial ? dkey : nullptr,
                      partial && with_aux ? daux : nullptr, ctx->compute);
@@ -796,9 +749,13 @@ skd_status run_knn_symmetric(skd_ctx *ctx, const skd_db *db, const EpiParams &E,
         if (smem > kMaxSmem)
             return fail(ctx, SKD_ERR_UNSUPPORTED, "%d k-mer lengths at %u bins need %zu B of shared memory per tile", E.nk,
                         E.nbins, smem);
-        st = timer_begin(ctx);
+        st = timer_begin(ctx, nullptr, 1);
         if (st) return st;
         CU(ctx, launch_tiles(db->dev, db->dev, E, S, off.back(), count32, smem, ctx->compute));
+        st = timer_end(ctx);
+        if (st) return st;
+        st = timer_begin(ctx);
+        if (st) return st;
         // rows of the group: candidates to their right; columns right of g0: candidates from the group's rows
         CU(ctx, launch_select_sym(false, with_aux, (const float *)D, ld, g0, (uint32_t)(g1 - g0), n, g0, g1, dkey, daux,
                                   (uint32_t)knn, ctx->compute));
@@ -811,16 +768,6 @@ skd_status run_knn_symmetric(skd_ctx *ctx, const skd_db *db, const EpiParams &E,
     }
     return SKD_OK;
 }
-
-// Shared by skd_db_upload (host or device array) and skd_db_load_skd (file): `fill` stages samples
-// [s0, s1) into pinned memory, or is null when `direct` already points at them.
-struct ChunkSource {
-    const uint64_t *direct = nullptr;  // array in the reference layout (host or device)
-    skd_loc loc = SKD_HOST;
-    int fd = -1;                       // .skd file
-    const uint64_t *indices = nullptr; // file positions, nullable
-    bool async = false;                // pinned host array: return once the copies are queued (skd_db_upload_async)
-};
 
 skd_status db_build(skd_ctx *ctx, const ChunkSource &src, uint64_t n, uint64_t sample_stride, uint64_t kmer_stride,
                     uint64_t W, uint64_t sketch_size, const uint64_t *kmers, uint32_t K, skd_db **out) {
@@ -865,6 +812,10 @@ skd_status db_build(skd_ctx *ctx, const ChunkSource &src, uint64_t n, uint64_t s
         CUB(cudaMallocAsync((void **)&db->lny_dev, lny.size() * sizeof(double), ctx->compute));
         CUB(cudaMemcpyAsync(db->lny_dev, lny.data(), lny.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->compute));
         CUB(cudaStreamSynchronize(ctx->compute));  // lny is a local vector
+    }
+    if (src.alloc_only) {  // peer.cu fills the planes from the peers' slices
+        *out = db;
+        return SKD_OK;
     }
     bool async_ok = false;
     if (n > 0 && src.async && src.direct && src.loc == SKD_HOST) {
@@ -918,6 +869,10 @@ skd_status db_build(skd_ctx *ctx, const ChunkSource &src, uint64_t n, uint64_t s
             if (st) return bail(st);
             st = scratch_get(ctx, "raw1", chunk_bytes, &raw[1]);
             if (st) return bail(st);
+            // the staging buffers come from the stream-ordered allocator of the compute stream: order the copy
+            // stream's first use after the allocation
+            CUB(cudaEventRecord(ctx->ev_a[0], ctx->compute));
+            CUB(cudaStreamWaitEvent(ctx->copy, ctx->ev_a[0], 0));
             const bool staged = src.fd >= 0;
             if (staged) {
                 st = pinned_get(ctx, chunk_bytes);
@@ -993,10 +948,20 @@ skd_status db_build(skd_ctx *ctx, const ChunkSource &src, uint64_t n, uint64_t s
     return SKD_OK;
 }
 
-}  // namespace
+}  // namespace skdi
+using namespace skdi;
 
 // =================================================================================================
 extern "C" {
+
+int skd_device_count(void) {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return count;
+}
 
 skd_status skd_ctx_create(int device, skd_ctx **out) {
     if (!out) return fail(nullptr, SKD_ERR_INVALID, "null output pointer");
@@ -1029,6 +994,14 @@ skd_status skd_ctx_create(int device, skd_ctx **out) {
                     prop.major, prop.minor);
     }
     ctx->sm_count = prop.multiProcessorCount;
+    if ((e = preload_kernels()) != cudaSuccess || (e = preload_peer_kernels()) != cudaSuccess) {
+        cudaStreamDestroy(ctx->compute);
+        cudaStreamDestroy(ctx->copy);
+        cudaStreamDestroy(ctx->aux[0]);
+        cudaStreamDestroy(ctx->aux[1]);
+        delete ctx;
+        return fail(nullptr, SKD_ERR_CUDA, "loading the kernels failed: %s", cudaGetErrorString(e));
+    }
     {   // keep freed database buffers in the device's default pool instead of returning them to the driver
         cudaMemPool_t pool;
         if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -1058,7 +1031,8 @@ void skd_ctx_destroy(skd_ctx *ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (auto &kv : ctx->scratch)
-        if (kv.second.first) cudaFree(kv.second.first);
+        if (kv.second.first) cudaFreeAsync(kv.second.first, ctx->compute);
+    if (ctx->compute) cudaStreamSynchronize(ctx->compute);
     for (int i = 0; i < 2; ++i) {
         if (ctx->pinned[i]) cudaFreeHost(ctx->pinned[i]);
         if (ctx->ev_a[i]) cudaEventDestroy(ctx->ev_a[i]);
@@ -1079,6 +1053,7 @@ const char *skd_last_error(const skd_ctx *ctx) { return ctx ? ctx->err.c_str() :
 int skd_ctx_device(const skd_ctx *ctx) { return ctx ? ctx->device : -1; }
 uint64_t skd_ctx_launch_count(const skd_ctx *ctx) { return ctx ? ctx->launches : 0; }
 float skd_ctx_last_kernel_ms(const skd_ctx *ctx) { return ctx ? ctx->last_ms : 0.f; }
+float skd_ctx_last_tile_kernel_ms(const skd_ctx *ctx) { return ctx ? ctx->last_tile_ms : 0.f; }
 void *skd_ctx_stream(const skd_ctx *ctx) { return ctx ? (void *)ctx->compute : nullptr; }
 
 skd_status skd_ctx_synchronize(skd_ctx *ctx) {

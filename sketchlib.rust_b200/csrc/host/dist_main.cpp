@@ -9,7 +9,10 @@
 // sub-commands are not implemented.
 // Extra flag: --gpu <id> (default 0).  --threads is accepted for compatibility (the work runs on the GPU).
 #include <algorithm>
+#include <array>
 #include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -86,7 +89,7 @@ const char *USAGE =
     "      --query-completeness-file <F>  Query completeness estimates (cross-query mode only)\n"
     "      --completeness-cutoff <X>      Minimum c1*c2 for the completeness correction [default: 0.64]\n"
     "      --gpu <ID>                     CUDA device [default: 0]\n"
-    "      --gpus <N>                     Use devices 0..N-1 for --knn runs (one host thread and context per device)\n"
+    "      --gpus <N>                     Use devices 0..N-1 (one host thread and context per device, joined in a peer group)\n"
     "      --ref-shard-mb <MB>            Cross --knn: load and compare the references in shards of this size, the next\n"
     "                                     shard loading while the previous one is compared [default: 4096]\n"
     "  -v, --verbose                      Show progress messages\n"
@@ -295,23 +298,83 @@ struct Pinned {
     ~Pinned() { skd_host_free(ctx, p); }
 };
 
-// ---- --gpus N for sparse (kNN) outputs: one host thread + context per device, no device-to-device traffic.
-// Self mode (knn <= 64): every device evaluates an equal-pair block of upper-triangle rows ONCE per unordered
-// pair and returns partial lists for all rows (skd_self_knn_partial).  Cross mode: the references are sharded,
-// each device loads only its part of the .skd (skd_cross_knn_partial).  The partial lists (rows x knn x 12 B per
-// device) are merged on the first device (skd_knn_merge).  Self mode with knn > 64 splits the rows instead.
+// ---- --gpus N: one host thread + context per device, joined in a peer group of the library (skd_comm_*).
+// Every device reads only its 1/N of the .skd (skd_comm_db_load_skd: the other slices arrive over NVLink).
+// Sparse self mode: every device evaluates an equal-pair block of upper-triangle rows, the partial lists are merged
+// out of peer memory and the final rows gathered on device 0 (skd_comm_self_dists_knn).  Sparse cross mode: the
+// references are sharded over the devices and, per device, streamed through HBM in shards of --ref-shard-mb (the next
+// shard loads while the previous one is compared); the per-shard lists are folded, merged across the devices and
+// gathered on device 0 (skd_comm_knn_merge).  Dense outputs: see dense_multi below.
 struct KnnOut {
     std::vector<uint64_t> idx;
     std::vector<float> d0, d1;
     uint64_t rows = 0, knn = 0;
 };
 
-uint64_t triangle_bound(uint64_t n, int r, int world) {  // same rule as sketchlib.rust_b200.triangle_row_partition
-    if (r <= 0) return 0;
-    if (r >= world) return n;
-    double x = (double)n * (1.0 - std::sqrt(1.0 - (double)r / world));
-    uint64_t b = (uint64_t)std::llround(x / 64.0) * 64;
-    return std::min(n, b);
+// Peer group of `world` worker threads: creates the contexts and windows, exchanges the handles, runs
+// body(rank, ctx, comm) on every thread and tears everything down once all threads are done.
+struct Rendezvous {
+    std::mutex m;
+    std::condition_variable cv;
+    int arrived = 0, generation = 0;
+    bool broken = false;
+    bool wait(int world) {  // false if a rank failed before everybody arrived
+        std::unique_lock<std::mutex> lk(m);
+        if (broken) return false;
+        const int gen = generation;
+        if (++arrived == world) {
+            arrived = 0;
+            ++generation;
+            cv.notify_all();
+            return true;
+        }
+        cv.wait(lk, [&] { return generation != gen || broken; });
+        return !broken;
+    }
+    void abort() {
+        std::lock_guard<std::mutex> lk(m);
+        broken = true;
+        cv.notify_all();
+    }
+};
+
+void run_peer_group(int world, int first_device, size_t window_bytes,
+                    const std::function<void(int, skd_ctx *, skd_comm *)> &body) {
+    std::vector<skd_ctx *> ctxs(world, nullptr);
+    std::vector<skd_comm *> comms(world, nullptr);
+    std::vector<unsigned char> handles((size_t)world * SKD_COMM_HANDLE_BYTES);
+    std::vector<std::string> errs(world);
+    Rendezvous gate;
+    auto worker = [&](int d) {
+        try {
+            // more ranks than devices (--gpus N on a smaller box): the ranks share the devices round robin
+            const int n_dev = std::max(1, skd_device_count());
+            const int dev = world == 1 ? first_device : d % n_dev;
+            if (skd_ctx_create(dev, &ctxs[d]) != SKD_OK)
+                throw std::runtime_error("device " + std::to_string(dev) + ": " + skd_last_error(nullptr));
+            auto chk = [&](skd_status st, const char *what) {
+                if (st != SKD_OK) throw std::runtime_error(std::string(what) + ": " + skd_last_error(ctxs[d]));
+            };
+            chk(skd_comm_create(ctxs[d], d, world, window_bytes, &comms[d]), "peer window");
+            chk(skd_comm_export(comms[d], handles.data() + (size_t)d * SKD_COMM_HANDLE_BYTES), "peer handle");
+            if (!gate.wait(world)) return;
+            chk(skd_comm_connect(comms[d], handles.data()), "peer connect");
+            if (!gate.wait(world)) return;
+            body(d, ctxs[d], comms[d]);
+        } catch (const std::exception &e) {
+            errs[d] = e.what();
+            gate.abort();
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int d = 0; d < world; ++d) pool.emplace_back(worker, d);
+    for (auto &t : pool) t.join();
+    for (int d = 0; d < world; ++d) {  // only now: a failing rank must not pull its window from under its peers
+        if (comms[d]) skd_comm_destroy(comms[d]);
+        if (ctxs[d]) skd_ctx_destroy(ctxs[d]);
+    }
+    for (auto &e : errs)
+        if (!e.empty()) throw std::runtime_error(e);
 }
 
 KnnOut multi_gpu_knn(const DistArgs &a, const MultiSketch &refs, const std::string &ref_prefix,
@@ -322,11 +385,15 @@ KnnOut multi_gpu_knn(const DistArgs &a, const MultiSketch &refs, const std::stri
     const bool cross = queries != nullptr;
     const uint64_t rows = cross ? queries->number_samples_loaded() : n;
     const bool with_aux = dt.kind == SKD_CORE_ACC;
-    const bool partial = cross || nn <= 64;
-    std::vector<std::vector<uint64_t>> keys(world);
-    std::vector<std::vector<float>> aux(world), pd0(world), pd1(world);
-    std::vector<std::string> errs(world);
-    std::vector<std::pair<uint64_t, uint64_t>> ranges(world);
+    const std::string ref_skd = ref_prefix + ".skd", q_skd = q_prefix + ".skd";
+    KnnOut out;
+    out.rows = rows;
+    out.knn = nn;
+    out.idx.resize(rows * nn);
+    out.d0.resize(rows * nn);
+    if (with_aux) out.d1.resize(rows * nn);
+    size_t window = skd_comm_window_bytes_knn(rows, nn, world);
+    window = std::max(window, skd_comm_window_bytes_db(cross ? rows : n, refs.sketchsize64, (uint32_t)refs.kmer_lengths.size(), world));
     auto file_indices = [&](uint64_t lo, uint64_t hi) {
         std::vector<uint64_t> v(hi - lo);
         // no subset: file POSITION, like the reference's read_sketch_data (multisketch.rs:167-184); after `delete`
@@ -334,132 +401,245 @@ KnnOut multi_gpu_knn(const DistArgs &a, const MultiSketch &refs, const std::stri
         for (uint64_t s = lo; s < hi; ++s) v[s - lo] = subset_idx ? (*subset_idx)[s] : s;
         return v;
     };
-    auto worker = [&](int d) {
-        skd_ctx *ctx = nullptr;
-        skd_db *rdb = nullptr, *qdb = nullptr;
-        auto fail = [&](const char *what) {
-            errs[d] = std::string(what) + ": " + skd_last_error(ctx);
+    run_peer_group(world, a.gpu, window, [&](int d, skd_ctx *ctx, skd_comm *comm) {
+        auto chk = [&](skd_status st, const char *what) {
+            if (st != SKD_OK) throw std::runtime_error(std::string(what) + ": " + skd_last_error(ctx));
         };
-        const int dev = world == 1 ? a.gpu : d;
-        if (skd_ctx_create(dev, &ctx) != SKD_OK) {
-            errs[d] = std::string("device ") + std::to_string(dev) + ": " + skd_last_error(nullptr);
+        struct Db {
+            skd_db *p = nullptr;
+            ~Db() {
+                if (p) skd_db_free(p);
+            }
+        };
+        uint64_t *oi = d == 0 ? out.idx.data() : nullptr;
+        float *o0 = d == 0 ? out.d0.data() : nullptr, *o1 = d == 0 && with_aux ? out.d1.data() : nullptr;
+        if (!cross) {
+            Db db;
+            chk(skd_comm_db_load_skd(comm, ref_skd.c_str(), subset_idx ? subset_idx->data() : nullptr, n, refs.sample_stride,
+                                     refs.kmer_stride, refs.sketchsize64, refs.sketch_size, refs.kmer_lengths.data(),
+                                     (uint32_t)refs.kmer_lengths.size(), &db.p),
+                "loading references");
+            chk(skd_comm_self_dists_knn(comm, db.p, nn, dt, ref_c, a.completeness_cutoff, 0, oi, o0, o1, SKD_HOST), "self kNN");
             return;
         }
-        do {
-            const uint64_t lo = cross ? n * d / world : 0, hi = cross ? n * (d + 1) / world : n;  // references of this device
-            auto load_refs = [&](skd_ctx *c, uint64_t s0, uint64_t s1, skd_db **out) {
-                std::vector<uint64_t> fi = file_indices(s0, s1);
-                return skd_db_load_skd(c, (ref_prefix + ".skd").c_str(), fi.data(), s1 - s0, refs.sample_stride,
-                                       refs.kmer_stride, refs.sketchsize64, refs.sketch_size, refs.kmer_lengths.data(),
-                                       (uint32_t)refs.kmer_lengths.size(), out) == SKD_OK;
-            };
-            if (cross) {
-                if (skd_db_load_skd(ctx, (q_prefix + ".skd").c_str(), nullptr, rows, queries->sample_stride,
-                                    queries->kmer_stride, queries->sketchsize64, queries->sketch_size,
-                                    queries->kmer_lengths.data(), (uint32_t)queries->kmer_lengths.size(), &qdb) != SKD_OK) {
-                    fail("loading queries");
-                    break;
-                }
-                // Reference shards of this device: shard i + 1 is read by a loader thread with its own context while
-                // shard i is compared, so file I/O + PCIe overlap the kernels and the references never have to fit
-                // in HBM at once.  Every shard yields one partial list set (merged at the end with the other devices').
-                uint64_t per_shard = std::max<uint64_t>(64, ((uint64_t)a.ref_shard_mb << 20) / (refs.sample_stride * 8) / 64 * 64);
-                const uint64_t max_parts = std::max<uint64_t>(1, 64 / (uint64_t)world);  // the final merge handles 64 lists
-                per_shard = std::max(per_shard, ((hi - lo + max_parts - 1) / max_parts + 63) / 64 * 64);
-                const uint64_t ns = hi > lo ? (hi - lo + per_shard - 1) / per_shard : 0;
-                keys[d].resize(ns * rows * nn);
-                if (with_aux) aux[d].resize(ns * rows * nn);
-                skd_ctx *lctx = nullptr;
-                if (ns > 1 && skd_ctx_create(dev, &lctx) != SKD_OK) {
-                    errs[d] = std::string("device ") + std::to_string(dev) + ": " + skd_last_error(nullptr);
-                    break;
-                }
-                skd_db *next = nullptr;
-                bool next_ok = ns == 0 || load_refs(ctx, lo, std::min(hi, lo + per_shard), &next);
-                if (!next_ok) fail("loading references");
-                for (uint64_t i = 0; i < ns && errs[d].empty(); ++i) {
-                    rdb = next;
-                    next = nullptr;
-                    const uint64_t s0 = lo + i * per_shard;
-                    std::thread loader;
-                    std::string load_err;
-                    if (i + 1 < ns)
-                        loader = std::thread([&, i] {
-                            const uint64_t n0 = lo + (i + 1) * per_shard;
-                            if (!load_refs(lctx, n0, std::min(hi, n0 + per_shard), &next))
-                                load_err = std::string("loading references: ") + skd_last_error(lctx);
-                        });
-                    if (skd_cross_knn_partial(ctx, rdb, qdb, nn, dt, ref_c ? ref_c + s0 : nullptr, query_c,
-                                              a.completeness_cutoff, s0, keys[d].data() + i * rows * nn,
-                                              with_aux ? aux[d].data() + i * rows * nn : nullptr, SKD_HOST) != SKD_OK)
-                        fail("cross kNN");
-                    skd_db_free(rdb);
-                    rdb = nullptr;
-                    if (loader.joinable()) loader.join();
-                    if (!load_err.empty()) errs[d] = load_err;
-                    if (next && skd_db_adopt(ctx, next) != SKD_OK) fail("adopting a reference shard");
-                }
-                if (next) skd_db_free(next);
-                if (lctx) skd_ctx_destroy(lctx);
-                break;
+        Db qdb;
+        chk(skd_comm_db_load_skd(comm, q_skd.c_str(), nullptr, rows, queries->sample_stride, queries->kmer_stride,
+                                 queries->sketchsize64, queries->sketch_size, queries->kmer_lengths.data(),
+                                 (uint32_t)queries->kmer_lengths.size(), &qdb.p),
+            "loading queries");
+        // references of this device, streamed through HBM in shards
+        uint64_t lo, hi;
+        skd_slice_rows(n, d, world, 64, &lo, &hi);
+        auto load_refs = [&](skd_ctx *c, uint64_t s0, uint64_t s1, skd_db **o) {
+            std::vector<uint64_t> fi = file_indices(s0, s1);
+            return skd_db_load_skd(c, ref_skd.c_str(), fi.data(), s1 - s0, refs.sample_stride, refs.kmer_stride,
+                                   refs.sketchsize64, refs.sketch_size, refs.kmer_lengths.data(),
+                                   (uint32_t)refs.kmer_lengths.size(), o) == SKD_OK;
+        };
+        uint64_t per_shard = std::max<uint64_t>(64, ((uint64_t)a.ref_shard_mb << 20) / (refs.sample_stride * 8) / 64 * 64);
+        const uint64_t max_parts = 32;  // lists folded per device
+        per_shard = std::max(per_shard, ((hi - lo + max_parts - 1) / max_parts + 63) / 64 * 64);
+        const uint64_t ns = hi > lo ? (hi - lo + per_shard - 1) / per_shard : 0;
+        const uint64_t np = std::max<uint64_t>(1, ns);
+        std::vector<uint64_t> keys(np * rows * nn, ~0ull);  // a device without references contributes only padding
+        std::vector<float> aux(with_aux ? np * rows * nn : 0, 0.f);
+        skd_ctx *lctx = nullptr;
+        if (ns > 1 && skd_ctx_create(skd_ctx_device(ctx), &lctx) != SKD_OK)
+            throw std::runtime_error(std::string("loader context: ") + skd_last_error(nullptr));
+        struct LoaderCtx {
+            skd_ctx *&c;
+            ~LoaderCtx() {
+                if (c) skd_ctx_destroy(c);
             }
-            if (!load_refs(ctx, 0, n, &rdb)) {
-                fail("loading references");
-                break;
-            }
-            if (partial) {
-                const uint64_t r0 = triangle_bound(n, d, world), r1 = triangle_bound(n, d + 1, world);
-                keys[d].resize(n * nn);
-                if (with_aux) aux[d].resize(n * nn);
-                if (skd_self_knn_partial(ctx, rdb, nn, dt, ref_c, a.completeness_cutoff, r0, r1, keys[d].data(),
-                                         with_aux ? aux[d].data() : nullptr, SKD_HOST) != SKD_OK)
-                    fail("self kNN");
-            } else {
-                const uint64_t r0 = n * d / world, r1 = n * (d + 1) / world;
-                ranges[d] = {r0, r1};
-                keys[d].resize((r1 - r0) * nn);  // neighbour indices of this device's rows
-                pd0[d].resize((r1 - r0) * nn);
-                if (with_aux) pd1[d].resize((r1 - r0) * nn);
-                if (skd_self_dists_knn(ctx, rdb, nn, dt, ref_c, a.completeness_cutoff, r0, r1, keys[d].data(), pd0[d].data(),
-                                       with_aux ? pd1[d].data() : nullptr, SKD_HOST) != SKD_OK)
-                    fail("self kNN");
-            }
-        } while (false);
-        if (rdb) skd_db_free(rdb);
-        if (qdb) skd_db_free(qdb);
-        skd_ctx_destroy(ctx);
-    };
-    std::vector<std::thread> pool;
-    for (int d = 0; d < world; ++d) pool.emplace_back(worker, d);
-    for (auto &t : pool) t.join();
-    for (auto &e : errs)
-        if (!e.empty()) throw std::runtime_error(e);
-    KnnOut out;
-    out.rows = rows;
-    out.knn = nn;
-    out.idx.resize(rows * nn);
-    out.d0.resize(rows * nn);
-    if (with_aux) out.d1.resize(rows * nn);
-    if (!partial) {  // row-split: concatenate
-        for (int d = 0; d < world; ++d) {
-            std::copy(keys[d].begin(), keys[d].end(), out.idx.begin() + ranges[d].first * nn);
-            std::copy(pd0[d].begin(), pd0[d].end(), out.d0.begin() + ranges[d].first * nn);
-            if (with_aux) std::copy(pd1[d].begin(), pd1[d].end(), out.d1.begin() + ranges[d].first * nn);
+        } loader_guard{lctx};
+        Db next;
+        if (ns > 0 && !load_refs(ctx, lo, std::min(hi, lo + per_shard), &next.p)) chk(SKD_ERR_IO, "loading references");
+        for (uint64_t i = 0; i < ns; ++i) {
+            Db cur;
+            std::swap(cur.p, next.p);
+            const uint64_t s0 = lo + i * per_shard;
+            std::thread loader;
+            std::string load_err;
+            if (i + 1 < ns)
+                loader = std::thread([&, i] {
+                    const uint64_t n0 = lo + (i + 1) * per_shard;
+                    if (!load_refs(lctx, n0, std::min(hi, n0 + per_shard), &next.p))
+                        load_err = std::string("loading references: ") + skd_last_error(lctx);
+                });
+            const skd_status st = skd_cross_knn_partial(ctx, cur.p, qdb.p, nn, dt, ref_c ? ref_c + s0 : nullptr, query_c,
+                                                        a.completeness_cutoff, s0, keys.data() + i * rows * nn,
+                                                        with_aux ? aux.data() + i * rows * nn : nullptr, SKD_HOST);
+            if (loader.joinable()) loader.join();
+            chk(st, "cross kNN");
+            if (!load_err.empty()) throw std::runtime_error(load_err);
+            if (next.p) chk(skd_db_adopt(ctx, next.p), "adopting a reference shard");
         }
-        return out;
-    }
-    std::vector<uint64_t> all_keys;
-    std::vector<float> all_aux;
-    for (int d = 0; d < world; ++d) {  // every device contributes one list set (self) or one per reference shard (cross)
-        all_keys.insert(all_keys.end(), keys[d].begin(), keys[d].end());
-        if (with_aux) all_aux.insert(all_aux.end(), aux[d].begin(), aux[d].end());
-    }
-    const uint32_t n_parts = (uint32_t)(all_keys.size() / std::max<uint64_t>(1, rows * nn));
-    Gpu g0;
-    if (skd_ctx_create(world == 1 ? a.gpu : 0, &g0.ctx) != SKD_OK) throw std::runtime_error(skd_last_error(nullptr));
-    g0.check(skd_knn_merge(g0.ctx, all_keys.data(), with_aux ? all_aux.data() : nullptr, n_parts, rows, nn, dt,
-                           SKD_HOST, out.idx.data(), out.d0.data(), with_aux ? out.d1.data() : nullptr, SKD_HOST));
+        chk(skd_comm_knn_merge(comm, keys.data(), with_aux ? aux.data() : nullptr, (uint32_t)np, SKD_HOST, rows, nn, dt, 0, oi,
+                               o0, o1, SKD_HOST),
+            "merging the partial lists");
+    });
     return out;
+}
+
+// ---- dense outputs on several devices.  The rows are cut into chunks of about 128 MB of results; chunk c is computed by
+// device c % N into one of that device's two pinned buffers (the kernels write them directly), and the main thread
+// formats and writes the chunks in row order while the devices work ahead: disjoint slices of the reference's
+// DistanceMatrix, no exchange between the devices (src/distances/mod.rs:58-130, 227-297).
+void dense_multi(const DistArgs &a, Out &out, const MultiSketch &refs, const std::string &ref_prefix,
+                 const std::vector<uint64_t> *subset_idx, const MultiSketch *queries, const std::string &q_prefix,
+                 skd_dist_type dt, const double *ref_c, const double *query_c) {
+    const int world = a.gpus;
+    const uint64_t n = refs.number_samples_loaded();
+    const bool cross = queries != nullptr;
+    const uint64_t nq = cross ? queries->number_samples_loaded() : 0;
+    const int ncols = dt.kind == SKD_CORE_ACC ? 2 : 1;
+    const size_t kChunkBytes = (size_t)128 << 20;
+    const uint64_t width = cross ? nq : n;
+    const uint64_t rows_per = std::max<uint64_t>(64, kChunkBytes / std::max<uint64_t>(1, width * ncols * 4) / 64 * 64);
+    const uint64_t last_row = cross ? n : (n >= 2 ? n - 1 : 0);  // self: the last row has no pairs
+    struct Chunk {
+        uint64_t r0, r1;
+    };
+    std::vector<Chunk> chunks;
+    for (uint64_t r0 = 0; r0 < last_row; r0 += rows_per) chunks.push_back({r0, std::min(cross ? n : n, r0 + rows_per)});
+    if (chunks.empty()) return;
+    auto elems = [&](const Chunk &c) {
+        return cross ? (c.r1 - c.r0) * nq : skd_self_pairs_in_rows(n, c.r0, c.r1);
+    };
+    size_t buf_elems = 0;
+    for (auto &c : chunks) buf_elems = std::max<size_t>(buf_elems, elems(c));
+    // slot s of device d holds chunk `holds`; state 0 = free, 1 = full
+    struct Slot {
+        void *p = nullptr;
+        int state = 0;
+        size_t chunk = 0;
+    };
+    std::vector<std::array<Slot, 2>> slots(world);
+    std::mutex m;
+    std::condition_variable cv;
+    bool failed = false;
+    const std::string ref_skd = ref_prefix + ".skd", q_skd = q_prefix + ".skd";
+    size_t window = skd_comm_window_bytes_db(n, refs.sketchsize64, (uint32_t)refs.kmer_lengths.size(), world);
+    if (cross) window = std::max(window, skd_comm_window_bytes_db(nq, refs.sketchsize64, (uint32_t)refs.kmer_lengths.size(), world));
+    std::exception_ptr writer_err;
+    std::thread writer([&] {
+        try {
+            for (size_t c = 0; c < chunks.size(); ++c) {
+                const int d = (int)(c % world);
+                Slot *s = nullptr;
+                {
+                    std::unique_lock<std::mutex> lk(m);
+                    cv.wait(lk, [&] {
+                        for (auto &sl : slots[d])
+                            if (sl.state == 1 && sl.chunk == c) s = &sl;
+                        return s != nullptr || failed;
+                    });
+                    if (failed) return;
+                }
+                const Chunk &ch = chunks[c];
+                const float *base = (const float *)s->p;
+                if (cross) {
+                    write_rows(out, ch.r0, ch.r1, (int)a.threads, [&](uint64_t i, std::string &txt) {
+                        const float *dd = base + (i - ch.r0) * nq * ncols;
+                        const std::string &rn = refs.sketch_name(i);
+                        for (uint64_t j = 0; j < nq; ++j, dd += ncols)
+                            append_line(txt, rn, queries->sketch_name(j), dd[0], ncols == 2 ? dd + 1 : nullptr);
+                    });
+                } else {
+                    write_rows(out, ch.r0, std::min(ch.r1, n - 1), (int)a.threads, [&](uint64_t i, std::string &txt) {
+                        const float *dd = base + skd_self_pairs_in_rows(n, ch.r0, i) * ncols;
+                        const std::string &rn = refs.sketch_name(i);
+                        for (uint64_t j = i + 1; j < n; ++j, dd += ncols)
+                            append_line(txt, rn, refs.sketch_name(j), dd[0], ncols == 2 ? dd + 1 : nullptr);
+                    });
+                }
+                {
+                    std::lock_guard<std::mutex> lk(m);
+                    s->state = 0;
+                }
+                cv.notify_all();
+            }
+        } catch (...) {
+            writer_err = std::current_exception();
+            std::lock_guard<std::mutex> lk(m);
+            failed = true;
+            cv.notify_all();
+        }
+    });
+    std::exception_ptr group_err;
+    try {
+        run_peer_group(world, a.gpu, window, [&](int d, skd_ctx *ctx, skd_comm *comm) {
+            auto chk = [&](skd_status st, const char *what) {
+                if (st != SKD_OK) throw std::runtime_error(std::string(what) + ": " + skd_last_error(ctx));
+            };
+            skd_db *rdb = nullptr, *qdb = nullptr;
+            try {
+                for (auto &sl : slots[d]) chk(skd_host_alloc(ctx, buf_elems * ncols * 4 + 16, &sl.p), "result buffer");
+                chk(skd_comm_db_load_skd(comm, ref_skd.c_str(), subset_idx ? subset_idx->data() : nullptr, n, refs.sample_stride,
+                                         refs.kmer_stride, refs.sketchsize64, refs.sketch_size, refs.kmer_lengths.data(),
+                                         (uint32_t)refs.kmer_lengths.size(), &rdb),
+                    "loading references");
+                if (cross)
+                    chk(skd_comm_db_load_skd(comm, q_skd.c_str(), nullptr, nq, queries->sample_stride, queries->kmer_stride,
+                                             queries->sketchsize64, queries->sketch_size, queries->kmer_lengths.data(),
+                                             (uint32_t)queries->kmer_lengths.size(), &qdb),
+                        "loading queries");
+                for (size_t c = (size_t)d; c < chunks.size(); c += world) {
+                    Slot *s = nullptr;
+                    {
+                        std::unique_lock<std::mutex> lk(m);
+                        cv.wait(lk, [&] {
+                            for (auto &sl : slots[d])
+                                if (sl.state == 0) s = &sl;
+                            return s != nullptr || failed;
+                        });
+                        if (failed) break;
+                    }
+                    const Chunk &ch = chunks[c];
+                    if (cross)
+                        chk(skd_cross_dists_all(ctx, rdb, qdb, dt, ref_c, query_c, a.completeness_cutoff, ch.r0, ch.r1,
+                                                (float *)s->p, SKD_HOST),
+                            "dense distances");
+                    else
+                        chk(skd_self_dists_all(ctx, rdb, dt, ref_c, a.completeness_cutoff, ch.r0, ch.r1, (float *)s->p, SKD_HOST),
+                            "dense distances");
+                    {
+                        std::lock_guard<std::mutex> lk(m);
+                        s->chunk = c;
+                        s->state = 1;
+                    }
+                    cv.notify_all();
+                }
+                {   // the buffers are read by the writer until the last chunk of this device is out
+                    std::unique_lock<std::mutex> lk(m);
+                    cv.wait(lk, [&] { return failed || (slots[d][0].state == 0 && slots[d][1].state == 0); });
+                }
+            } catch (...) {
+                {
+                    std::lock_guard<std::mutex> lk(m);
+                    failed = true;
+                }
+                cv.notify_all();
+                if (rdb) skd_db_free(rdb);
+                if (qdb) skd_db_free(qdb);
+                for (auto &sl : slots[d])
+                    if (sl.p) skd_host_free(ctx, sl.p);
+                throw;
+            }
+            if (rdb) skd_db_free(rdb);
+            if (qdb) skd_db_free(qdb);
+            for (auto &sl : slots[d])
+                if (sl.p) skd_host_free(ctx, sl.p);
+        });
+    } catch (...) {
+        group_err = std::current_exception();
+        std::lock_guard<std::mutex> lk(m);
+        failed = true;
+        cv.notify_all();
+    }
+    writer.join();
+    if (group_err) std::rethrow_exception(group_err);
+    if (writer_err) std::rethrow_exception(writer_err);
 }
 
 int run(const DistArgs &a) {
@@ -516,6 +696,9 @@ int run(const DistArgs &a) {
     // references are then streamed through HBM shard by shard, each loaded while the previous one is compared.
     const bool sharded_refs = a.has_query && a.knn >= 0 &&
                               n * refs.meta.sample_stride * 8 > ((uint64_t)a.ref_shard_mb << 20);
+    if (a.gpus > 1 && skd_device_count() > 0 && skd_device_count() < a.gpus)
+        log_warn("--gpus " + std::to_string(a.gpus) + " but only " + std::to_string(skd_device_count()) +
+                 " device(s) visible: the ranks share them");
     if ((a.gpus > 1 || sharded_refs) && a.knn >= 0) {
         Out out(a);
         skd_dist_type dt;
@@ -561,7 +744,33 @@ int run(const DistArgs &a) {
         out.flush();
         return 0;
     }
-    if (a.gpus > 1) log_info("--gpus applies to --knn runs; dense output uses device " + std::to_string(a.gpu));
+    if (a.gpus > 1) {  // dense outputs: disjoint row chunks per device, written in row order
+        Out out(a);
+        skd_dist_type dt;
+        dt.kind = a.kmer < 0 ? SKD_CORE_ACC : (a.ani ? SKD_ANI : SKD_JACCARD);
+        dt.k_idx = a.kmer < 0 ? 0 : (int32_t)*refs.meta.get_k_idx((uint64_t)a.kmer);
+        if (dt.kind == SKD_CORE_ACC) {
+            if (refs.meta.kmer_lengths.size() < 2)
+                throw Panic("Need at least two k-mer lengths to calculate core/accessory distances");
+            log_info("Distances: core/accessory regression");
+        } else {
+            log_info(std::string(dt.kind == SKD_ANI ? "Distances: ANI at k=" : "Distances: Jaccard distances at k=") +
+                     std::to_string(a.kmer));
+        }
+        if (a.has_query && !refs.meta.is_compatible_with(queries.meta))
+            throw std::runtime_error("reference and query databases differ in sketch size or k-mer lengths");
+        log_info(std::string(a.has_query ? "Calculating all ref vs query distances" : "Calculating all ref vs ref distances") +
+                 " on " + std::to_string(a.gpus) + " devices");
+        const bool any = a.has_query ? (n > 0 && queries.meta.number_samples_loaded() > 0) : n >= 2;
+        if (any) {
+            log_info("Writing out in long matrix form");
+            dense_multi(a, out, refs.meta, ref_name, a.subset.empty() ? nullptr : &subset_idx,
+                        a.has_query ? &queries.meta : nullptr, qname, dt, has_ref_c ? ref_c.data() : nullptr,
+                        has_query_c ? query_c.data() : nullptr);
+        }
+        out.flush();
+        return 0;
+    }
 
     // ---- device phase
     Out out(a);

@@ -1,0 +1,112 @@
+// Internals of libsketchdist shared by capi.cu (single-device entry points) and peer.cu (peer groups of several
+// devices): context / database objects and the host-side drivers the multi-device operations are built from.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/sketchdist.h"
+#include "kernels.h"
+#include "layout.h"
+
+namespace skdi {
+constexpr size_t kMaxSmem = 232448;           // 227 KB opt-in dynamic shared memory per CTA on sm_100
+constexpr uint32_t kSymKnnMax = 64;           // symmetric self-kNN keeps 128-slot lists: knn + 64 candidates per step
+}  // namespace skdi
+
+struct skd_ctx {
+    int device = 0;
+    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaStream_t aux[2] = {nullptr, nullptr};  // async-upload dense runs: re-tiling / every other column band
+    std::string err;
+    uint64_t launches = 0;
+    float last_ms = 0.f;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> timers;  // event pairs around kernel launches of a call
+    std::vector<int> timer_tags;  // 1 = a tile_kernel / stream_kernel launch (the path's dominant kernel)
+    size_t timers_used = 0;
+    float last_tile_ms = 0.f;
+    cudaEvent_t ev_a[2] = {nullptr, nullptr}, ev_b[2] = {nullptr, nullptr};
+    std::map<std::string, std::pair<void *, size_t>> scratch;  // named device buffers reused across calls
+    void *pinned[2] = {nullptr, nullptr};
+    size_t pinned_bytes = 0;
+    int sm_count = 148;
+    bool knn_symmetric = true;  // SKD_KNN_SYMMETRIC=0: whole-matrix self kNN evaluates both (i,j) and (j,i)
+    bool zero_copy = true;   // dense kernels store straight into pinned host results (SKD_ZEROCOPY=0 disables)
+    // Tunables, read once from the environment when the context is created.
+    size_t upload_chunk_bytes = 64ull << 20;  // SKD_UPLOAD_CHUNK_MB: staging chunk of a pageable/file upload
+    size_t result_chunk_bytes = 64ull << 20;  // SKD_RESULT_CHUNK_MB: staged D2H chunk of dense results
+    uint32_t group = 8;                       // SKD_GROUP: row blocks per L2 group of the tile scheduler
+    size_t sym_chunk_bytes = 2ull << 30;      // SKD_SYM_CHUNK_MB: HBM key buffer of one symmetric-kNN row group
+    uint64_t few_queries = 1ull << 20;        // SKD_FEW_QUERIES: cross kNN up to this many queries goes dense keys + select
+    size_t read_threads = 8;                  // SKD_READ_THREADS: host threads copying an .skd chunk into pinned staging
+                                              // (default: the host's hardware threads, at most 16)
+};
+
+struct skd_db {
+    skd_ctx *ctx = nullptr;
+    skd::DevDb dev{};
+    uint32_t *tiled = nullptr;
+    size_t tiled_bytes = 0;
+    std::vector<uint64_t> kmers;
+    uint64_t sketch_size = 0, W = 0, n = 0;
+    double *lny_dev = nullptr;  // [nbins + 1]
+    // skd_db_upload_async: the raw planes are still arriving (copy stream, one event per chunk of whole sample
+    // blocks); they are re-tiled by the first compute call -- band by band, interleaved with the tile kernel, when
+    // that call is a dense self run, so that the PCIe transfer overlaps the distance computation.
+    struct Pending {
+        uint64_t *raw = nullptr;                 // device copy in the reference layout
+        uint64_t sample_stride = 0, kmer_stride = 0;
+        std::vector<cudaEvent_t> ready;          // chunk c has arrived
+        std::vector<uint32_t> block_end;         // chunk c covers sample blocks [block_end[c-1], block_end[c])
+    } pending;
+    bool is_pending() const { return pending.raw != nullptr; }
+};
+
+namespace skdi {
+
+skd_status fail(skd_ctx *ctx, skd_status st, const char *fmt, ...);
+
+#define CU(ctx, expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (expr);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return skdi::fail(ctx, SKD_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, \
+                              __LINE__);                                                                \
+    } while (0)
+
+cudaError_t preload_peer_kernels();  // peer.cu
+skd_status scratch_get(skd_ctx *ctx, const char *name, size_t bytes, void **out);
+void timers_reset(skd_ctx *ctx);
+skd_status timer_begin(skd_ctx *ctx, cudaStream_t stream = nullptr, int tag = 0);
+skd_status timer_end(skd_ctx *ctx, cudaStream_t stream = nullptr);
+skd_status timers_collect(skd_ctx *ctx);  // call after the compute stream is idle
+
+skd_status build_epi(skd_ctx *ctx, const skd_db *A, const skd_db *B, skd_dist_type dist, const double *a_comp,
+                     const double *b_comp, double cutoff, skd::EpiParams *E);
+skd_status check_pair(skd_ctx *ctx, const skd_db *A, const skd_db *B, bool keep_pending = false);
+
+// Row-owned kNN (capi.cu): final sparse rows, or (key_out set) one sorted composite list per row.
+skd_status run_knn(skd_ctx *ctx, const skd_db *R, const skd_db *Q, bool self, const skd::EpiParams &E, uint64_t knn,
+                   uint64_t row_begin, uint64_t row_end, uint64_t *idx_out, float *d0_out, float *d1_out, skd_loc out_loc,
+                   uint64_t *key_out = nullptr, float *aux_out = nullptr, uint64_t idx_offset = 0);
+// Symmetric self-kNN over triangle rows [row_begin, row_end): lists dkey/daux [n][knn] in device memory.
+skd_status run_knn_symmetric(skd_ctx *ctx, const skd_db *db, const skd::EpiParams &E, uint64_t knn, uint64_t row_begin,
+                             uint64_t row_end, unsigned long long *dkey, float *daux);
+
+// Source of a database build: an array in the reference layout (host or device), an .skd file, or nothing
+// (allocate only: the tiled planes are filled by the caller, peer.cu gathers them from the peers' slices).
+struct ChunkSource {
+    const uint64_t *direct = nullptr;  // array in the reference layout (host or device)
+    skd_loc loc = SKD_HOST;
+    int fd = -1;                       // .skd file
+    const uint64_t *indices = nullptr; // file positions, nullable
+    bool async = false;                // pinned host array: return once the copies are queued (skd_db_upload_async)
+    bool alloc_only = false;
+};
+skd_status db_build(skd_ctx *ctx, const ChunkSource &src, uint64_t n, uint64_t sample_stride, uint64_t kmer_stride,
+                    uint64_t W, uint64_t sketch_size, const uint64_t *kmers, uint32_t K, skd_db **out);
+
+}  // namespace skdi

@@ -171,15 +171,6 @@ __device__ __forceinline__ void regress(double ysum, double xysum, double ysq, i
     acc_out = (float)acc;
 }
 
-// Total-order key for non-NaN floats, so that (key, idx) sorts as one u64.
-__device__ __forceinline__ uint32_t float_order_bits(float f) {
-    uint32_t b = __float_as_uint(f);
-    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
-}
-__device__ __forceinline__ float float_from_order_bits(uint32_t b) {
-    return __uint_as_float((b & 0x80000000u) ? (b & 0x7fffffffu) : ~b);
-}
-
 // ------------------------------------------------------------------------------------------------
 // The tile kernel.
 //
@@ -1415,6 +1406,45 @@ void launch_pairs(const DevDb &A, const DevDb &B, const EpiParams &E, const uint
     const int warps = 8;
     pair_kernel<<<(unsigned)((n_pairs + warps - 1) / warps), warps * 32, 0, st>>>(A, B, E, pairs, n_pairs, counts_out,
                                                                                    dist_out);
+}
+
+// With lazy module loading (the CUDA 12 default) the first launch of a kernel loads it, and that load can wait for
+// the device to go idle.  A peer barrier (peer.cu) spins on the device until the other ranks arrive, so a rank that
+// shares the GPU with a spinning peer must never load code at that moment: every kernel is loaded when a context is
+// created.
+cudaError_t preload_kernels() {
+    cudaFuncAttributes a;
+    cudaError_t e = cudaSuccess;
+#define SKD_PRELOAD(...)                                                              \
+    do {                                                                              \
+        if (e == cudaSuccess) e = cudaFuncGetAttributes(&a, (const void *)(__VA_ARGS__)); \
+    } while (0)
+    SKD_PRELOAD(repack_kernel);
+    SKD_PRELOAD(tile_kernel<uint16_t, 8>);
+    SKD_PRELOAD(tile_kernel<uint16_t, 16>);
+    SKD_PRELOAD(tile_kernel<uint16_t, 32>);
+    SKD_PRELOAD(tile_kernel<uint16_t, TS>);
+    SKD_PRELOAD(tile_kernel<uint32_t, 8>);
+    SKD_PRELOAD(tile_kernel<uint32_t, 16>);
+    SKD_PRELOAD(tile_kernel<uint32_t, 32>);
+    SKD_PRELOAD(tile_kernel<uint32_t, TS>);
+    SKD_PRELOAD(stream_kernel<1>);
+    SKD_PRELOAD(stream_kernel<2>);
+    SKD_PRELOAD(stream_kernel<4>);
+    SKD_PRELOAD(stream_kernel<8>);
+    SKD_PRELOAD(knn_merge_kernel);
+    SKD_PRELOAD(select_few_kernel<true>);
+    SKD_PRELOAD(select_few_kernel<false>);
+    SKD_PRELOAD(select_sym_kernel<true, true>);
+    SKD_PRELOAD(select_sym_kernel<true, false>);
+    SKD_PRELOAD(select_sym_kernel<false, true>);
+    SKD_PRELOAD(select_sym_kernel<false, false>);
+    SKD_PRELOAD(knn_finalize_kernel);
+    SKD_PRELOAD(fill_u64_kernel);
+    SKD_PRELOAD(knn_candidates_kernel);
+    SKD_PRELOAD(pair_kernel);
+#undef SKD_PRELOAD
+    return e;
 }
 
 }  // namespace skd

@@ -43,6 +43,9 @@ cudaError_t launch_knn_candidates(const DevDb &A, const EpiParams &E, const uint
                                   uint64_t n_rows, uint32_t knn, uint32_t cap, int retain, unsigned long long *idx_out,
                                   float *d0_out, cudaStream_t st);
 
+// Loads every kernel of kernels.cu into the current context (see the comment at the definition).
+cudaError_t preload_kernels();
+
 void launch_pairs(const DevDb &A, const DevDb &B, const EpiParams &E, const uint64_t *pairs, uint64_t n_pairs,
                   uint32_t *counts_out, float *dist_out, cudaStream_t st);
 

@@ -41,6 +41,17 @@ __host__ __device__ inline uint64_t slab_index(const DevDb &d, uint32_t k, uint3
     return ((uint64_t)k * d.W + w) * d.nb + b;
 }
 
+#ifdef __CUDACC__
+// Total-order key for non-NaN floats, so that (key, neighbour index) sorts as one u64 composite.
+__device__ __forceinline__ uint32_t float_order_bits(float f) {
+    uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float float_from_order_bits(uint32_t b) {
+    return __uint_as_float((b & 0x80000000u) ? (b & 0x7fffffffu) : ~b);
+}
+#endif
+
 enum : int { KIND_CORE_ACC = 0, KIND_JACCARD = 1, KIND_ANI = 2 };
 
 // Everything the fused epilogue needs.  Tables are indexed by the per-k match count (`samebits`).

@@ -374,10 +374,9 @@ def test_full_pipeline_fasta_to_distances(tools, tmp_path):
 
 
 @pytest.mark.gpu
-def test_cli_multi_gpu_knn_equals_single_gpu(tools, tmp_path):
-    import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+def test_cli_multi_gpu_equals_single_gpu(tools, tmp_path):
+    """--gpus 2 (two ranks of a peer group; on a one-GPU box both ranks share the device) against --gpus 1: sparse self
+    and cross outputs (symmetric partial lists, row split for knn > 64, reference shards) and dense outputs."""
     cli, _ = tools
     ref, qry = synth_pair(700, 90, 16, [17, 21, 25, 29], seed=95, n_families=9)
     ref.names = [f"r{i}" for i in range(700)]
@@ -385,16 +384,20 @@ def test_cli_multi_gpu_knn_equals_single_gpu(tools, tmp_path):
     rp, qp = write_skm_skd(str(tmp_path / "ref"), ref), write_skm_skd(str(tmp_path / "qry"), qry)
     sub = tmp_path / "subset.txt"
     sub.write_text("".join(f"r{i}\n" for i in range(699, 100, -3)))
+    env = dict(os.environ, SKD_PEER_TIMEOUT_S="30")
     for args in (["--knn", "20"], ["--knn", "20", "-k", "21"], ["--knn", "80", "-k", "21", "--ani"], [qp, "--knn", "7"],
-                 [qp, "--knn", "7", "-k", "25"], ["--knn", "5", "--subset", str(sub)]):
+                 [qp, "--knn", "7", "-k", "25"], ["--knn", "5", "--subset", str(sub)],
+                 [], ["-k", "21"], [qp], [qp, "-k", "25", "--ani"], ["--subset", str(sub)]):
         one = run([cli, "dist", rp] + args)
-        two = run([cli, "dist", rp] + args + ["--gpus", "2"])
+        two = run([cli, "dist", rp] + args + ["--gpus", "2", "--threads", "3"], env=env)
         assert one.returncode == 0 and two.returncode == 0, (args, one.stderr, two.stderr)
         assert one.stdout == two.stdout and len(one.stdout) > 0, args
     # both devices stream their half of the references in several shards (700 refs, 1 MB = 128 refs per shard)
     one = run([cli, "dist", rp, qp, "--knn", "9"])
-    two = run([cli, "dist", rp, qp, "--knn", "9", "--gpus", "2", "--ref-shard-mb", "1", "-v"])
+    two = run([cli, "dist", rp, qp, "--knn", "9", "--gpus", "2", "--ref-shard-mb", "1", "-v"], env=env)
     assert two.returncode == 0 and two.stdout == one.stdout and "references in shards" in two.stderr
+    three = run([cli, "dist", rp, qp, "--knn", "9", "--gpus", "3", "-k", "29"], env=env)
+    assert three.returncode == 0 and three.stdout == run([cli, "dist", rp, qp, "--knn", "9", "-k", "29"]).stdout
 
 
 # ---------------------------------------------------------------- inverted index (.ski / .skq) and precluster

@@ -111,9 +111,36 @@ def _shard_worker(rank, world, port, tmp):
     # kNN: even row split
     k0, k1 = sk.row_partition(db.n, rank, world)
     idx, d0, _ = oracle.self_dists_knn(db, 5, k_idx=1, rows=(k0, k1))
+    # symmetric kNN the way the peer group does it: triangle rows per rank (skd_triangle_rows) -> partial lists for ALL
+    # rows (each unordered pair evaluated once, credited to both rows) -> the owner of a row (skd_slice_rows) merges
+    import ctypes as C
+    a, b = C.c_uint64(), C.c_uint64()
+    lib.skd_triangle_rows(db.n, rank, world, C.byref(a), C.byref(b))
+    t0, t1 = a.value, b.value
+    knn = 5
+    tfirst, tcount = int(lib.skd_self_pairs_in_rows(db.n, 0, t0)), int(lib.skd_self_pairs_in_rows(db.n, t0, t1))
+    c0 = tfirst - tfirst % 1000
+    vals = oracle.self_dists_all(db, k_idx=1, first=c0, count=tcount + tfirst - c0)[tfirst - c0:]
+    cand = [[] for _ in range(db.n)]
+    p = 0
+    for i in range(t0, t1):
+        for j in range(i + 1, db.n):
+            cand[i].append((float(vals[p]), j))
+            cand[j].append((float(vals[p]), i))
+            p += 1
+    assert p == tcount
+    partial = [sorted(c)[:knn] for c in cand]
+    lists = [None] * world
+    dist.all_gather_object(lists, partial)
+    lib.skd_slice_rows(db.n, rank, world, 1, C.byref(a), C.byref(b))
+    merged = {r: sorted(sum((lists[q][r] for q in range(world)), []))[:knn] for r in range(a.value, b.value)}
     gathered = [None] * world
-    dist.all_gather_object(gathered, (r0, r1, mine, k0, k1, idx, d0))
+    dist.all_gather_object(gathered, (r0, r1, mine, k0, k1, idx, d0, merged))
     if rank == 0:
+        sym = {}
+        for g in gathered:
+            sym.update(g[7])
+        np.save(os.path.join(tmp, "sym_d0.npy"), np.array([[d for d, _ in sym[r]] for r in range(db.n)], dtype=np.float32))
         np.save(os.path.join(tmp, "dense.npy"), np.concatenate([g[2] for g in gathered]))
         np.save(os.path.join(tmp, "knn_idx.npy"), np.concatenate([g[5] for g in gathered]))
         assert gathered[0][0] == 0 and gathered[-1][1] == db.n and gathered[0][3] == 0 and gathered[-1][4] == db.n
@@ -128,14 +155,23 @@ def test_two_rank_sharding_over_gloo(tmp_path):
     db = synth_db(150, 2, [17, 21, 25], seed=4, n_families=3)
     assert np.array_equal(np.load(tmp_path / "dense.npy"), oracle.self_dists_all(db))
     assert np.array_equal(np.load(tmp_path / "knn_idx.npy"), oracle.self_dists_knn(db, 5, k_idx=1)[0])
+    assert np.array_equal(np.load(tmp_path / "sym_d0.npy"), oracle.self_dists_knn(db, 5, k_idx=1)[1])
 
 
 def test_bench_workload_sizes():
     import bench
-    assert bench.n_for_gpus(1) == 10000 and bench.LOP3_PER_PAIR == 3584 and bench.POPC_PER_PAIR == 256
+    import sketchlib.rust_b200 as sk
+    assert bench.N_KNN == 100000 and bench.KNN == 50                      # BASELINE.json configs[2], every N
+    assert bench.dense_n_for_gpus(1) == 10000 and bench.LOP3_PER_PAIR == 3584 and bench.POPC_PER_PAIR == 256
     for g in (2, 4, 8):
-        n = bench.n_for_gpus(g)
+        n = bench.dense_n_for_gpus(g)
         assert n % 64 == 0 and abs(n * (n - 1) / 2 / g - 49995000) / 49995000 < 0.02
+        # strong-scaled kNN job: the ranks' triangle blocks tile the rows and hold about equal pair counts
+        lib = sk.load_library()
+        parts = [sk.triangle_row_partition(bench.N_KNN, r, g) for r in range(g)]
+        assert parts[0][0] == 0 and parts[-1][1] == bench.N_KNN and all(parts[i][1] == parts[i + 1][0] for i in range(g - 1))
+        pairs = [int(lib.skd_self_pairs_in_rows(bench.N_KNN, a, b)) for a, b in parts]
+        assert sum(pairs) == bench.N_KNN * (bench.N_KNN - 1) // 2 and max(pairs) / (sum(pairs) / g) < 1.006
 
 
 def test_python_multisketch_and_inverted_mirror_the_reference_types(tmp_path):
