@@ -107,7 +107,7 @@ def int_peaks():
     exe = os.path.join(ROOT, "tools", "int_peak")
     if not os.path.exists(exe):
         try:
-            subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-o", exe, exe + ".cu"])
+            subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-o", exe, exe + ".cu", "-ldl"])
         except Exception:
             return None
     try:

@@ -211,8 +211,9 @@ skd_status check_pair(skd_ctx *ctx, const skd_db *A, const skd_db *B, bool keep_
 }
 
 // Group offsets for a dense launch over row blocks [rb0, rb0 + n_rb).
+// `pairs`: the launch goes to dense_kernel, whose tiles span two adjacent column blocks.
 void build_groups(uint32_t group, bool self, uint32_t rb0, uint32_t n_rb, uint32_t nbB, std::vector<uint64_t> *off,
-                  uint32_t cb_lo = 0, uint32_t cb_hi = 0) {
+                  bool pairs, uint32_t cb_lo = 0, uint32_t cb_hi = 0) {
     uint32_t n_groups = (n_rb + group - 1) / group;
     off->assign(n_groups + 1, 0);
     const uint32_t hi = cb_hi ? std::min(cb_hi, nbB) : nbB;
@@ -220,8 +221,14 @@ void build_groups(uint32_t group, bool self, uint32_t rb0, uint32_t n_rb, uint32
         uint32_t rows = std::min(group, n_rb - g * group);
         const uint32_t first = std::max(self ? rb0 + g * group : 0u, cb_lo);  // the kernel's cb_first
         uint64_t cols = hi > first ? hi - first : 0;
+        if (pairs) cols = (cols + 1) / 2;
         (*off)[g + 1] = (*off)[g] + (uint64_t)rows * cols;
     }
+}
+
+// Dense launches (all 64 columns of a tile in use) go to the persistent dense_kernel unless SKD_DENSE_V1 is set.
+bool uses_dense_kernel(const skd_ctx *ctx, int mode, const skd_db *B) {
+    return ctx->dense_v2 && (mode == MODE_DENSE_SELF || mode == MODE_DENSE_CROSS) && B->n > 32;
 }
 
 // Re-tile chunk c of an asynchronously uploaded database (compute stream waits for its arrival).
@@ -257,6 +264,16 @@ skd_status materialize(skd_ctx *ctx, const skd_db *cdb) {
     return finish_pending(ctx, db);
 }
 
+// Match-count scratch of the persistent dense kernel, one per stream that can carry dense launches (the async-upload
+// path alternates column bands between the compute stream and aux[1]).  Allocated on the compute stream: callers that
+// launch on aux[1] make that stream wait for the compute stream first (run_dense does).
+skd_status dense_scratch(skd_ctx *ctx, const EpiParams &E, int slot, void **out) {
+    *out = nullptr;
+    if (!ctx->dense_v2) return SKD_OK;
+    return scratch_get(ctx, slot ? "tile_counts1" : "tile_counts0",
+                       dense_kernel_scratch_bytes(E.kp, E.nbins >= 65536, ctx->sm_count), out);
+}
+
 // Launch the tile kernel for rows [r0, r1) writing to device memory `dout`.  `d_grp_off` is the device copy
 // of `off` (group offsets built by build_groups for exactly this row range).
 skd_status launch_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, const EpiParams &E, int mode, uint64_t r0,
@@ -284,10 +301,16 @@ skd_status launch_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, const Ep
     S.cb_hi = cb_hi;
     const bool count32 = E.nbins >= 65536;
     size_t smem = tile_kernel_smem(E.nk, count32, false, 0, false);
-    if (smem > kMaxSmem)
+    skd_status st = SKD_OK;
+    if (uses_dense_kernel(ctx, mode, B)) {
+        st = dense_scratch(ctx, E, stream == ctx->aux[1] ? 1 : 0, &S.counts_scratch);
+        if (st) return st;
+    }
+    // tile_kernel keeps a tile's counts in shared memory; dense_kernel keeps them in L2
+    if (!S.counts_scratch && smem > kMaxSmem)
         return fail(ctx, SKD_ERR_UNSUPPORTED, "%d k-mer lengths at %u bins need %zu B of shared memory per tile", E.nk,
                     E.nbins, smem);
-    skd_status st = timer_begin(ctx, stream, 1);
+    st = timer_begin(ctx, stream, 1);
     if (st) return st;
     CU(ctx, launch_tiles(A->dev, B->dev, E, S, off.back(), count32, smem, stream));
     ctx->launches++;
@@ -335,7 +358,7 @@ skd_status run_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, bool self, 
         c.r0 = r;
         c.r1 = std::min(row_end, (r / TS) * TS + rows_per_chunk);
         build_groups(ctx->group, self, (uint32_t)(c.r0 / TS), (uint32_t)((c.r1 + TS - 1) / TS) - (uint32_t)(c.r0 / TS), B->dev.nb,
-                     &c.off);
+                     &c.off, uses_dense_kernel(ctx, mode, B));
         c.off_pos = off_total;
         off_total += c.off.size();
         chunk_elems = std::max<size_t>(chunk_elems, elems_before(c.r1) - elems_before(c.r0));
@@ -368,7 +391,8 @@ skd_status run_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, bool self, 
                 const uint64_t r1 = std::min<uint64_t>(row_end, (uint64_t)b1 * TS);
                 pos[c] = flat.size();
                 if (r1 > row_begin) {
-                    build_groups(ctx->group, true, rb0, (uint32_t)((r1 + TS - 1) / TS) - rb0, A->dev.nb, &offs[c], b0, b1);
+                    build_groups(ctx->group, true, rb0, (uint32_t)((r1 + TS - 1) / TS) - rb0, A->dev.nb, &offs[c],
+                                 uses_dense_kernel(ctx, mode, A), b0, b1);
                     flat.insert(flat.end(), offs[c].begin(), offs[c].end());
                 }
             }
@@ -385,6 +409,11 @@ skd_status run_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, bool self, 
                 for (auto e : retiled)
                     if (e) cudaEventDestroy(e);
             };
+            for (int slot = 0; slot < 2; ++slot) {  // both streams' count scratch exists before the helpers start
+                void *unused;
+                st = dense_scratch(ctx, E, slot, &unused);
+                if (st) return st;
+            }
             CU(ctx, cudaEventRecord(ctx->ev_a[0], ctx->compute));  // database buffers exist, offsets uploaded
             CU(ctx, cudaStreamWaitEvent(ctx->aux[0], ctx->ev_a[0], 0));
             CU(ctx, cudaStreamWaitEvent(ctx->aux[1], ctx->ev_a[0], 0));
@@ -514,7 +543,8 @@ skd_status run_knn_few_queries(skd_ctx *ctx, const skd_db *R, const skd_db *Q, c
     for (uint32_t c = 0; c < n_chunks; ++c) {
         const uint64_t g0 = (uint64_t)c * rows_chunk, g1 = std::min(n_ref, g0 + rows_chunk);
         std::vector<uint64_t> off;
-        build_groups(ctx->group, false, (uint32_t)(g0 / TS), (uint32_t)((g1 + TS - 1) / TS) - (uint32_t)(g0 / TS), Q->dev.nb, &off);
+        build_groups(ctx->group, false, (uint32_t)(g0 / TS), (uint32_t)((g1 + TS - 1) / TS) - (uint32_t)(g0 / TS), Q->dev.nb, &off,
+                     uses_dense_kernel(ctx, MODE_DENSE_CROSS, Q));
         void *doff;
         st = scratch_get(ctx, "grp_off", off.size() * sizeof(uint64_t), &doff);
         if (st) return st;
@@ -731,7 +761,7 @@ skd_status run_knn_symmetric(skd_ctx *ctx, const skd_db *db, const EpiParams &E,
         S.n_rb = (uint32_t)((g1 + TS - 1) / TS) - S.rb0;
         S.group = ctx->group;
         std::vector<uint64_t> off;
-        build_groups(ctx->group, true, S.rb0, S.n_rb, db->dev.nb, &off);
+        build_groups(ctx->group, true, S.rb0, S.n_rb, db->dev.nb, &off, uses_dense_kernel(ctx, MODE_DENSE_SELF, db));
         S.n_groups = (uint32_t)off.size() - 1;
         void *doff;
         st = scratch_get(ctx, "grp_off", off.size() * sizeof(uint64_t), &doff);
@@ -746,7 +776,11 @@ skd_status run_knn_symmetric(skd_ctx *ctx, const skd_db *db, const EpiParams &E,
         S.rect_c0 = g0;
         const bool count32 = E.nbins >= 65536;
         const size_t smem = tile_kernel_smem(E.nk, count32, false, 0, false);
-        if (smem > kMaxSmem)
+        if (uses_dense_kernel(ctx, MODE_DENSE_SELF, db)) {
+            st = dense_scratch(ctx, E, 0, &S.counts_scratch);
+            if (st) return st;
+        }
+        if (!S.counts_scratch && smem > kMaxSmem)
             return fail(ctx, SKD_ERR_UNSUPPORTED, "%d k-mer lengths at %u bins need %zu B of shared memory per tile", E.nk,
                         E.nbins, smem);
         st = timer_begin(ctx, nullptr, 1);
@@ -855,6 +889,8 @@ skd_status db_build(skd_ctx *ctx, const ChunkSource &src, uint64_t n, uint64_t s
         }
     } else if (n > 0) {
         if (src.direct && src.loc == SKD_DEVICE) {
+            // a device array is usually produced on another stream (a framework's): wait for the whole device
+            CUB(cudaDeviceSynchronize());
             launch_repack(src.direct, n, sample_stride, kmer_stride, db->tiled, db->dev, 0, db->dev.nb, ctx->compute);
             CUB(cudaGetLastError());
             ctx->launches++;
@@ -1010,6 +1046,7 @@ skd_status skd_ctx_create(int device, skd_ctx **out) {
         }
     }
     if (const char *e = getenv("SKD_ZEROCOPY")) ctx->zero_copy = atoi(e) != 0;
+    if (const char *e = getenv("SKD_DENSE_V1")) ctx->dense_v2 = atoi(e) == 0;
     if (const char *e = getenv("SKD_GROUP")) ctx->group = (uint32_t)std::max(1, atoi(e));
     if (const char *e = getenv("SKD_UPLOAD_CHUNK_MB")) ctx->upload_chunk_bytes = (size_t)std::max(1, atoi(e)) << 20;
     if (const char *e = getenv("SKD_KNN_SYMMETRIC")) ctx->knn_symmetric = atoi(e) != 0;

@@ -34,6 +34,7 @@ struct skd_ctx {
     size_t pinned_bytes = 0;
     int sm_count = 148;
     bool knn_symmetric = true;  // SKD_KNN_SYMMETRIC=0: whole-matrix self kNN evaluates both (i,j) and (j,i)
+    bool dense_v2 = true;    // dense modes run the persistent barrier-free dense_kernel (SKD_DENSE_V1=1: tile_kernel)
     bool zero_copy = true;   // dense kernels store straight into pinned host results (SKD_ZEROCOPY=0 disables)
     // Tunables, read once from the environment when the context is created.
     size_t upload_chunk_bytes = 64ull << 20;  // SKD_UPLOAD_CHUNK_MB: staging chunk of a pageable/file upload

@@ -577,6 +577,454 @@ __global__ void __launch_bounds__(THREADS, 2)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// The dense kernel (round 2): the same match-count arithmetic and epilogue as tile_kernel's dense modes, restructured
+// around what the loop model (tools/loop_model.cu, profiles/README.md) says bounds this loop: a 4 x 4 pair tile per
+// thread needs 16 LDS per 128 LOP3 and tops out at 0.77 of the LOP3 issue rate whatever else is done, a 4 x 8 tile
+// needs 12 and reaches 0.92 -- if nothing synchronises the CTA.
+//   * CTA tile 64 rows x 128 columns (one row block, two adjacent column blocks), 8 consumer warps of 16 x 64 pairs,
+//     4 x 8 pairs per thread (~150 registers: one CTA per SM), plus one producer warp.
+//   * Persistent CTAs take tiles from a global counter (linear tile id -> (row block, column block pair) through the
+//     same L2-friendly groups as tile_kernel), so the SMs stay balanced to the last tile.
+//   * A ring of DNST stages (one 64-bin word: the row slab + the two column slabs, 21 KB), filled by bulk copies onto
+//     per-stage "full" mbarriers.  Consumers never meet at a barrier: a warp that has finished a stage arrives on the
+//     stage's "empty" mbarrier and moves on; the producer lane (suspended in try_wait, not polling) refills a stage
+//     once all 8 warps have released it, and its cursor runs on into the next tile, so the pipeline never drains
+//     between tiles.
+//   * Per-pair match counts do not go through shared memory: a thread keeps the counts of its own 32 pairs in a
+//     per-CTA scratch area in global memory (L2 resident, [pair slot][thread][kp], one 16-byte word per pair for
+//     K <= 8) and runs the fused epilogue for exactly those pairs, so a warp goes from its last word straight into
+//     its epilogue while the other warps are still counting (f64/LSU work overlaps LOP3 work) and on into the next
+//     tile.  Shared memory holds only the ring, and any number of k-mer lengths fits.
+#ifndef SKD_DNST
+#define SKD_DNST 6
+#endif
+constexpr int DNST = SKD_DNST;
+static_assert(DNST >= 2 && DNST <= 10, "ring depth");
+constexpr int TRING = 16;                          // published tiles kept in shared memory
+constexpr int DSTAGE_U32 = 3 * STAGE_U32;          // row slab + two column slabs
+constexpr int DENSE_THREADS = 288;                 // 8 consumer warps + 1 producer warp
+constexpr int DJ = 8;                              // column groups per thread (4 x 8 pair tile)
+
+// Mismatch counts of one 32-bin half for a thread's 4 x 8 pair tile: rows arow0 + 4 i of the row slab, columns
+// bcol0 + 8 j (j < 8: all 64 columns of ONE column slab; a warp works on one of the tile's two column slabs).
+__device__ __forceinline__ void half_mismatches_4x8(const uint32_t *sa, const uint32_t *sb, int arow0, int bcol0,
+                                                    uint32_t one, uint32_t (&mism)[4][DJ]) {
+    uint32_t d[4][DJ];
+    const uint4 *a4 = reinterpret_cast<const uint4 *>(sa);
+    const uint4 *b4 = reinterpret_cast<const uint4 *>(sb);
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {  // planes 4q .. 4q+3: one LDS.128 per sample
+        uint4 av[4], bv[DJ];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) av[i] = a4[q * TS + arow0 + 4 * i];
+#pragma unroll
+        for (int j = 0; j < DJ; ++j) bv[j] = b4[q * TS + bcol0 + 8 * j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < DJ; ++j) {
+                if (q == 0)
+                    d[i][j] = av[i].x ^ bv[j].x;
+                else
+                    d[i][j] |= av[i].x ^ bv[j].x;
+                d[i][j] |= av[i].y ^ bv[j].y;
+                d[i][j] |= av[i].z ^ bv[j].z;
+                d[i][j] |= av[i].w ^ bv[j].w;
+            }
+    }
+    {  // planes 12, 13: one LDS.64 per sample
+        const uint2 *a2 = reinterpret_cast<const uint2 *>(sa + TAIL_U32);
+        const uint2 *b2 = reinterpret_cast<const uint2 *>(sb + TAIL_U32);
+        uint2 av[4], bv[DJ];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) av[i] = a2[arow0 + 4 * i];
+#pragma unroll
+        for (int j = 0; j < DJ; ++j) bv[j] = b2[bcol0 + 8 * j];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < DJ; ++j) {
+                d[i][j] |= av[i].x ^ bv[j].x;
+                d[i][j] |= av[i].y ^ bv[j].y;
+            }
+    }
+    // accumulate on the FMA pipe (IMAD with a run-time 1) so the ALU pipe only sees the LOP3s
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < DJ; ++j) mism[i][j] = __popc(d[i][j]) * one + mism[i][j];
+}
+
+// Distances of one pair from its per-k match counts, for dense_kernel: the out-of-line part of the epilogue (pairs
+// that really go through the regression, or any pair when completeness vectors are given).  The counts live k-major
+// in the CTA's scratch: the word of k is words[k * kstride]; for 16-bit counts a word packs the counts of two
+// neighbouring pairs (`shift` selects the half).  Same arithmetic, order and guards as pair_epilogue
+// (jaccard.rs:61-142).
+template <typename CountT>
+__device__ __forceinline__ float2 pair_epilogue_k(const uint32_t *words, size_t kstride, int shift, const EpiParams &E,
+                                                  uint64_t gi, uint64_t gj, bool for_knn) {
+    constexpr uint32_t MASK = sizeof(CountT) == 2 ? 0xffffu : 0xffffffffu;
+    const bool comp = E.has_c != 0;
+    double cc1 = 0.0, cc2 = 0.0;
+    if (comp) {
+        cc1 = E.a_comp[gi];
+        cc2 = E.b_comp[gj];
+    }
+    float d0, d1 = 0.0f;
+    if (E.kind == KIND_CORE_ACC) {
+        double ysum = 0.0, xysum = 0.0, ysq = 0.0;
+        int n = 0;
+        bool alive = true;
+        for (int kb = 0; kb < E.nk && alive; kb += 8) {
+            uint32_t c[8];
+            double y[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+                c[t] = kb + t < E.nk ? (__ldcg(words + (size_t)(kb + t) * kstride) >> shift) & MASK : 0u;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                if (kb + t >= E.nk)
+                    y[t] = 0.0;
+                else if (comp)
+                    y[t] = log(corrected_jaccard(c[t], cc1, cc2, E));
+                else
+                    y[t] = __ldg(&E.lny[c[t]]);
+            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                if (alive && kb + t < E.nk) {
+                    if (y[t] < E.tolerance) {
+                        alive = false;  // the reference breaks: later k are ignored (jaccard.rs:89-91)
+                    } else {
+                        ysum = __dadd_rn(ysum, y[t]);
+                        xysum = __dadd_rn(xysum, __dmul_rn(E.kf[kb + t], y[t]));
+                        ysq = __dadd_rn(ysq, __dmul_rn(y[t], y[t]));
+                        ++n;
+                    }
+                }
+            }
+        }
+        regress(ysum, xysum, ysq, n, E, d0, d1);
+    } else {  // single k with completeness vectors
+        const uint32_t c = (__ldcg(words) >> shift) & MASK;
+        const double j = corrected_jaccard(c, cc1, cc2, E);
+        if (E.kind == KIND_ANI) {
+            const double a = ani_pois_dev(j, E.k_single);
+            d0 = for_knn ? (float)__dsub_rn(1.0, a) : (float)a;
+        } else {
+            d0 = (float)__dsub_rn(1.0, j);
+        }
+    }
+    return make_float2(d0, d1);
+}
+
+template <typename CountT>
+__global__ void __launch_bounds__(DENSE_THREADS, 1)
+    dense_kernel(const __grid_constant__ DevDb A, const __grid_constant__ DevDb B, const __grid_constant__ EpiParams E,
+                 const __grid_constant__ SchedParams S, const uint64_t n_tiles, unsigned long long *__restrict__ tile_counter,
+                 CountT *__restrict__ scratch_all) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint32_t *stage_mem = reinterpret_cast<uint32_t *>(smem_raw);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)DNST * DSTAGE_U32 * 4);
+    uint64_t *empty_bar = full_bar + DNST;  // 8 arrivals (one per consumer warp) release a stage
+    uint2 *tiles = reinterpret_cast<uint2 *>(empty_bar + DNST);
+    volatile uint32_t *published = reinterpret_cast<volatile uint32_t *>(tiles + TRING);  // tiles[j % TRING] valid for j < it
+    uint16_t *warp_lists = reinterpret_cast<uint16_t *>(const_cast<uint32_t *>(published) + 4);  // [8 warps][1024]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t W = A.W, nk = (uint32_t)E.nk, kp = (uint32_t)E.kp;
+    const uint32_t n_it = nk * W;
+    const uint32_t nbins = 64u * W;
+    // column blocks this launch may touch: [.., cb_limit) (a band of an upload in flight ends at cb_hi)
+    const uint32_t cb_limit = S.cb_hi ? min(S.cb_hi, B.nb) : B.nb;
+
+    if (tid == 0) {
+        for (int s = 0; s < DNST; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 8);
+        }
+        *published = 0;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // Every wait below ends by construction; should a bug ever break that, trap after 20 s instead of hanging the GPU.
+    uint64_t t_start;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_start));
+    uint32_t spins = 0;
+    auto spin_guard = [&]() {
+        if ((++spins & 0xffu) == 0) {
+            uint64_t now;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+            if (now - t_start > 20000000000ull) __trap();
+        }
+    };
+
+    if (warp == 8) {
+        // ---- producer warp: one lane walks the schedule (tiles from the global counter, words of a tile in order)
+        // and refills a stage as soon as all 8 consumer warps have released its previous word
+        if (lane != 0) return;
+        uint32_t grp_hint = 0;
+        auto fetch_tile = [&]() -> uint2 {  // next valid tile (rb, first cb); (0xffffffff, 0) = schedule exhausted
+            for (;;) {
+                const uint64_t t = atomicAdd(tile_counter, 1ull);
+                if (t >= n_tiles) return make_uint2(0xffffffffu, 0u);
+                uint32_t g = grp_hint;
+                if (!(S.grp_off[g] <= t && t < S.grp_off[g + 1])) {
+                    uint32_t lo = 0, hi = S.n_groups;  // largest g with grp_off[g] <= t
+                    while (hi - lo > 1) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (S.grp_off[mid] <= t) lo = mid; else hi = mid;
+                    }
+                    g = grp_hint = lo;
+                }
+                const uint32_t rows_in_g = min(S.group, S.n_rb - g * S.group);
+                const uint64_t local = t - S.grp_off[g];
+                const uint32_t rb = S.rb0 + g * S.group + (uint32_t)(local % rows_in_g);
+                const uint32_t cb_first = max(S.mode == MODE_DENSE_SELF ? S.rb0 + g * S.group : 0u, S.cb_lo);
+                const uint32_t cb = cb_first + 2u * (uint32_t)(local / rows_in_g);  // column block PAIRS
+                if (S.mode == MODE_DENSE_SELF && cb + 1 < rb) continue;  // wholly below the diagonal
+                return make_uint2(rb, cb);
+            }
+        };
+        uint32_t n_pub = 0;
+        auto publish_tile = [&]() -> uint2 {
+            const uint2 rc = fetch_tile();
+            tiles[n_pub % TRING] = rc;
+            __threadfence_block();
+            *published = ++n_pub;
+            return rc;
+        };
+        uint2 rc = publish_tile();
+        uint32_t s = 0, use = 0;
+        const uint64_t a_step = (uint64_t)A.nb * STAGE_U32, b_step = (uint64_t)B.nb * STAGE_U32;  // next (k, w) slab
+        while (rc.x != 0xffffffffu) {
+            const uint2 next = publish_tile();  // the tile after this one: a whole tile ahead of its first use
+            const uint32_t *a_src = A.tiled + slab_index(A, (uint32_t)E.k0, 0, rc.x) * STAGE_U32;
+            const uint32_t *b_src = B.tiled + slab_index(B, (uint32_t)E.k0, 0, rc.y) * STAGE_U32;
+            // the second column block may not exist (odd count, end of a band): its slab is then not loaded and its
+            // columns are masked in the epilogue
+            const uint32_t b_bytes = rc.y + 1 < cb_limit ? 2u * STAGE_BYTES : (uint32_t)STAGE_BYTES;
+            for (uint32_t it = 0; it < n_it; ++it) {
+                // wait until all 8 consumer warps have released the stage's previous word.  try_wait suspends the
+                // lane in hardware: a polling loop here took 14 % of the issue slots of the scheduler this warp
+                // shares with two consumer warps, and the whole CTA then ran at the pace of those two.
+#ifndef SKD_ABL_NOWAIT
+                if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1u);
+#else
+                if (use > 0) break;  // ablation: fill the ring once
+#endif
+                uint32_t *dst = stage_mem + s * DSTAGE_U32;
+                uint64_t *bar = &full_bar[s];
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic reads before async writes
+                mbar_expect_tx(bar, STAGE_BYTES + b_bytes);
+                bulk_g2s(dst, a_src, STAGE_BYTES, bar);
+                bulk_g2s(dst + STAGE_U32, b_src, b_bytes, bar);
+                a_src += a_step;
+                b_src += b_step;
+                if (++s == (uint32_t)DNST) {
+                    s = 0;
+                    ++use;
+                }
+            }
+            rc = next;
+        }
+        return;
+    }
+
+    // ---- consumer warps: warp tile 16 rows x 64 columns, thread tile rows arow0 + 4 i, columns bcol0 + 8 j
+    const int arow0 = 16 * (warp >> 1) + (lane >> 3);
+    const int bcol0 = 64 * (warp & 1) + (lane & 7);            // column inside the 128-column tile
+    // this thread's words in the CTA's count scratch, k-major so that a warp's store is one contiguous line:
+    // word [k][slot][tid]; 16-bit counts: slot = pair / 2 holds pairs (i, 2 jj) and (i, 2 jj + 1), else slot = pair
+    constexpr int PACK = sizeof(CountT) == 2 ? 2 : 1;
+    constexpr int SLOTS = 4 * DJ / PACK;
+    const size_t kstride = (size_t)SLOTS * 256;  // words between consecutive k
+    uint32_t *my_words = reinterpret_cast<uint32_t *>(scratch_all) + (size_t)blockIdx.x * nk * kstride + tid;
+
+    uint32_t mism[4][DJ];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < DJ; ++j) mism[i][j] = 0;
+    uint32_t s = 0, ph = 0, w_in_k = 0, kk = 0;
+    bool ready = false;
+    // core/accessory: bit c of `dead` = pair c is known to be (1, 1); with fewer than three k-mer lengths every pair is
+    const bool track_dead = E.kind == KIND_CORE_ACC;
+    const uint32_t dead_init = (E.kind == KIND_CORE_ACC && nk < 3) ? 0xffffffffu : 0u;
+    uint32_t dead = dead_init;
+    const uint64_t nA = A.n;
+    const uint64_t col_end = min((uint64_t)B.n, (uint64_t)cb_limit * TS);
+    const bool rect = S.rect_ld != 0;
+    // operand offsets inside a stage: the warp's column half selects the first or second column slab
+    const int b_slab = (warp & 1) * STAGE_U32;
+    const int bcol_in_slab = lane & 7;
+
+    for (uint32_t tj = 0;; ++tj) {
+        while (*published <= tj) {  // (published a tile ahead of use: spins only at the very start)
+            __nanosleep(20);
+            spin_guard();
+        }
+        __threadfence_block();
+        const uint2 rc = tiles[tj % TRING];
+        if (rc.x == 0xffffffffu) break;
+        for (uint32_t it = 0; it < n_it; ++it) {
+#ifndef SKD_ABL_NOWAIT
+            if (!ready) mbar_wait(&full_bar[s], ph);  // try_wait suspends the warp in hardware: no issue slots burned
+#endif
+            const uint32_t *sa = stage_mem + s * DSTAGE_U32;
+            const uint32_t *sb = sa + STAGE_U32 + b_slab;
+            half_mismatches_4x8(sa, sb, arow0, bcol_in_slab, S.one, mism);
+#ifndef SKD_ABL_NOWAIT
+            {   // probe the next stage now: the ~90-cycle latency of the phase check hides behind the second half
+                const uint32_t s1 = s + 1 == (uint32_t)DNST ? 0u : s + 1;
+                ready = mbar_test(&full_bar[s1], s1 == 0 ? ph ^ 1u : ph);
+            }
+#endif
+            half_mismatches_4x8(sa + HALF_U32, sb + HALF_U32, arow0, bcol_in_slab, S.one, mism);
+#ifndef SKD_ABL_NOWAIT
+            __syncwarp();  // every lane has consumed its operands of this stage
+            if (lane == 0) mbar_arrive(&empty_bar[s]);  // release
+#endif
+            if (++w_in_k == W) {  // finished this k
+                // A pair without any match at one of the first three k-mer lengths is (1, 1) whatever follows (the
+                // reference's loop breaks there with n < 3, jaccard.rs:89-91, 117-119).  With unrelated samples that
+                // is nearly every pair: remember it in a bit mask, and neither store nor ever read its counts.
+                if (track_dead && kk < 3) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < DJ; ++j)
+                            if (nbins - mism[i][j] <= E.expected) dead |= 1u << (i * DJ + j);
+                }
+                // park the match counts of the pairs still alive (coalesced: 128 contiguous bytes per warp and slot)
+                uint32_t *kw = my_words + (size_t)kk * kstride;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < DJ; j += PACK) {
+                        uint32_t v = nbins - mism[i][j];
+                        if (PACK == 2) v |= (nbins - mism[i][j + 1]) << 16;
+                        const uint32_t both = (PACK == 2 ? 3u : 1u) << (i * DJ + j);
+#ifdef SKD_ABL_NOCOUNTS
+                        if (v == 0x12345u)
+#endif
+                        if ((dead & both) != both) __stcg(kw + (size_t)((i * DJ + j) / PACK) * 256, v);
+                    }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < DJ; ++j) mism[i][j] = 0;
+                w_in_k = 0;
+                if (++kk == nk) kk = 0;
+            }
+            if (++s == (uint32_t)DNST) {
+                s = 0;
+                ph ^= 1u;
+            }
+        }
+        // ---- fused epilogue for this thread's own 32 pairs (no CTA-wide step: other warps may still be counting).
+        // Pass 1, every lane for its own pairs: core/accessory pairs known to be (1, 1) are stored as such, single-k
+        // pairs take one table look-up (or the completeness arithmetic).  Core/accessory pairs that need the
+        // regression are only collected: with 1 % of them spread over the lanes, running the regression where they sit
+        // would take the whole warp through that long, latency-bound code once per pair slot (measured: 10 % of the
+        // kernel).  Pass 2 instead compacts them over the warp (list in shared memory) and gives every lane one.
+#ifdef SKD_ABL_NOEPI
+        if (dead != 0x12345u) dead = 0x12345u; else
+#endif
+        {
+            const bool two = E.kind == KIND_CORE_ACC;
+            const bool single_plain = !two && !E.has_c;
+            const float *tab = rect ? E.key_tab : E.val_tab;
+            auto row_base_of = [&](uint64_t gi) -> uint64_t {  // output index of column 0 of row gi
+                if (rect) return (gi - S.row_begin) * S.rect_ld - (S.mode == MODE_DENSE_SELF ? S.rect_c0 : 0);
+                if (S.mode == MODE_DENSE_SELF) return nA * gi - ((gi * (gi + 1)) >> 1) - 1 - gi - S.out_base;  // condensed
+                return (gi - S.row_begin) * B.n;
+            };
+            auto store = [&](uint64_t idx, float2 d) {
+#ifdef SKD_ABL_NOSTORE
+                if (d.x == 12345.f)
+#endif
+                if (rect) {  // read back soon by the select kernels: normal (L2-resident) stores
+                    if (two)
+                        reinterpret_cast<float2 *>(S.out)[idx] = d;
+                    else
+                        S.out[idx] = d.x;
+                } else if (two) {
+                    __stcs(reinterpret_cast<float2 *>(S.out) + idx, d);
+                } else {
+                    __stcs(S.out + idx, d.x);
+                }
+            };
+            uint32_t todo = 0;  // bit c: pair c needs the regression
+#pragma unroll 1
+            for (int i = 0; i < 4; ++i) {
+                const uint64_t gi = (uint64_t)rc.x * TS + arow0 + 4 * i;
+                if (gi < S.row_begin || gi >= S.row_end) continue;
+                const uint64_t row_base = row_base_of(gi);
+                uint32_t w_single[DJ];  // single-k: the count words of this row's slots, all in flight at once
+                if (!two) {
+#pragma unroll
+                    for (int j = 0; j < DJ; j += PACK) w_single[j] = __ldcg(my_words + (size_t)((i * DJ + j) / PACK) * 256);
+                }
+#pragma unroll
+                for (int j = 0; j < DJ; ++j) {
+                    const uint64_t gj = (uint64_t)rc.y * TS + bcol0 + 8 * j;
+                    if (gj >= col_end || (S.mode == MODE_DENSE_SELF && gj <= gi)) continue;
+                    const int c = i * DJ + j;
+                    if (two) {
+                        if ((dead >> c) & 1u)
+                            store(row_base + gj, make_float2(1.0f, 1.0f));
+                        else
+                            todo |= 1u << c;
+                    } else if (single_plain) {
+                        const uint32_t cnt = (w_single[j - j % PACK] >> (16 * (j % PACK))) & (PACK == 2 ? 0xffffu : 0xffffffffu);
+                        store(row_base + gj, make_float2(__ldg(&tab[cnt]), 0.0f));
+                    } else {
+                        store(row_base + gj, pair_epilogue_k<CountT>(my_words + (size_t)(c / PACK) * 256, kstride,
+                                                                     16 * (c % PACK), E, gi, gj, rect));
+                    }
+                }
+            }
+            if (two) {  // pass 2 (warp-uniform branch)
+                const uint32_t cnt = __popc(todo);
+                uint32_t incl = cnt;
+#pragma unroll
+                for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, dlt);
+                    if (lane >= dlt) incl += t;
+                }
+                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                if (total) {
+                    uint16_t *list = warp_lists + warp * 1024;  // (owner lane << 5) | pair
+                    uint32_t r = incl - cnt;
+                    for (uint32_t m = todo; m; m &= m - 1) list[r++] = (uint16_t)((lane << 5) | (__ffs(m) - 1));
+                    __syncwarp();  // the list, and the owners' count words, are visible to the whole warp
+                    for (uint32_t item = lane; item < total; item += 32) {
+                        const uint32_t e = list[item], o = e >> 5, c = e & 31u;
+                        const uint64_t gi = (uint64_t)rc.x * TS + 16 * (warp >> 1) + (o >> 3) + 4 * (c / DJ);
+                        const uint64_t gj = (uint64_t)rc.y * TS + 64 * (warp & 1) + (o & 7) + 8 * (c % DJ);
+                        const uint32_t *words = my_words - lane + o + (size_t)(c / PACK) * 256;
+                        store(row_base_of(gi) + gj, pair_epilogue_k<CountT>(words, kstride, 16 * (c % PACK), E, gi, gj, rect));
+                    }
+                    __syncwarp();  // the list is reused by the next tile
+                }
+            }
+        }
+        dead = dead_init;
+    }
+}
+
+size_t dense_kernel_smem() {
+    return (size_t)DNST * DSTAGE_U32 * 4 + 2 * DNST * 8 + TRING * sizeof(uint2) + 16 + 8 * 1024 * sizeof(uint16_t);
+}
+// per-CTA count scratch (one CTA per SM, 64 x 128 pairs each, nk <= kp words of 4 bytes per pair slot) + 256 bytes
+// in front for the tile counter
+size_t dense_kernel_scratch_bytes(int kp, bool count32, int sm_count) {
+    return 256 + (size_t)sm_count * 2 * TS * TS * kp * (count32 ? 4 : 2);
+}
+
 int counts_per_pair(int nk, bool count32) {
     const int per = count32 ? 4 : 8;
     return (nk + per - 1) / per * per;
@@ -787,6 +1235,31 @@ cudaError_t launch_tiles(const DevDb &A, const DevDb &B, const EpiParams &E, con
     // large reference database) only those columns are loaded and compared.
     const int cols = S.mode == MODE_KNN || TJ != 4 ? TS : (B.n <= 8 ? 8 : B.n <= 16 ? 16 : B.n <= 32 ? 32 : TS);
     cudaError_t err = cudaSuccess;
+    if (cols == TS && TJ == 4 && S.counts_scratch && (S.mode == MODE_DENSE_SELF || S.mode == MODE_DENSE_CROSS)) {
+        // the barrier-free persistent kernel: 2 CTAs per SM, each walking up to MAXT tiles per launch
+        int dev = 0, sm_count = 148;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0)
+            sm_count = 148;
+        const uint64_t max_ctas = (uint64_t)sm_count;  // one CTA per SM
+        const size_t dsmem = dense_kernel_smem();
+        if (count32)
+            err = cudaFuncSetAttribute(dense_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem);
+        else
+            err = cudaFuncSetAttribute(dense_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem);
+        if (err != cudaSuccess) return err;
+        // the tile counter sits in front of the count scratch and is reset (stream-ordered) before every launch
+        unsigned long long *counter = reinterpret_cast<unsigned long long *>(S.counts_scratch);
+        unsigned char *counts = reinterpret_cast<unsigned char *>(S.counts_scratch) + 256;
+        err = cudaMemsetAsync(counter, 0, 8, st);
+        if (err != cudaSuccess) return err;
+        const unsigned grid = (unsigned)std::min<uint64_t>(n_ctas, max_ctas);
+        if (count32)
+            dense_kernel<uint32_t><<<grid, DENSE_THREADS, dsmem, st>>>(A, B, E, S, n_ctas, counter, (uint32_t *)counts);
+        else
+            dense_kernel<uint16_t><<<grid, DENSE_THREADS, dsmem, st>>>(A, B, E, S, n_ctas, counter, (uint16_t *)counts);
+        return cudaGetLastError();
+    }
 #define SKD_LAUNCH(T, C)                                                                                      \
     do {                                                                                                      \
         err = cudaFuncSetAttribute(tile_kernel<T, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
@@ -1428,6 +1901,8 @@ cudaError_t preload_kernels() {
     SKD_PRELOAD(tile_kernel<uint32_t, 16>);
     SKD_PRELOAD(tile_kernel<uint32_t, 32>);
     SKD_PRELOAD(tile_kernel<uint32_t, TS>);
+    SKD_PRELOAD(dense_kernel<uint16_t>);
+    SKD_PRELOAD(dense_kernel<uint32_t>);
     SKD_PRELOAD(stream_kernel<1>);
     SKD_PRELOAD(stream_kernel<2>);
     SKD_PRELOAD(stream_kernel<4>);

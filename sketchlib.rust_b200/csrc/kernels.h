@@ -15,6 +15,8 @@ void launch_repack(const uint64_t *raw, uint64_t raw_samples, uint64_t sample_st
 int counts_per_pair(int nk, bool count32);
 size_t tile_kernel_smem(int nk, bool count32, bool knn_mode, uint32_t cap, bool with_aux);
 
+size_t dense_kernel_smem();
+size_t dense_kernel_scratch_bytes(int kp, bool count32, int sm_count);
 cudaError_t launch_tiles(const DevDb &A, const DevDb &B, const EpiParams &E, const SchedParams &S, uint64_t n_ctas,
                          bool count32, size_t smem, cudaStream_t st);
 

@@ -16,7 +16,7 @@ constexpr int NST = 3;                     // pipeline stages
 #endif
 constexpr int TJ = SKD_TJ;                 // columns per thread: 4 (8 warps, warp tile 16x32) or 8 (4 warps, 16x64)
 constexpr int THREADS = TJ == 4 ? 256 : 128;  // thread tile 4 x TJ pairs
-constexpr int MAXK = 32;                   // k-mer lengths supported by the fused core/accessory epilogue
+constexpr int MAXK = 64;                   // k-mer lengths supported by the fused core/accessory epilogue
 
 // Tiled layout ("k-major, 64-bin-word, sample-block"): one (k, w, b) slab = 64 samples x 14 planes x 64 bins =
 // STAGE_U32 u32 = 7168 contiguous bytes, exactly what one bulk (TMA) copy moves into shared memory.  Inside a
@@ -107,6 +107,9 @@ struct SchedParams {
     unsigned long long *part_key; // [n_rb][n_split][TS][cap] composite (key bits << 32 | idx); the first knn
                                   // of each list are its best, ascending, when the kernel ends
     float *part_aux;              // same shape: accessory distance (core/acc only)
+    // dense modes: per-CTA match-count scratch of dense_kernel (2 x SM count CTAs x 4096 pairs x kp counts); null
+    // selects the one-tile-per-CTA tile_kernel
+    void *counts_scratch;
 };
 
 }  // namespace skd

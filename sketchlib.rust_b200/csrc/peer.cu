@@ -62,7 +62,7 @@ struct skd_comm {
     bool opened[kMaxWorld] = {};      // mapped with cudaIpcOpenMemHandle (to be closed)
     bool connected = false;
     uint32_t epoch = 0;
-    uint32_t *err_host = nullptr, *err_dev = nullptr;  // mapped pinned flag: a barrier timed out
+    uint32_t *err_host = nullptr, *err_dev = nullptr;  // mapped pinned word: result of the last barrier wait
     double timeout_s = 60.0;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // op begin / local kernels done / op end
     float last_ms = 0.f, last_xchg_ms = 0.f;
@@ -86,23 +86,38 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
     return t;
 }
 
-// One thread per peer: publish `epoch` in the peer's flag slot of this rank, then wait for the peer's epoch in the own
-// window.  Everything this rank's stream did before the barrier is visible to a peer that has passed it.
-__global__ void peer_barrier_kernel(PeerBases P, int rank, int world, uint32_t epoch, uint32_t *err, uint64_t timeout_ns) {
+// Flag barrier.  One thread per peer: (signal) publish `epoch` in the peer's flag slot of this rank, (wait) spin on the
+// peer's slot in the own window for at most spin_ns, then report in *status whether every peer has arrived.  The host
+// re-launches the wait until it succeeds (enqueue_barrier): the device never spins for long, so another host thread that
+// shares this GPU and sits in a device-synchronising driver call (a first kernel load, a memory-pool growth) always
+// gets through -- a pure device spin dead-locks against it.  Everything this rank's stream did before the barrier is
+// visible to a peer that has passed it.
+__global__ void peer_barrier_kernel(PeerBases P, int rank, int world, uint32_t epoch, int do_signal, uint64_t spin_ns,
+                                    uint32_t *status) {
     const int p = threadIdx.x;
-    if (p >= world) return;
-    __threadfence_system();
-    st_release_sys(reinterpret_cast<uint32_t *>(P.base[p]) + rank, epoch);
-    const uint32_t *mine = reinterpret_cast<const uint32_t *>(P.base[rank]) + p;
-    const uint64_t t0 = global_timer_ns();
-    while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
-        if (global_timer_ns() - t0 > timeout_ns) {
-            *reinterpret_cast<volatile uint32_t *>(err) = 1u + (uint32_t)p;
-            break;
+    bool ok = true;
+    if (p < world) {
+        if (do_signal) {
+            __threadfence_system();
+            st_release_sys(reinterpret_cast<uint32_t *>(P.base[p]) + rank, epoch);
         }
-        __nanosleep(200);
+        const uint32_t *mine = reinterpret_cast<const uint32_t *>(P.base[rank]) + p;
+        const uint64_t t0 = global_timer_ns();
+        while ((int32_t)(ld_acquire_sys(mine) - epoch) < 0) {
+            if (global_timer_ns() - t0 > spin_ns) {
+                ok = false;
+                break;
+            }
+            __nanosleep(100);
+        }
+        __threadfence_system();
     }
-    __threadfence_system();
+    const unsigned all = __ballot_sync(0xffffffffu, ok);
+    if (p == 0) {
+        uint32_t missing = 0;  // lowest rank that has not arrived, + 1
+        if (all != 0xffffffffu) missing = (uint32_t)__ffs(~all);
+        *reinterpret_cast<volatile uint32_t *>(status) = missing;
+    }
 }
 
 // Distributed loader, second half.  Rank p's window holds its slice re-tiled as [K*W rows][nb_p blocks] slabs
@@ -220,35 +235,41 @@ bool g_debug = getenv("SKD_PEER_DEBUG") != nullptr;
 
 skd_status comm_fail(skd_comm *c, skd_status st, const char *msg) { return fail(c ? c->ctx : nullptr, st, "%s", msg); }
 
-// Enqueues one flag barrier on the compute stream.
+// One flag barrier on the compute stream; returns when every rank has reached it (the stream is idle then).
 skd_status enqueue_barrier(skd_comm *c) {
     if (c->world == 1) return SKD_OK;
     if (!c->connected) return comm_fail(c, SKD_ERR_INVALID, "peer group is not connected (skd_comm_connect)");
+    skd_ctx *ctx = c->ctx;
     c->epoch++;
-    PEER_LOG(c, "barrier %u enqueued", c->epoch);
-    peer_barrier_kernel<<<1, 32, 0, c->ctx->compute>>>(c->peers, c->rank, c->world, c->epoch, c->err_dev,
-                                                       (uint64_t)(c->timeout_s * 1e9));
-    CU(c->ctx, cudaGetLastError());
-    c->ctx->launches++;
-    return SKD_OK;
+    PEER_LOG(c, "barrier %u", c->epoch);
+    const double t0 = now_s();
+    for (int attempt = 0;; ++attempt) {
+        // first wait: 2 ms on the device (ranks of a balanced job arrive within that); later ones short, with the host
+        // sleeping in between so that the GPU is free for whoever is blocked on it
+        const uint64_t spin_ns = attempt == 0 ? 2000000ull : 200000ull;
+        peer_barrier_kernel<<<1, 32, 0, ctx->compute>>>(c->peers, c->rank, c->world, c->epoch, attempt == 0, spin_ns, c->err_dev);
+        CU(ctx, cudaGetLastError());
+        ctx->launches++;
+        CU(ctx, cudaStreamSynchronize(ctx->compute));
+        const uint32_t missing = *reinterpret_cast<volatile uint32_t *>(c->err_host);
+        if (missing == 0) return SKD_OK;
+        if (now_s() - t0 > c->timeout_s)
+            return fail(ctx, SKD_ERR_CUDA, "peer barrier timed out after %.0f s: rank %u of %d never arrived", c->timeout_s,
+                        missing - 1, c->world);
+        usleep(attempt < 50 ? 50 : 500);
+    }
 }
 
-// Synchronises the compute stream and turns a barrier timeout into an error.
+// Ends a collective call: synchronises the compute stream and collects the timings.
 skd_status finish_op(skd_comm *c) {
     CU(c->ctx, cudaStreamSynchronize(c->ctx->compute));
-    PEER_LOG(c, "op finished (epoch %u, err flag %u)", c->epoch, c->err_host ? *c->err_host : 0u);
-    if (c->err_host && *c->err_host) {
-        const uint32_t who = *c->err_host - 1;
-        *c->err_host = 0;
-        return fail(c->ctx, SKD_ERR_CUDA, "peer barrier timed out after %.0f s: rank %u of %d never arrived", c->timeout_s, who,
-                    c->world);
-    }
+    PEER_LOG(c, "op finished (epoch %u)", c->epoch);
     float a = 0.f, b = 0.f;
     CU(c->ctx, cudaEventElapsedTime(&a, c->ev[0], c->ev[2]));
     CU(c->ctx, cudaEventElapsedTime(&b, c->ev[1], c->ev[2]));
     c->last_ms = a;
     c->last_xchg_ms = b;
-    return SKD_OK;
+    return timers_collect(c->ctx);
 }
 
 struct KnnLayout {  // offsets into the window's data area
@@ -386,6 +407,7 @@ skd_status begin_op(skd_comm *c) {
     if (!c || !c->ctx) return SKD_ERR_INVALID;
     CU(c->ctx, cudaSetDevice(c->ctx->device));
     if (c->world > 1 && !c->connected) return comm_fail(c, SKD_ERR_INVALID, "peer group is not connected (skd_comm_connect)");
+    timers_reset(c->ctx);
     CU(c->ctx, cudaEventRecord(c->ev[0], c->ctx->compute));
     return enqueue_barrier(c);  // no peer is still reading this window on behalf of the previous call
 }

@@ -3,11 +3,40 @@
 // tile kernel (MEASURED_PEAKS.json only has HBM and bf16 peaks).  Prints one JSON object.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o int_peak int_peak.cu && ./int_peak [seconds]
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <unistd.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
+
+// SM clock from NVML (libnvidia-ml.so.1, loaded at run time), sampled by the host while a kernel runs: clock64()
+// does not tick at the SM clock on this GPU (round 1 derived 1230 MHz from it while nvidia-smi showed 1965 MHz).
+struct Nvml {
+    void *lib = nullptr, *dev = nullptr;
+    int (*clock_info)(void *, int, unsigned *) = nullptr;
+    bool ok = false;
+    Nvml() {
+        lib = dlopen("libnvidia-ml.so.1", RTLD_NOW);
+        if (!lib) return;
+        auto init = (int (*)())dlsym(lib, "nvmlInit_v2");
+        auto by_pci = (int (*)(const char *, void **))dlsym(lib, "nvmlDeviceGetHandleByPciBusId_v2");
+        clock_info = (int (*)(void *, int, unsigned *))dlsym(lib, "nvmlDeviceGetClockInfo");
+        if (!init || !by_pci || !clock_info || init() != 0) return;
+        char bus[32];
+        int dev_id = 0;
+        cudaGetDevice(&dev_id);
+        if (cudaDeviceGetPCIBusId(bus, sizeof bus, dev_id) != cudaSuccess) return;
+        ok = by_pci(bus, &dev) == 0;
+    }
+    double sm_mhz() const {
+        unsigned mhz = 0;
+        if (!ok || clock_info(dev, 1 /* NVML_CLOCK_SM */, &mhz) != 0) return 0.0;
+        return (double)mhz;
+    }
+};
 
 constexpr int CHAINS = 16;
 constexpr int UNROLL = 8;
@@ -61,10 +90,11 @@ __global__ void __launch_bounds__(256) peak_kernel(uint32_t *out, uint32_t a, ui
 
 struct Result {
     double ops_per_s, ops_per_clk_sm, sm_mhz, ms;
+    int clock_samples;
 };
 
 template <int MODE>
-Result run(int sms, int ctas_per_sm, double seconds, uint32_t *out, unsigned long long *cyc) {
+Result run(const Nvml &nvml, int sms, int ctas_per_sm, double seconds, uint32_t *out, unsigned long long *cyc) {
     const int grid = sms * ctas_per_sm, block = 256;
     const double ops_per_iter = (MODE == M_MIX ? 14.0 * 2 : 1.0 * UNROLL) * CHAINS;  // counted op: LOP3 in the mix
     cudaEvent_t e0, e1;
@@ -72,28 +102,32 @@ Result run(int sms, int ctas_per_sm, double seconds, uint32_t *out, unsigned lon
     cudaEventCreate(&e1);
     int iters = 2000;
     float ms = 0;
+    std::vector<double> clocks;
     for (int attempt = 0; attempt < 6; ++attempt) {  // warm up and scale to the wanted duration
+        clocks.clear();
         cudaEventRecord(e0);
         peak_kernel<MODE><<<grid, block>>>(out, 0x12345u, 0x9e3779b9u, iters, cyc);
         cudaEventRecord(e1);
+        while (cudaEventQuery(e1) == cudaErrorNotReady) {  // sample the SM clock while the kernel runs
+            const double mhz = nvml.sm_mhz();
+            if (mhz > 0) clocks.push_back(mhz);
+            usleep(10000);
+        }
         cudaEventSynchronize(e1);
         cudaEventElapsedTime(&ms, e0, e1);
         if (ms > seconds * 1000 * 0.8) break;
         double scale = seconds * 1000 / (ms > 0.01 ? ms : 0.01);
         iters = (int)(iters * (scale > 50 ? 50 : scale));
     }
-    std::vector<unsigned long long> h(grid);
-    cudaMemcpy(h.data(), cyc, grid * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
-    double cyc_mean = 0;
-    for (auto c : h) cyc_mean += (double)c;
-    cyc_mean /= grid;
     double total = ops_per_iter * (double)iters * block * grid;
     Result r;
     r.ms = ms;
     r.ops_per_s = total / (ms * 1e-3);
-    // every CTA is resident for the whole kernel: per-SM rate = ops of its CTAs / cycles it ran
-    r.ops_per_clk_sm = ops_per_iter * (double)iters * block * ctas_per_sm / cyc_mean;
-    r.sm_mhz = cyc_mean / (ms * 1e3);
+    // median of the NVML samples taken during the final (long) launch; 0 if NVML is unavailable
+    std::sort(clocks.begin(), clocks.end());
+    r.sm_mhz = clocks.empty() ? 0.0 : clocks[clocks.size() / 2];
+    r.clock_samples = (int)clocks.size();
+    r.ops_per_clk_sm = r.sm_mhz > 0 ? r.ops_per_s / (sms * r.sm_mhz * 1e6) : 0.0;
     return r;
 }
 
@@ -107,13 +141,17 @@ int main(int argc, char **argv) {
     unsigned long long *cyc;
     cudaMalloc(&out, (size_t)sms * cps * 256 * 4);
     cudaMalloc(&cyc, (size_t)sms * cps * 8);
-    Result l = run<M_LOP3>(sms, cps, seconds, out, cyc);
-    Result p = run<M_POPC>(sms, cps, seconds, out, cyc);
-    Result m = run<M_MIX>(sms, cps, seconds, out, cyc);
+    Nvml nvml;
+    Result l = run<M_LOP3>(nvml, sms, cps, seconds, out, cyc);
+    Result p = run<M_POPC>(nvml, sms, cps, seconds, out, cyc);
+    Result m = run<M_MIX>(nvml, sms, cps, seconds, out, cyc);
     printf("{\"gpu\": \"%s\", \"sms\": %d, \"seconds_each\": %.2f, \"warps_per_sm\": %d,\n", prop.name, sms, seconds, cps * 8);
     printf(" \"lop3_per_s\": %.4e, \"lop3_per_clk_sm\": %.2f, \"lop3_sm_mhz\": %.0f,\n", l.ops_per_s, l.ops_per_clk_sm, l.sm_mhz);
     printf(" \"popc_per_s\": %.4e, \"popc_per_clk_sm\": %.2f, \"popc_sm_mhz\": %.0f,\n", p.ops_per_s, p.ops_per_clk_sm, p.sm_mhz);
     printf(" \"mix_lop3_per_s\": %.4e, \"mix_lop3_per_clk_sm\": %.2f, \"mix_sm_mhz\": %.0f,\n", m.ops_per_s, m.ops_per_clk_sm, m.sm_mhz);
+    printf(" \"sm_mhz\": %.0f, \"clock_source\": \"%s\", \"clock_samples\": %d,\n", l.sm_mhz,
+           nvml.ok ? "NVML nvmlDeviceGetClockInfo(SM), median of samples taken while the LOP3 kernel ran" : "unavailable",
+           l.clock_samples);
     printf(" \"how\": \"16 independent chains per thread, 32 warps per SM, all SMs; volatile inline PTX; LOP3 of the 14:1:1 LOP3:POPC:IADD mix counted for mix_*\"}\n");
     return cudaGetLastError() == cudaSuccess ? 0 : 1;
 }
