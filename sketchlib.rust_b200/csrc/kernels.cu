@@ -731,6 +731,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1)
     uint2 *tiles = reinterpret_cast<uint2 *>(empty_bar + DNST);
     volatile uint32_t *published = reinterpret_cast<volatile uint32_t *>(tiles + TRING);  // tiles[j % TRING] valid for j < it
     uint16_t *warp_lists = reinterpret_cast<uint16_t *>(const_cast<uint32_t *>(published) + 4);  // [8 warps][1024]
+    unsigned char *out_stage = reinterpret_cast<unsigned char *>(warp_lists + 8 * 1024);          // [8 warps][16][64] float2
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t W = A.W, nk = (uint32_t)E.nk, kp = (uint32_t)E.kp;
@@ -942,7 +943,13 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1)
                 if (S.mode == MODE_DENSE_SELF) return nA * gi - ((gi * (gi + 1)) >> 1) - 1 - gi - S.out_base;  // condensed
                 return (gi - S.row_begin) * B.n;
             };
-            auto store = [&](uint64_t idx, float2 d) {
+            // Dense outputs are staged per warp in shared memory (16 rows x 64 columns) and written out row by row,
+            // 256 contiguous bytes per store: when the destination is pinned host memory (zero-copy results) the
+            // PCIe writes are full-size instead of the 64-byte pieces a thread-private store pattern gives.
+            // kNN key matrices (rect) stay in HBM and are stored directly.
+            float2 *wst2 = reinterpret_cast<float2 *>(out_stage) + warp * (16 * 64);
+            float *wst1 = reinterpret_cast<float *>(wst2);
+            auto put = [&](int lrow, int lcol, uint64_t idx, float2 d) {
 #ifdef SKD_ABL_NOSTORE
                 if (d.x == 12345.f)
 #endif
@@ -952,9 +959,9 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1)
                     else
                         S.out[idx] = d.x;
                 } else if (two) {
-                    __stcs(reinterpret_cast<float2 *>(S.out) + idx, d);
+                    wst2[lrow * 64 + lcol] = d;
                 } else {
-                    __stcs(S.out + idx, d.x);
+                    wst1[lrow * 64 + lcol] = d.x;
                 }
             };
             uint32_t todo = 0;  // bit c: pair c needs the regression
@@ -975,15 +982,15 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1)
                     const int c = i * DJ + j;
                     if (two) {
                         if ((dead >> c) & 1u)
-                            store(row_base + gj, make_float2(1.0f, 1.0f));
+                            put((lane >> 3) + 4 * i, (lane & 7) + 8 * j, row_base + gj, make_float2(1.0f, 1.0f));
                         else
                             todo |= 1u << c;
                     } else if (single_plain) {
                         const uint32_t cnt = (w_single[j - j % PACK] >> (16 * (j % PACK))) & (PACK == 2 ? 0xffffu : 0xffffffffu);
-                        store(row_base + gj, make_float2(__ldg(&tab[cnt]), 0.0f));
+                        put((lane >> 3) + 4 * i, (lane & 7) + 8 * j, row_base + gj, make_float2(__ldg(&tab[cnt]), 0.0f));
                     } else {
-                        store(row_base + gj, pair_epilogue_k<CountT>(my_words + (size_t)(c / PACK) * 256, kstride,
-                                                                     16 * (c % PACK), E, gi, gj, rect));
+                        put((lane >> 3) + 4 * i, (lane & 7) + 8 * j, row_base + gj,
+                            pair_epilogue_k<CountT>(my_words + (size_t)(c / PACK) * 256, kstride, 16 * (c % PACK), E, gi, gj, rect));
                     }
                 }
             }
@@ -1006,10 +1013,32 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1)
                         const uint64_t gi = (uint64_t)rc.x * TS + 16 * (warp >> 1) + (o >> 3) + 4 * (c / DJ);
                         const uint64_t gj = (uint64_t)rc.y * TS + 64 * (warp & 1) + (o & 7) + 8 * (c % DJ);
                         const uint32_t *words = my_words - lane + o + (size_t)(c / PACK) * 256;
-                        store(row_base_of(gi) + gj, pair_epilogue_k<CountT>(words, kstride, 16 * (c % PACK), E, gi, gj, rect));
+                        put((int)((o >> 3) + 4 * (c / DJ)), (int)((o & 7) + 8 * (c % DJ)), row_base_of(gi) + gj,
+                            pair_epilogue_k<CountT>(words, kstride, 16 * (c % PACK), E, gi, gj, rect));
                     }
                     __syncwarp();  // the list is reused by the next tile
                 }
+            }
+            if (!rect) {  // write the warp's 16 x 64 block out, one row per step, coalesced
+                __syncwarp();
+                const uint64_t gj0 = (uint64_t)rc.y * TS + 64 * (warp & 1);
+#pragma unroll 1
+                for (int lrow = 0; lrow < 16; ++lrow) {
+                    const uint64_t gi = (uint64_t)rc.x * TS + 16 * (warp >> 1) + lrow;
+                    if (gi < S.row_begin || gi >= S.row_end) continue;
+                    const uint64_t row_base = row_base_of(gi);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int lcol = h * 32 + lane;
+                        const uint64_t gj = gj0 + lcol;
+                        if (gj >= col_end || (S.mode == MODE_DENSE_SELF && gj <= gi)) continue;
+                        if (two)
+                            __stcs(reinterpret_cast<float2 *>(S.out) + row_base + gj, wst2[lrow * 64 + lcol]);
+                        else
+                            __stcs(S.out + row_base + gj, wst1[lrow * 64 + lcol]);
+                    }
+                }
+                __syncwarp();  // the staging block is reused by the next tile
             }
         }
         dead = dead_init;
@@ -1017,7 +1046,8 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1)
 }
 
 size_t dense_kernel_smem() {
-    return (size_t)DNST * DSTAGE_U32 * 4 + 2 * DNST * 8 + TRING * sizeof(uint2) + 16 + 8 * 1024 * sizeof(uint16_t);
+    return (size_t)DNST * DSTAGE_U32 * 4 + 2 * DNST * 8 + TRING * sizeof(uint2) + 16 + 8 * 1024 * sizeof(uint16_t) +
+           8 * 16 * 64 * sizeof(float2);
 }
 // per-CTA count scratch (one CTA per SM, 64 x 128 pairs each, nk <= kp words of 4 bytes per pair slot) + 256 bytes
 // in front for the tile counter

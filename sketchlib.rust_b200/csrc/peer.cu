@@ -130,13 +130,14 @@ struct GatherDbParams {
     uint32_t nb_total;
 };
 __global__ void __launch_bounds__(256) peer_gather_db_kernel(const __grid_constant__ GatherDbParams G, uint4 *__restrict__ dst) {
-    constexpr uint64_t U = STAGE_BYTES / 16;  // 16-byte units per slab
-    const int p = blockIdx.y;
-    const uint64_t per_row = (uint64_t)G.nb[p] * U, total = per_row * G.rows;
+    constexpr uint32_t U = STAGE_BYTES / 16;  // 16-byte units per slab
+    const int p = blockIdx.z;                 // source rank
+    const uint32_t per_row = G.nb[p] * U;
     const uint4 *src = G.src[p];
-    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (uint64_t)gridDim.x * blockDim.x) {
-        const uint64_t row = e / per_row, col = e - row * per_row;
-        dst[(row * G.nb_total + G.b0[p]) * U + col] = src[e];
+    for (uint32_t row = blockIdx.y; row < G.rows; row += gridDim.y) {
+        const uint4 *s = src + (uint64_t)row * per_row;
+        uint4 *d = dst + ((uint64_t)row * G.nb_total + G.b0[p]) * U;
+        for (uint32_t col = blockIdx.x * blockDim.x + threadIdx.x; col < per_row; col += gridDim.x * blockDim.x) d[col] = s[col];
     }
 }
 
@@ -447,9 +448,10 @@ skd_status gather_db(skd_comm *c, skd_db *slice, uint64_t n_total, uint64_t samp
         most = std::max(most, G.nb[p]);
     }
     if (most) {
-        const uint64_t units = (uint64_t)most * G.rows * (STAGE_BYTES / 16);
-        const unsigned gx = (unsigned)std::min<uint64_t>((units + 255) / 256, (uint64_t)(8 * ctx->sm_count / c->world + 1));
-        peer_gather_db_kernel<<<dim3(gx, c->world), 256, 0, ctx->compute>>>(G, reinterpret_cast<uint4 *>(db->tiled));
+        const uint32_t per_row = most * (STAGE_BYTES / 16);
+        const unsigned gx = std::max(1u, std::min(16u, (per_row + 255) / 256));
+        const unsigned gy = std::min<uint32_t>(G.rows, std::max<uint32_t>(1, (uint32_t)(16 * ctx->sm_count) / (gx * c->world)));
+        peer_gather_db_kernel<<<dim3(gx, gy, c->world), 256, 0, ctx->compute>>>(G, reinterpret_cast<uint4 *>(db->tiled));
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) {
             skd_db_free(db);
@@ -640,6 +642,8 @@ skd_status skd_comm_db_upload(skd_comm *c, const uint64_t *bins_slice, skd_loc b
     uint64_t s0, s1;
     skd_slice_rows(n_total, c->rank, c->world, TS, &s0, &s1);
     if (s1 > s0 && !bins_slice) return fail(ctx, SKD_ERR_INVALID, "null bins");
+    if (c->world == 1)  // a group of one: the slice is the database
+        return skd_db_upload(ctx, bins_slice, bins_loc, n_total, sample_stride, kmer_stride, W, sketch_size, kmers, K, out);
     skd_status st = begin_op(c);
     if (st) return st;
     skd_db *slice = nullptr;
@@ -660,6 +664,8 @@ skd_status skd_comm_db_load_skd(skd_comm *c, const char *skd_path, const uint64_
     skd_ctx *ctx = c->ctx;
     uint64_t s0, s1;
     skd_slice_rows(n_total, c->rank, c->world, TS, &s0, &s1);
+    if (c->world == 1)
+        return skd_db_load_skd(ctx, skd_path, sample_indices, n_total, sample_stride, kmer_stride, W, sketch_size, kmers, K, out);
     skd_status st = begin_op(c);
     if (st) return st;
     skd_db *slice = nullptr;
