@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libsketchdist.so")
-SOURCES = ["kernels.cu", "capi.cu", "peer.cu"]
+SOURCES = ["kernels.cu", "capi.cu", "peer.cu", "sortknn.cu"]
 HEADERS = ["kernels.h", "layout.h", "internal.h", os.path.join("..", "..", "include", "sketchdist.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -29,13 +29,31 @@ def stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    if not force and not stale():
+def build(force=False, verbose=False, extra_flags=(), out=None):
+    """Compiles every source to an object (in parallel, only the stale ones) and links the shared library."""
+    out = out or LIB
+    if not force and not extra_flags and out == LIB and not stale():
         return LIB
-    os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    cmd = [find_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
-    subprocess.check_call(cmd, cwd=CSRC)
-    return LIB
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    tag = "" if not extra_flags else "_" + "".join(c if c.isalnum() else "_" for c in " ".join(extra_flags))
+    objdir = os.path.join(HERE, "build")
+    os.makedirs(objdir, exist_ok=True)
+    nvcc = find_nvcc()
+    flags = [f for f in NVCC_FLAGS if f != "-shared"] + list(extra_flags) + (["-Xptxas", "-v"] if verbose else [])
+    hdr_t = max(os.path.getmtime(os.path.join(CSRC, h)) for h in HEADERS)
+    hdr_t = max(hdr_t, os.path.getmtime(os.path.abspath(__file__)))
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + tag + ".o")
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(hdr_t, os.path.getmtime(os.path.join(CSRC, src))):
+            subprocess.check_call([nvcc] + flags + ["-c", "-o", obj, src], cwd=CSRC)
+        return obj
+
+    with ThreadPoolExecutor(len(SOURCES)) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static", "-o", out] + objs)
+    return out
 
 
 BIN = os.path.join(HERE, "bin")

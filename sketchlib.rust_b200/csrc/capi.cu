@@ -213,7 +213,7 @@ skd_status check_pair(skd_ctx *ctx, const skd_db *A, const skd_db *B, bool keep_
 // Group offsets for a dense launch over row blocks [rb0, rb0 + n_rb).
 // `pairs`: the launch goes to dense_kernel, whose tiles span two adjacent column blocks.
 void build_groups(uint32_t group, bool self, uint32_t rb0, uint32_t n_rb, uint32_t nbB, std::vector<uint64_t> *off,
-                  bool pairs, uint32_t cb_lo = 0, uint32_t cb_hi = 0) {
+                  bool pairs, uint32_t cb_lo, uint32_t cb_hi) {
     uint32_t n_groups = (n_rb + group - 1) / group;
     off->assign(n_groups + 1, 0);
     const uint32_t hi = cb_hi ? std::min(cb_hi, nbB) : nbB;
@@ -227,8 +227,11 @@ void build_groups(uint32_t group, bool self, uint32_t rb0, uint32_t n_rb, uint32
 }
 
 // Dense launches (all 64 columns of a tile in use) go to the persistent dense_kernel unless SKD_DENSE_V1 is set.
-bool uses_dense_kernel(const skd_ctx *ctx, int mode, const skd_db *B) {
-    return ctx->dense_v2 && (mode == MODE_DENSE_SELF || mode == MODE_DENSE_CROSS) && B->n > 32;
+// Narrow column sides (<= 32 samples) keep the narrow tile_kernel variants -- unless there are so many k-mer lengths
+// that a tile's counts do not fit shared memory: dense_kernel keeps them in L2 and takes any number.
+bool uses_dense_kernel(const skd_ctx *ctx, int mode, const skd_db *B, const EpiParams &E) {
+    if (!ctx->dense_v2 || (mode != MODE_DENSE_SELF && mode != MODE_DENSE_CROSS)) return false;
+    return B->n > 32 || tile_kernel_smem(E.nk, E.nbins >= 65536, false, 0, false) > kMaxSmem;
 }
 
 // Re-tile chunk c of an asynchronously uploaded database (compute stream waits for its arrival).
@@ -278,8 +281,7 @@ skd_status dense_scratch(skd_ctx *ctx, const EpiParams &E, int slot, void **out)
 // of `off` (group offsets built by build_groups for exactly this row range).
 skd_status launch_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, const EpiParams &E, int mode, uint64_t r0,
                         uint64_t r1, float *dout, const std::vector<uint64_t> &off, const uint64_t *d_grp_off,
-                        uint64_t rect_ld = 0, uint32_t cb_lo = 0, uint32_t cb_hi = 0, uint64_t out_row_begin = ~0ull,
-                        cudaStream_t stream = nullptr) {
+                        uint64_t rect_ld, uint32_t cb_lo, uint32_t cb_hi, uint64_t out_row_begin, cudaStream_t stream) {
     if (!stream) stream = ctx->compute;
     SchedParams S{};
     S.mode = mode;
@@ -302,7 +304,8 @@ skd_status launch_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, const Ep
     const bool count32 = E.nbins >= 65536;
     size_t smem = tile_kernel_smem(E.nk, count32, false, 0, false);
     skd_status st = SKD_OK;
-    if (uses_dense_kernel(ctx, mode, B)) {
+    // the count scratch: dense_kernel's tiles, or the one-pass stream kernel for 9..16 queries (kernels.cu)
+    if (uses_dense_kernel(ctx, mode, B, E) || (mode == MODE_DENSE_CROSS && B->n > 8 && B->n <= 16 && !count32)) {
         st = dense_scratch(ctx, E, stream == ctx->aux[1] ? 1 : 0, &S.counts_scratch);
         if (st) return st;
     }
@@ -358,7 +361,7 @@ skd_status run_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, bool self, 
         c.r0 = r;
         c.r1 = std::min(row_end, (r / TS) * TS + rows_per_chunk);
         build_groups(ctx->group, self, (uint32_t)(c.r0 / TS), (uint32_t)((c.r1 + TS - 1) / TS) - (uint32_t)(c.r0 / TS), B->dev.nb,
-                     &c.off, uses_dense_kernel(ctx, mode, B));
+                     &c.off, uses_dense_kernel(ctx, mode, B, E));
         c.off_pos = off_total;
         off_total += c.off.size();
         chunk_elems = std::max<size_t>(chunk_elems, elems_before(c.r1) - elems_before(c.r0));
@@ -392,7 +395,7 @@ skd_status run_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, bool self, 
                 pos[c] = flat.size();
                 if (r1 > row_begin) {
                     build_groups(ctx->group, true, rb0, (uint32_t)((r1 + TS - 1) / TS) - rb0, A->dev.nb, &offs[c],
-                                 uses_dense_kernel(ctx, mode, A), b0, b1);
+                                 uses_dense_kernel(ctx, mode, A, E), b0, b1);
                     flat.insert(flat.end(), offs[c].begin(), offs[c].end());
                 }
             }
@@ -506,10 +509,6 @@ skd_status run_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, bool self, 
 // it still loses 5 % to its in-kernel candidate lists.
 // E is oriented for the row-owned call (a = queries, b = refs).
 
-skd_status finalize_lists(skd_ctx *ctx, const unsigned long long *dkeys, const float *daux, uint32_t n_parts,
-                          uint64_t part_stride, uint64_t n_rows, uint64_t knn, int kind, uint64_t *idx_out, float *d0_out,
-                          float *d1_out, skd_loc out_loc);
-
 skd_status run_knn_few_queries(skd_ctx *ctx, const skd_db *R, const skd_db *Q, const EpiParams &E, uint64_t knn,
                                uint64_t *idx_out, float *d0_out, float *d1_out, skd_loc out_loc, uint64_t *key_out,
                                float *aux_out, uint64_t idx_offset) {
@@ -544,7 +543,7 @@ skd_status run_knn_few_queries(skd_ctx *ctx, const skd_db *R, const skd_db *Q, c
         const uint64_t g0 = (uint64_t)c * rows_chunk, g1 = std::min(n_ref, g0 + rows_chunk);
         std::vector<uint64_t> off;
         build_groups(ctx->group, false, (uint32_t)(g0 / TS), (uint32_t)((g1 + TS - 1) / TS) - (uint32_t)(g0 / TS), Q->dev.nb, &off,
-                     uses_dense_kernel(ctx, MODE_DENSE_CROSS, Q));
+                     uses_dense_kernel(ctx, MODE_DENSE_CROSS, Q, Ed));
         void *doff;
         st = scratch_get(ctx, "grp_off", off.size() * sizeof(uint64_t), &doff);
         if (st) return st;
@@ -608,16 +607,14 @@ skd_status run_knn(skd_ctx *ctx, const skd_db *R, const skd_db *Q, bool self, co
     const bool partial = key_out != nullptr;
     uint32_t cap = 128;
     while (cap < knn + TS) cap <<= 1;
-    if ((size_t)cap * 12 > (size_t)NST * 2 * STAGE_BYTES)
-        return fail(ctx, SKD_ERR_UNSUPPORTED, "knn=%llu exceeds the device top-k capacity (%d); use the dense output",
-                    (unsigned long long)knn, (int)((size_t)NST * 2 * STAGE_BYTES / 12 / 2 - TS));
     const bool count32 = E.nbins >= 65536;
     size_t smem = tile_kernel_smem(E.nk, count32, true, cap, with_aux);
-    if (smem > kMaxSmem)
-        return fail(ctx, SKD_ERR_UNSUPPORTED,
-                    "knn=%llu with %d k-mer lengths needs %zu B of shared memory per CTA (limit %zu); use a smaller "
-                    "--knn or the dense output",
-                    (unsigned long long)knn, E.nk, smem, kMaxSmem);
+    // Beyond what the list-keeping kernel holds per row in shared memory (knn > 1984), or with so many k-mer lengths
+    // that a tile's counts do not fit: dense keys + a full sort of every row (sortknn.cu).  The reference has no such
+    // limits (--knn is clamped to n - 1, src/lib.rs:379-382; any number of k-mer lengths, jaccard.rs:77).
+    if ((size_t)cap * 12 > (size_t)NST * 2 * STAGE_BYTES || smem > kMaxSmem)
+        return run_knn_sorted(ctx, R, Q, self, E, knn, row_begin, row_end, idx_out, d0_out, d1_out, out_loc, key_out,
+                              aux_out, idx_offset);
     SchedParams S{};
     S.mode = MODE_KNN;
     S.one = 1;
@@ -761,7 +758,7 @@ skd_status run_knn_symmetric(skd_ctx *ctx, const skd_db *db, const EpiParams &E,
         S.n_rb = (uint32_t)((g1 + TS - 1) / TS) - S.rb0;
         S.group = ctx->group;
         std::vector<uint64_t> off;
-        build_groups(ctx->group, true, S.rb0, S.n_rb, db->dev.nb, &off, uses_dense_kernel(ctx, MODE_DENSE_SELF, db));
+        build_groups(ctx->group, true, S.rb0, S.n_rb, db->dev.nb, &off, uses_dense_kernel(ctx, MODE_DENSE_SELF, db, E));
         S.n_groups = (uint32_t)off.size() - 1;
         void *doff;
         st = scratch_get(ctx, "grp_off", off.size() * sizeof(uint64_t), &doff);
@@ -776,7 +773,7 @@ skd_status run_knn_symmetric(skd_ctx *ctx, const skd_db *db, const EpiParams &E,
         S.rect_c0 = g0;
         const bool count32 = E.nbins >= 65536;
         const size_t smem = tile_kernel_smem(E.nk, count32, false, 0, false);
-        if (uses_dense_kernel(ctx, MODE_DENSE_SELF, db)) {
+        if (uses_dense_kernel(ctx, MODE_DENSE_SELF, db, E)) {
             st = dense_scratch(ctx, E, 0, &S.counts_scratch);
             if (st) return st;
         }
@@ -1346,8 +1343,6 @@ skd_status skd_self_knn_partial(skd_ctx *ctx, const skd_db *db, uint64_t knn, sk
     if (db->n < 2 || knn == 0 || knn > db->n - 1)
         return fail(ctx, SKD_ERR_INVALID, "knn must be in [1, n-1] (n = %llu, knn = %llu)", (unsigned long long)db->n,
                     (unsigned long long)knn);
-    if (knn > kSymKnnMax)
-        return fail(ctx, SKD_ERR_UNSUPPORTED, "symmetric self kNN supports knn <= %u", kSymKnnMax);
     if (row_begin % TS != 0) return fail(ctx, SKD_ERR_INVALID, "row_begin must be a multiple of %d", TS);
     EpiParams E;
     st = build_epi(ctx, db, db, dist, completeness, completeness, cutoff, &E);
@@ -1370,7 +1365,18 @@ skd_status skd_self_knn_partial(skd_ctx *ctx, const skd_db *db, uint64_t knn, sk
         return fail(ctx, SKD_ERR_INVALID, "aux_out is required for core/accessory");
     }
     timers_reset(ctx);
-    st = run_knn_symmetric(ctx, db, E, knn, row_begin, std::max(row_begin, row_end), dk, da);
+    if (knn <= kSymKnnMax) {
+        st = run_knn_symmetric(ctx, db, E, knn, row_begin, std::max(row_begin, row_end), dk, da);
+    } else {
+        // The symmetric fold keeps knn + 64 candidates per row and step; beyond that the rows [row_begin, row_end) are
+        // evaluated against ALL columns (both orders of a pair, like the reference) and only they get lists: the row
+        // blocks of a triangle partition cover every row once, so the merged result is the same.
+        launch_fill_u64(dk, n * knn, ~0ull, ctx->compute);
+        ctx->launches++;
+        row_end = std::max(row_begin, row_end);
+        st = run_knn(ctx, db, db, true, E, knn, row_begin, row_end, nullptr, nullptr, nullptr, SKD_DEVICE,
+                     (uint64_t *)(dk + row_begin * knn), with_aux ? da + row_begin * knn : nullptr, 0);
+    }
     if (st) return st;
     if (out_loc == SKD_HOST) {
         CU(ctx, cudaMemcpyAsync(keys_out, dk, n * knn * 8, cudaMemcpyDeviceToHost, ctx->compute));

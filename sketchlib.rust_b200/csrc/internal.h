@@ -93,6 +93,23 @@ skd_status check_pair(skd_ctx *ctx, const skd_db *A, const skd_db *B, bool keep_
 skd_status run_knn(skd_ctx *ctx, const skd_db *R, const skd_db *Q, bool self, const skd::EpiParams &E, uint64_t knn,
                    uint64_t row_begin, uint64_t row_end, uint64_t *idx_out, float *d0_out, float *d1_out, skd_loc out_loc,
                    uint64_t *key_out = nullptr, float *aux_out = nullptr, uint64_t idx_offset = 0);
+// The same contract for the corners of the envelope (knn beyond the per-row list capacity, k-mer counts beyond shared
+// memory): dense keys + a full sort of every row (sortknn.cu).
+skd_status run_knn_sorted(skd_ctx *ctx, const skd_db *R, const skd_db *Q, bool self, const skd::EpiParams &E, uint64_t knn,
+                          uint64_t row_begin, uint64_t row_end, uint64_t *idx_out, float *d0_out, float *d1_out,
+                          skd_loc out_loc, uint64_t *key_out, float *aux_out, uint64_t idx_offset);
+// Dense launches (capi.cu): tile-group offsets, kernel choice, one launch over rows [r0, r1) into device memory.
+void build_groups(uint32_t group, bool self, uint32_t rb0, uint32_t n_rb, uint32_t nbB, std::vector<uint64_t> *off,
+                  bool pairs, uint32_t cb_lo = 0, uint32_t cb_hi = 0);
+bool uses_dense_kernel(const skd_ctx *ctx, int mode, const skd_db *B, const skd::EpiParams &E);
+skd_status launch_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, const skd::EpiParams &E, int mode, uint64_t r0,
+                        uint64_t r1, float *dout, const std::vector<uint64_t> &off, const uint64_t *d_grp_off,
+                        uint64_t rect_ld = 0, uint32_t cb_lo = 0, uint32_t cb_hi = 0, uint64_t out_row_begin = ~0ull,
+                        cudaStream_t stream = nullptr);
+// Final sparse rows from n_parts device-resident partial lists (keys[part][n_rows][knn]).
+skd_status finalize_lists(skd_ctx *ctx, const unsigned long long *dkeys, const float *daux, uint32_t n_parts,
+                          uint64_t part_stride, uint64_t n_rows, uint64_t knn, int kind, uint64_t *idx_out, float *d0_out,
+                          float *d1_out, skd_loc out_loc);
 // Symmetric self-kNN over triangle rows [row_begin, row_end): lists dkey/daux [n][knn] in device memory.
 skd_status run_knn_symmetric(skd_ctx *ctx, const skd_db *db, const skd::EpiParams &E, uint64_t knn, uint64_t row_begin,
                              uint64_t row_end, unsigned long long *dkey, float *daux);

@@ -57,6 +57,18 @@ __device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
         : "r"(smem_u32(bar)), "r"(parity));
     return ok != 0;
 }
+// Wait with back-off for a thread that has nothing else to do (the dense kernel's producer lane).  try_wait alone
+// returns within a few cycles when the phase is still open, and the retry loop (SYNCS + BRA + YIELD) then eats the
+// issue slots of the scheduler the lane shares with consumer warps (ncu, round 2: 14.7 % of all warp instructions of
+// the kernel, ~40 % of that scheduler's slots).  A sleeping warp issues nothing.
+#ifndef SKD_PROD_SLEEP_NS
+#define SKD_PROD_SLEEP_NS 200
+#endif
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) {
+    while (!mbar_test(bar, parity)) {
+        if (SKD_PROD_SLEEP_NS > 0) __nanosleep(SKD_PROD_SLEEP_NS);
+    }
+}
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                      smem_u32(dst_smem)),
@@ -808,11 +820,9 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1)
             // columns are masked in the epilogue
             const uint32_t b_bytes = rc.y + 1 < cb_limit ? 2u * STAGE_BYTES : (uint32_t)STAGE_BYTES;
             for (uint32_t it = 0; it < n_it; ++it) {
-                // wait until all 8 consumer warps have released the stage's previous word.  try_wait suspends the
-                // lane in hardware: a polling loop here took 14 % of the issue slots of the scheduler this warp
-                // shares with two consumer warps, and the whole CTA then ran at the pace of those two.
+                // wait (asleep between probes) until all 8 consumer warps have released the stage's previous word
 #ifndef SKD_ABL_NOWAIT
-                if (use > 0) mbar_wait(&empty_bar[s], (use - 1) & 1u);
+                if (use > 0) mbar_wait_sleep(&empty_bar[s], (use - 1) & 1u);
 #else
                 if (use > 0) break;  // ablation: fill the ring once
 #endif
@@ -1086,7 +1096,11 @@ struct RefWord {  // the 14 planes of both 32-bin halves of one 64-bin word of o
     uint2 t[2];
 };
 
-template <int NQ>
+// GC (9..16 queries in ONE pass over the references instead of two passes of 8): the query side alone fills shared
+// memory (16 x 14 336 B at 1024 bins x 8 k), so the match counts go k-major to the L2-resident count scratch of the
+// dense kernel ([warp][k][query pair][lane], two 16-bit counts per word, 128 contiguous bytes per warp store) and the
+// epilogue reads them back from there (pair_epilogue_k).
+template <int NQ, bool GC>
 __global__ void __launch_bounds__(STREAM_THREADS, 1)
     stream_kernel(const __grid_constant__ DevDb A, const __grid_constant__ DevDb B, const __grid_constant__ EpiParams E,
                   const __grid_constant__ SchedParams S, const uint32_t q0) {
@@ -1095,6 +1109,8 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
     uint4 *qquad = reinterpret_cast<uint4 *>(smem_raw);                   // [word][half][quad][NQ]
     uint2 *qtail = reinterpret_cast<uint2 *>(qquad + (size_t)n_words * 6 * NQ);  // [word][half][NQ]
     uint16_t *counts_all = reinterpret_cast<uint16_t *>(qtail + (size_t)n_words * 2 * NQ);
+    static_assert(!GC || NQ % 2 == 0, "count words pack two queries");
+    constexpr size_t GKSTRIDE = (size_t)(NQ / 2) * 32;  // GC: words between consecutive k of one warp
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t nq_all = (uint32_t)B.n;                      // this launch: queries [q0, q0 + nq)
@@ -1115,8 +1131,13 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
             live ? *reinterpret_cast<const uint2 *>(slab + TAIL_U32 + (q0 + q) * 2) : make_uint2(0, 0);
     }
     uint16_t *counts = counts_all + (size_t)warp * 32 * NQ * E.kp;
-    if (E.kp != E.nk)  // padding slots of the per-pair count words must hold a valid table index
+    uint32_t *gwords = nullptr;  // GC: this lane's count words
+    if (GC) {
+        gwords = reinterpret_cast<uint32_t *>(reinterpret_cast<unsigned char *>(S.counts_scratch) + 256) +
+                 ((size_t)blockIdx.x * (STREAM_THREADS / 32) + warp) * (size_t)E.nk * GKSTRIDE + lane;
+    } else if (E.kp != E.nk) {  // padding slots of the per-pair count words must hold a valid table index
         for (int e = lane; e < 32 * NQ * E.kp; e += 32) counts[e] = 0;
+    }
     __syncthreads();
 
     const uint32_t nbins = 64u * W;
@@ -1172,9 +1193,14 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
                 }
             }
             if (++w_in_k == W) {
+                if (GC) {
+#pragma unroll
+                    for (int q = 0; q < NQ; q += 2)
+                        __stcg(gwords + (size_t)kk * GKSTRIDE + (q / 2) * 32, (nbins - mism[q]) | ((nbins - mism[q + 1]) << 16));
+                }
 #pragma unroll
                 for (int q = 0; q < NQ; ++q) {
-                    counts[(lane * NQ + q) * E.kp + kk] = (uint16_t)(nbins - mism[q]);
+                    if (!GC) counts[(lane * NQ + q) * E.kp + kk] = (uint16_t)(nbins - mism[q]);
                     mism[q] = 0;
                 }
                 w_in_k = 0;
@@ -1189,12 +1215,25 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
                 const uint64_t gj = q0 + q;
                 if (S.mode == MODE_COUNTS) {
                     uint32_t *o = reinterpret_cast<uint32_t *>(S.out) + ((gi - S.row_begin) * nq_all + gj) * (uint64_t)E.nk;
-                    for (int k = 0; k < E.nk; ++k) o[k] = counts[pair * E.kp + k];
+                    for (int k = 0; k < E.nk; ++k)
+                        o[k] = GC ? (__ldcg(gwords + (size_t)k * GKSTRIDE + (q / 2) * 32) >> (16 * (q & 1))) & 0xffffu
+                                  : counts[pair * E.kp + k];
                     continue;
                 }
                 const uint64_t idx = (gi - S.row_begin) * (rect ? S.rect_ld : (uint64_t)nq_all) + gj;
                 float d0, d1;
-                if (E.has_c)
+                if (GC) {
+                    const uint32_t *words = gwords + (q / 2) * 32;
+                    if (E.kind != KIND_CORE_ACC && !E.has_c) {
+                        const uint32_t cnt = (__ldcg(words) >> (16 * (q & 1))) & 0xffffu;
+                        d0 = __ldg(&(rect ? E.key_tab : E.val_tab)[cnt]);
+                        d1 = 0.0f;
+                    } else {
+                        const float2 d = pair_epilogue_k<uint16_t>(words, GKSTRIDE, 16 * (int)(q & 1), E, gi, gj, rect);
+                        d0 = d.x;
+                        d1 = d.y;
+                    }
+                } else if (E.has_c)
                     pair_epilogue<uint16_t, true>(counts, pair, E, gi, gj, rect, d0, d1);
                 else
                     pair_epilogue<uint16_t, false>(counts, pair, E, gi, gj, rect, d0, d1);
@@ -1214,11 +1253,15 @@ __global__ void __launch_bounds__(STREAM_THREADS, 1)
     }
 }
 
-// Shared memory of stream_kernel<NQ>; 0 if the query side does not fit.
-static size_t stream_smem(const DevDb &A, const EpiParams &E, int NQ) {
+// Shared memory of stream_kernel<NQ>; 0 if the query side does not fit.  gc: counts in the L2 scratch instead.
+static size_t stream_smem(const DevDb &A, const EpiParams &E, int NQ, bool gc = false) {
     const size_t n_words = (size_t)E.nk * A.W;
-    const size_t bytes = n_words * 2 * NQ * (3 * 16 + 8) + (size_t)(STREAM_THREADS / 32) * 32 * NQ * E.kp * 2;
+    const size_t bytes = n_words * 2 * NQ * (3 * 16 + 8) + (gc ? 0 : (size_t)(STREAM_THREADS / 32) * 32 * NQ * E.kp * 2);
     return bytes <= 232448 ? bytes : 0;
+}
+// 9..16 queries in one pass: needs the count scratch (dense_kernel_scratch_bytes covers 16 warps x 32 x 16 pairs per SM)
+static bool stream_one_pass_16(const DevDb &A, const DevDb &B, const EpiParams &E, const SchedParams &S) {
+    return B.n > 8 && B.n <= 16 && S.counts_scratch != nullptr && stream_smem(A, E, 16, true) != 0;
 }
 
 static bool stream_applies(const DevDb &A, const DevDb &B, const EpiParams &E, const SchedParams &S, bool count32) {
@@ -1237,16 +1280,23 @@ static cudaError_t launch_stream(const DevDb &A, const DevDb &B, const EpiParams
         cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sm_count <= 0)
         sm_count = 148;
     const int NQ = B.n <= 1 ? 1 : B.n <= 2 ? 2 : B.n <= 4 ? 4 : 8;
-    const size_t smem = stream_smem(A, E, NQ);
+    const bool one16 = stream_one_pass_16(A, B, E, S);
+    const size_t smem = one16 ? stream_smem(A, E, 16, true) : stream_smem(A, E, NQ);
     const uint64_t units = (S.row_end + 31) / 32 - S.row_begin / 32;
     if (units == 0) return cudaSuccess;
     const unsigned ctas = (unsigned)std::min<uint64_t>((uint64_t)sm_count, (units + STREAM_THREADS / 32 - 1) / (STREAM_THREADS / 32));
     cudaError_t err = cudaSuccess;
+    if (one16) {
+        err = cudaFuncSetAttribute(stream_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (err != cudaSuccess) return err;
+        stream_kernel<16, true><<<ctas, STREAM_THREADS, smem, st>>>(A, B, E, S, 0);
+        return cudaGetLastError();
+    }
 #define SKD_STREAM(N)                                                                                          \
     do {                                                                                                       \
-        err = cudaFuncSetAttribute(stream_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+        err = cudaFuncSetAttribute((stream_kernel<N, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
         if (err != cudaSuccess) return err;                                                                    \
-        for (uint32_t q0 = 0; q0 < B.n; q0 += N) stream_kernel<N><<<ctas, STREAM_THREADS, smem, st>>>(A, B, E, S, q0); \
+        for (uint32_t q0 = 0; q0 < B.n; q0 += N) stream_kernel<N, false><<<ctas, STREAM_THREADS, smem, st>>>(A, B, E, S, q0); \
     } while (0)
     if (NQ == 1) SKD_STREAM(1);
     else if (NQ == 2) SKD_STREAM(2);
@@ -1265,7 +1315,9 @@ cudaError_t launch_tiles(const DevDb &A, const DevDb &B, const EpiParams &E, con
     // large reference database) only those columns are loaded and compared.
     const int cols = S.mode == MODE_KNN || TJ != 4 ? TS : (B.n <= 8 ? 8 : B.n <= 16 ? 16 : B.n <= 32 ? 32 : TS);
     cudaError_t err = cudaSuccess;
-    if (cols == TS && TJ == 4 && S.counts_scratch && (S.mode == MODE_DENSE_SELF || S.mode == MODE_DENSE_CROSS)) {
+    // the caller chose dense_kernel (count scratch given, tile groups built over column block pairs)
+    if (TJ == 4 && S.counts_scratch && (S.mode == MODE_DENSE_SELF || S.mode == MODE_DENSE_CROSS) &&
+        (B.n > 32 || smem > 232448)) {  // the rule of uses_dense_kernel (capi.cu)
         // the barrier-free persistent kernel: 2 CTAs per SM, each walking up to MAXT tiles per launch
         int dev = 0, sm_count = 148;
         if (cudaGetDevice(&dev) != cudaSuccess ||
@@ -1933,10 +1985,11 @@ cudaError_t preload_kernels() {
     SKD_PRELOAD(tile_kernel<uint32_t, TS>);
     SKD_PRELOAD(dense_kernel<uint16_t>);
     SKD_PRELOAD(dense_kernel<uint32_t>);
-    SKD_PRELOAD(stream_kernel<1>);
-    SKD_PRELOAD(stream_kernel<2>);
-    SKD_PRELOAD(stream_kernel<4>);
-    SKD_PRELOAD(stream_kernel<8>);
+    SKD_PRELOAD((stream_kernel<1, false>));
+    SKD_PRELOAD((stream_kernel<2, false>));
+    SKD_PRELOAD((stream_kernel<4, false>));
+    SKD_PRELOAD((stream_kernel<8, false>));
+    SKD_PRELOAD((stream_kernel<16, true>));
     SKD_PRELOAD(knn_merge_kernel);
     SKD_PRELOAD(select_few_kernel<true>);
     SKD_PRELOAD(select_few_kernel<false>);

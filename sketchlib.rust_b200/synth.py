@@ -31,16 +31,24 @@ def bit_slice(bins: torch.Tensor) -> torch.Tensor:
 
 
 def make_bins(n, sketchsize64, kmers, seed=0, family_mean=50, mu_range=(0.001, 0.03), acc_range=(0.0, 0.3),
-              device="cpu", chunk=8192):
-    """Returns int64 tensor [n * K * W * 14] (bit pattern = u64 .skd layout) on `device`."""
+              device="cpu", chunk=8192, n_families=None, member_seed=None):
+    """Returns int64 tensor [n * K * W * 14] (bit pattern = u64 .skd layout) on `device`.
+    `n_families` / `member_seed`: the family ancestors depend only on (seed, n_families, sketch shape); with a
+    different member_seed the same families get different members -- queries related to a reference set."""
     g = torch.Generator(device=device)
     g.manual_seed(int(seed))
     K, nbins = len(kmers), 64 * sketchsize64
-    n_fam = max(1, int(round(n / family_mean)))
+    n_fam = int(n_families) if n_families else max(1, int(round(n / family_mean)))
     # geometric-ish family sizes: assign each sample a family with exponentially decaying weights
     w = torch.rand(n_fam, generator=g, device=device).clamp_min(1e-6).log().neg()  # Exp(1) weights
-    fam = torch.multinomial(w, n, replacement=True, generator=g)
-    anc = torch.randint(0, 1 << BBITS, (n_fam, K, nbins), generator=g, device=device, dtype=torch.int16)
+    if member_seed is None:
+        fam = torch.multinomial(w, n, replacement=True, generator=g)
+        anc = torch.randint(0, 1 << BBITS, (n_fam, K, nbins), generator=g, device=device, dtype=torch.int16)
+    else:  # ancestors first (independent of n), then the members from their own stream
+        anc = torch.randint(0, 1 << BBITS, (n_fam, K, nbins), generator=g, device=device, dtype=torch.int16)
+        g = torch.Generator(device=device)
+        g.manual_seed(int(member_seed))
+        fam = torch.multinomial(w, n, replacement=True, generator=g)
     mu = torch.empty(n, device=device).uniform_(*mu_range, generator=g)
     acc = torch.empty(n, device=device).uniform_(*acc_range, generator=g)
     kt = torch.tensor(list(kmers), device=device, dtype=torch.float32)

@@ -499,8 +499,78 @@ def test_self_knn_partials_merge_like_ranks(sk, ctx):
             assert np.array_equal(merged.idx, whole.idx) and np.array_equal(merged.d0, whole.d0)
             if dt.kind == sk.CORE_ACC:
                 assert np.array_equal(merged.d1, whole.d1)
-    with pytest.raises(sk.SketchDistError, match="knn <= 64"):
-        sk.self_knn_partial(g, knn=65, dist_type=sk.set_k(g, 21))
+    # beyond the symmetric fold's list size (64) the row blocks are evaluated against all columns: same merged rows
+    dt = sk.set_k(g)
+    whole = sk.self_dists_knn(g, knn=100, dist_type=dt)
+    parts = [sk.self_knn_partial(g, knn=100, dist_type=dt, rows=sk.triangle_row_partition(650, r, 3)) for r in range(3)]
+    merged = sk.knn_merge(ctx, [p[0] for p in parts], [p[1] for p in parts], dt, db.names)
+    assert np.array_equal(merged.d0, whole.d0) and np.array_equal(merged.d1, whole.d1)
+
+
+# ------------------------------------------------------------------ the reference's envelope (no knn or k-mer limits)
+def test_knn_beyond_list_capacity_and_up_to_n_minus_1(sk, ctx):
+    """--knn is clamped to n - 1 and runs (src/lib.rs:379-382): knn = 2000 (more than the row-owned kernel's 1984
+    shared-memory candidates) and knn = n - 1 (every other sample, sorted) go through dense keys + a full row sort."""
+    n = 2300
+    db = synth_db(n, 16, [15, 19, 23, 27], seed=80, n_families=20, unrelated_frac=0.05)
+    g = up(sk, ctx, db)
+    for knn in (2000, n - 1):
+        got = sk.self_dists_knn(g, knn=knn, dist_type=sk.set_k(g, 19))
+        assert got.idx.shape == (n, knn) and (np.diff(got.d0, axis=1) >= 0).all()
+        assert (got.idx != np.arange(n)[:, None]).all()
+        oidx, od0, _ = oracle.self_dists_knn(db, knn, k_idx=1, threads=16, rows=(0, 40))
+        assert_knn_matches(got.idx[:40], got.d0[:40], None, oidx, od0, None, True)
+        oidx, od0, _ = oracle.self_dists_knn(db, knn, k_idx=1, threads=16, rows=(n - 30, n))
+        assert_knn_matches(got.idx[n - 30:], got.d0[n - 30:], None, oidx, od0, None, True)
+    assert all(sorted(r.tolist()) == [x for x in range(n) if x != i] for i, r in enumerate(got.idx[:50]))
+    # core/accessory, row range, and the ANI round trip on the same path
+    got = sk.self_dists_knn(g, knn=2100, dist_type=sk.set_k(g), rows=(100, 164))
+    oidx, od0, od1 = oracle.self_dists_knn(db, 2100, threads=16, rows=(100, 164))
+    assert_knn_matches(got.idx, got.d0, got.d1, oidx, od0, od1, False)
+    got = sk.self_dists_knn(g, knn=2000, dist_type=sk.set_k(g, 19, ani=True), rows=(0, 16))
+    _, od0, _ = oracle.self_dists_knn(db, 2000, k_idx=1, ani=True, threads=16, rows=(0, 16))
+    assert np.array_equal(got.d0, od0)
+    # cross: knn larger than the list capacity, clamped to the number of references
+    ref, qry = synth_pair(2100, 70, 16, [15, 19, 23, 27], seed=81, n_families=15)
+    gr, gq = up(sk, ctx, ref), up(sk, ctx, qry)
+    got = sk.cross_dists_knn(gr, gq, knn=5000, dist_type=sk.set_k(gr))
+    assert got.knn == 2100 and got.idx.shape == (70, 2100)
+    oidx, od0, od1 = oracle.cross_dists_knn(ref, qry, 5000, threads=16)
+    assert_knn_matches(got.idx, got.d0, got.d1, oidx, od0, od1, False)
+
+
+def test_thirty_kmer_lengths(sk, ctx):
+    """The reference's regression loops over any number of k-mer lengths (src/distances/jaccard.rs:77).  30 of them:
+    a 64 x 64 tile's counts no longer fit shared memory, so dense runs keep them in L2 (dense_kernel) and kNN runs go
+    through the symmetric fold / dense keys."""
+    kmers = list(range(5, 65, 2))
+    assert len(kmers) == 30
+    n = 400
+    db = synth_db(n, 16, kmers, seed=82, n_families=5, mu_range=(0.0005, 0.004))
+    g = up(sk, ctx, db)
+    dt = sk.set_k(g)
+    check_close(sk.self_dists_all(g, dist_type=dt).distances, oracle.self_dists_all(db, threads=16))
+    got = sk.self_dists_knn(g, knn=20, dist_type=dt)
+    oidx, od0, od1 = oracle.self_dists_knn(db, 20, threads=16)
+    assert_knn_matches(got.idx, got.d0, got.d1, oidx, od0, od1, False)
+    rows = sk.self_dists_knn(g, knn=20, dist_type=dt, rows=(64, 200))   # row-owned call: the sorted path
+    assert np.array_equal(rows.d0, got.d0[64:200])
+    ref, qry = synth_pair(300, 90, 16, kmers, seed=83, n_families=4, mu_range=(0.0005, 0.004))
+    gr, gq = up(sk, ctx, ref), up(sk, ctx, qry)
+    check_close(sk.cross_dists_all(gr, gq, dist_type=sk.set_k(gr)).distances, oracle.cross_dists_all(ref, qry, threads=16))
+    gotc = sk.cross_dists_knn(gr, gq, knn=15, dist_type=sk.set_k(gr))
+    oidx, od0, od1 = oracle.cross_dists_knn(ref, qry, 15, threads=16)
+    assert_knn_matches(gotc.idx, gotc.d0, gotc.d1, oidx, od0, od1, False)
+    # a handful of queries: too many k-mer lengths for the narrow shared-memory variants as well
+    few = oracle.Db(qry.bins[:5 * qry.sample_stride], 5, kmers, 16)
+    gf = up(sk, ctx, few)
+    check_close(sk.cross_dists_all(gr, gf, dist_type=sk.set_k(gr)).distances, oracle.cross_dists_all(ref, few, threads=16))
+    gotf = sk.cross_dists_knn(gr, gf, knn=15, dist_type=sk.set_k(gr))
+    oidx, od0, od1 = oracle.cross_dists_knn(ref, few, 15, threads=16)
+    assert_knn_matches(gotf.idx, gotf.d0, gotf.d1, oidx, od0, od1, False)
+    # single k of the 30 and the raw counts
+    c = sk.match_counts(g, g, pairs=[(0, 1), (5, 399)])
+    assert np.array_equal(c, oracle.match_counts(db, db, [(0, 1), (5, 399)]))
 
 
 def test_cross_knn_ref_shards_merge(sk, ctx):
