@@ -415,7 +415,7 @@ def main():
         per_gpu = [p * LOP3_PER_PAIR / (t * 1e-3) / 1e12 for p, t in zip(pairs_all, tile_ms_all)]
         achieved = per_gpu[0]
         ncu = None
-        p = os.path.join(ROOT, "profiles", "ncu_tile_kernel_summary.json")
+        p = os.path.join(ROOT, "profiles", "r2_ncu_dense_kernel_knn100k.json")
         if os.path.exists(p):
             try:
                 ncu = json.load(open(p))
@@ -424,7 +424,7 @@ def main():
         roofline = {
             "bound": "int",
             "bound_note": "integer ALU (LOP3) issue: the kernel is bitwise, neither HBM- nor tensor-core-bound",
-            "kernel": "skd::tile_kernel<uint16_t, 64> (rect mode: kNN keys of upper-triangle row groups)",
+            "kernel": "skd::dense_kernel<uint16_t> (rect mode: kNN keys of upper-triangle row groups, persistent 64x128 tiles)",
             "achieved": achieved, "peak": lop3_peak, "unit": "TLOP3/s", "frac": achieved / lop3_peak,
             "per_gpu_frac": [a / lop3_peak for a in per_gpu],
             "tile_kernel_ms_per_step": tile_ms, "all_kernels_ms_per_step": kern_ms,
@@ -435,6 +435,7 @@ def main():
             "mix_frac": achieved * 1e12 / peaks["mix_lop3_per_s"] if peaks and peaks.get("mix_lop3_per_s") else None,
             "peak_clock_mhz": (peaks or {}).get("sm_mhz"),
             "traffic": (ncu or {}).get("dram_bytes_per_launch"),
+            "traffic_note": (ncu or {}).get("traffic_note"),
             "int_peaks": peaks,
         }
         line = {

@@ -231,7 +231,11 @@ void build_groups(uint32_t group, bool self, uint32_t rb0, uint32_t n_rb, uint32
 // that a tile's counts do not fit shared memory: dense_kernel keeps them in L2 and takes any number.
 bool uses_dense_kernel(const skd_ctx *ctx, int mode, const skd_db *B, const EpiParams &E) {
     if (!ctx->dense_v2 || (mode != MODE_DENSE_SELF && mode != MODE_DENSE_CROSS)) return false;
-    return B->n > 32 || tile_kernel_smem(E.nk, E.nbins >= 65536, false, 0, false) > kMaxSmem;
+    if (tile_kernel_smem(E.nk, E.nbins >= 65536, false, 0, false) > kMaxSmem) return true;
+    // dense_kernel's tiles span two column blocks: with an odd, small number of them (cross runs against 33..64,
+    // 129..192, ... queries) the empty half of the last pair would idle half the warps of 1 / (nb + 1) of the tiles
+    const uint32_t nb = B->dev.nb;
+    return mode == MODE_DENSE_SELF ? B->n > 64 : (nb >= 2 && (nb % 2 == 0 || nb >= 16));
 }
 
 // Re-tile chunk c of an asynchronously uploaded database (compute stream waits for its arrival).
@@ -305,12 +309,13 @@ skd_status launch_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, const Ep
     size_t smem = tile_kernel_smem(E.nk, count32, false, 0, false);
     skd_status st = SKD_OK;
     // the count scratch: dense_kernel's tiles, or the one-pass stream kernel for 9..16 queries (kernels.cu)
-    if (uses_dense_kernel(ctx, mode, B, E) || (mode == MODE_DENSE_CROSS && B->n > 8 && B->n <= 16 && !count32)) {
+    S.dense_pairs = uses_dense_kernel(ctx, mode, B, E);
+    if (S.dense_pairs || (mode == MODE_DENSE_CROSS && B->n > 8 && B->n <= 16 && !count32)) {
         st = dense_scratch(ctx, E, stream == ctx->aux[1] ? 1 : 0, &S.counts_scratch);
         if (st) return st;
     }
     // tile_kernel keeps a tile's counts in shared memory; dense_kernel keeps them in L2
-    if (!S.counts_scratch && smem > kMaxSmem)
+    if (!S.dense_pairs && smem > kMaxSmem)
         return fail(ctx, SKD_ERR_UNSUPPORTED, "%d k-mer lengths at %u bins need %zu B of shared memory per tile", E.nk,
                     E.nbins, smem);
     st = timer_begin(ctx, stream, 1);
@@ -773,11 +778,12 @@ skd_status run_knn_symmetric(skd_ctx *ctx, const skd_db *db, const EpiParams &E,
         S.rect_c0 = g0;
         const bool count32 = E.nbins >= 65536;
         const size_t smem = tile_kernel_smem(E.nk, count32, false, 0, false);
-        if (uses_dense_kernel(ctx, MODE_DENSE_SELF, db, E)) {
+        S.dense_pairs = uses_dense_kernel(ctx, MODE_DENSE_SELF, db, E);
+        if (S.dense_pairs) {
             st = dense_scratch(ctx, E, 0, &S.counts_scratch);
             if (st) return st;
         }
-        if (!S.counts_scratch && smem > kMaxSmem)
+        if (!S.dense_pairs && smem > kMaxSmem)
             return fail(ctx, SKD_ERR_UNSUPPORTED, "%d k-mer lengths at %u bins need %zu B of shared memory per tile", E.nk,
                         E.nbins, smem);
         st = timer_begin(ctx, nullptr, 1);

@@ -1316,8 +1316,7 @@ cudaError_t launch_tiles(const DevDb &A, const DevDb &B, const EpiParams &E, con
     const int cols = S.mode == MODE_KNN || TJ != 4 ? TS : (B.n <= 8 ? 8 : B.n <= 16 ? 16 : B.n <= 32 ? 32 : TS);
     cudaError_t err = cudaSuccess;
     // the caller chose dense_kernel (count scratch given, tile groups built over column block pairs)
-    if (TJ == 4 && S.counts_scratch && (S.mode == MODE_DENSE_SELF || S.mode == MODE_DENSE_CROSS) &&
-        (B.n > 32 || smem > 232448)) {  // the rule of uses_dense_kernel (capi.cu)
+    if (TJ == 4 && S.dense_pairs && S.counts_scratch && (S.mode == MODE_DENSE_SELF || S.mode == MODE_DENSE_CROSS)) {
         // the barrier-free persistent kernel: 2 CTAs per SM, each walking up to MAXT tiles per launch
         int dev = 0, sm_count = 148;
         if (cudaGetDevice(&dev) != cudaSuccess ||

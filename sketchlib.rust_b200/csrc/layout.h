@@ -107,9 +107,11 @@ struct SchedParams {
     unsigned long long *part_key; // [n_rb][n_split][TS][cap] composite (key bits << 32 | idx); the first knn
                                   // of each list are its best, ascending, when the kernel ends
     float *part_aux;              // same shape: accessory distance (core/acc only)
-    // dense modes: per-CTA match-count scratch of dense_kernel (2 x SM count CTAs x 4096 pairs x kp counts); null
-    // selects the one-tile-per-CTA tile_kernel
+    // dense modes: match-count scratch in L2 (SM count x 8192 pairs x kp counts, behind a 256-byte header holding
+    // dense_kernel's tile counter): used by dense_kernel and by the one-pass 16-query stream kernel
     void *counts_scratch;
+    // the launch goes to dense_kernel (tile groups were built over column block PAIRS); 0 = tile_kernel
+    uint32_t dense_pairs;
 };
 
 }  // namespace skd

@@ -17,7 +17,8 @@ gr = sk.SketchDb.upload(ctx, bins.data_ptr(), n_ref, kmers, 16, bins_loc=sk.SKD_
 del bins
 torch.cuda.empty_cache()
 peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists("MEASURED_PEAKS.json") else 6551.4
-for nq in (1, 4, 8, 16, 32, 48, 64, 128):
+LOP3_PEAK = float(os.environ.get("SKD_LOP3_PEAK", 18.44e12))  # tools/int_peak on this pool
+for nq in (1, 4, 8, 9, 12, 16, 24, 32, 48, 64, 128):
     q = synth.make_bins(nq, 16, kmers, seed=7, device="cuda")
     gq = sk.SketchDb.upload(ctx, q.data_ptr(), nq, kmers, 16, bins_loc=sk.SKD_DEVICE)
     dt = sk.set_k(gr)
@@ -30,5 +31,8 @@ for nq in (1, 4, 8, 16, 32, 48, 64, 128):
     knn_ms = ctx.last_kernel_ms
     print(json.dumps({"n_ref": n_ref, "n_query": nq, "dense_ms": best, "ref_stream_GBps": gr.hbm_bytes / best / 1e6,
                       "frac_of_hbm_peak": gr.hbm_bytes / best / 1e6 / peak, "pairs_per_s": n_ref * nq / best * 1e3,
-                      "knn50_ms": knn_ms}))
+                      "knn50_ms": knn_ms,
+                      # the path's two rooflines for this shape: one pass over the reference planes / the LOP3 issue rate
+                      "bound_ms": max(gr.hbm_bytes / peak / 1e6, n_ref * nq * 3584 / LOP3_PEAK * 1e3),
+                      "frac_of_bound": max(gr.hbm_bytes / peak / 1e6, n_ref * nq * 3584 / LOP3_PEAK * 1e3) / best}))
     ctx.device_free(out); gq.free()

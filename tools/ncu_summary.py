@@ -56,12 +56,13 @@ def main():
                 continue
             if u in UNIT_SCALE and "bytes" in h:
                 x, u = x * UNIT_SCALE[u], "byte"
-            metrics[h] = {"value": x, "unit": u}
+            metrics[h] = (x, u)
+    flat = {f"{h} [{u}]" if u else h: x for h, (x, u) in metrics.items()}
     out = {"report": args.rep, "command": args.command, "note": args.note, "kernel": row[ki],
            "grid": row[hdr.index("Grid Size")] if "Grid Size" in hdr else None,
-           "block": row[hdr.index("Block Size")] if "Block Size" in hdr else None, "metrics": metrics}
+           "block": row[hdr.index("Block Size")] if "Block Size" in hdr else None, "metrics": flat}
     if "dram__bytes_read.sum" in metrics:
-        out["dram_bytes_per_launch"] = metrics["dram__bytes_read.sum"]["value"] + metrics["dram__bytes_write.sum"]["value"]
+        out["dram_bytes_per_launch"] = metrics["dram__bytes_read.sum"][0] + metrics["dram__bytes_write.sum"][0]
     src = ncu_csv(args.rep, "source")
     # the source page holds one table per kernel: take the one whose title matches
     start = 0
