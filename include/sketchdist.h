@@ -66,6 +66,14 @@ const char *skd_last_error(const skd_ctx *ctx);
 int skd_ctx_device(const skd_ctx *ctx);
 /* Kernels launched by this context since creation (bench.py's gpu_launches). */
 uint64_t skd_ctx_launch_count(const skd_ctx *ctx);
+/* Work actually done by the dense core/accessory kernel since the context was created (or the last reset): like the
+ * reference's loop (src/distances/jaccard.rs:89-91: `break` at the first k-mer length without a match) the kernel stops
+ * counting a 16 x 64 block of pairs after the third k-mer length when (almost) every pair of it is already final.
+ * steps_computed / steps_total = the share of the (warp, 64-bin word) match-count steps that were executed;
+ * pairs_deferred = pairs finished one by one afterwards.  SKD_EARLY_OUT=0 in the environment disables the early exit
+ * (steps_computed == steps_total).  Measurement aid; synchronises the context's streams. */
+skd_status skd_ctx_work_counters(skd_ctx *ctx, uint64_t *steps_computed, uint64_t *steps_total, uint64_t *pairs_deferred,
+                                 int reset);
 /* Device time in ms of the distance kernels of the last compute call, measured with CUDA events on
  * the context's compute stream (the stream the kernels are launched on). */
 float skd_ctx_last_kernel_ms(const skd_ctx *ctx);

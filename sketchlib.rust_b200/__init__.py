@@ -63,6 +63,7 @@ def load_library(build=True):
         "skd_last_error": (C.c_char_p, [vp]),
         "skd_ctx_device": (C.c_int, [vp]),
         "skd_ctx_launch_count": (u64, [vp]),
+        "skd_ctx_work_counters": (C.c_int, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]),
         "skd_ctx_last_kernel_ms": (C.c_float, [vp]),
         "skd_ctx_last_tile_kernel_ms": (C.c_float, [vp]),
         "skd_ctx_synchronize": (C.c_int, [vp]),
@@ -187,6 +188,12 @@ class Context:
     @property
     def launch_count(self):
         return int(self.lib.skd_ctx_launch_count(self.handle))
+
+    def work_counters(self, reset=False):
+        """(steps_computed, steps_total, pairs_deferred) of the dense core/accessory kernel (skd_ctx_work_counters)."""
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(self.lib.skd_ctx_work_counters(self.handle, C.byref(a), C.byref(b), C.byref(c), int(bool(reset))))
+        return int(a.value), int(b.value), int(c.value)
 
     @property
     def last_kernel_ms(self):

@@ -34,8 +34,23 @@ def build(force=False, verbose=False, extra_flags=(), out=None):
     out = out or LIB
     if not force and not extra_flags and out == LIB and not stale():
         return LIB
+    import fcntl
     from concurrent.futures import ThreadPoolExecutor
     os.makedirs(os.path.dirname(out), exist_ok=True)
+    # several ranks of one job may find the library stale at the same moment: one builds, the others wait and re-check
+    lock = open(os.path.join(os.path.dirname(out), ".build.lock"), "w")
+    fcntl.flock(lock, fcntl.LOCK_EX)
+    try:
+        if not force and not extra_flags and out == LIB and not stale():
+            return LIB
+        return _build_locked(force, verbose, extra_flags, out)
+    finally:
+        fcntl.flock(lock, fcntl.LOCK_UN)
+        lock.close()
+
+
+def _build_locked(force, verbose, extra_flags, out):
+    from concurrent.futures import ThreadPoolExecutor
     tag = "" if not extra_flags else "_" + "".join(c if c.isalnum() else "_" for c in " ".join(extra_flags))
     objdir = os.path.join(HERE, "build")
     os.makedirs(objdir, exist_ok=True)

@@ -280,6 +280,38 @@ skd_status dense_scratch(skd_ctx *ctx, const EpiParams &E, int slot, void **out)
     return scratch_get(ctx, slot ? "tile_counts1" : "tile_counts0",
                        dense_kernel_scratch_bytes(E.kp, E.nbins >= 65536, ctx->sm_count), out);
 }
+// The early exit of dense_kernel (core/accessory, more than three k-mer lengths): list for the deferred pairs.
+constexpr uint32_t kDeferCap = 8u << 20;  // entries of 32 bytes
+skd_status ensure_rows(skd_ctx *ctx, const skd_db *cdb) {
+    skd_db *db = const_cast<skd_db *>(cdb);
+    if (db->rows || db->n == 0 || db->is_pending()) return SKD_OK;
+    const size_t bytes = (size_t)db->n * db->kmers.size() * db->W * BBITS * sizeof(uint64_t);
+    CU(ctx, cudaMallocAsync((void **)&db->rows, bytes, ctx->compute));
+    launch_untile(db->dev, db->rows, ctx->compute);
+    CU(ctx, cudaGetLastError());
+    ctx->launches++;
+    return SKD_OK;
+}
+skd_status defer_setup(skd_ctx *ctx, const skd_db *A, const skd_db *B, const EpiParams &E, int slot, SchedParams *S) {
+    S->defer_list = nullptr;
+    S->defer_cap = S->defer_max = 0;
+    S->a_rows = S->b_rows = nullptr;
+    S->work_stats = ctx->work_stats;
+    if (!ctx->early_out || !S->dense_pairs || E.kind != KIND_CORE_ACC || E.nk <= 3) return SKD_OK;
+    if (A->is_pending() || B->is_pending() || slot != 0) return SKD_OK;  // column bands of an upload still in flight
+    skd_status st = ensure_rows(ctx, A);
+    if (st) return st;
+    if ((st = ensure_rows(ctx, B))) return st;
+    void *p;
+    st = scratch_get(ctx, "defer_list0", (size_t)kDeferCap * 2 * sizeof(uint4), &p);
+    if (st) return st;
+    S->defer_list = (uint4 *)p;
+    S->defer_cap = kDeferCap;
+    S->defer_max = ctx->defer_max;
+    S->a_rows = A->rows;
+    S->b_rows = B->rows;
+    return SKD_OK;
+}
 
 // Launch the tile kernel for rows [r0, r1) writing to device memory `dout`.  `d_grp_off` is the device copy
 // of `off` (group offsets built by build_groups for exactly this row range).
@@ -314,6 +346,8 @@ skd_status launch_dense(skd_ctx *ctx, const skd_db *A, const skd_db *B, const Ep
         st = dense_scratch(ctx, E, stream == ctx->aux[1] ? 1 : 0, &S.counts_scratch);
         if (st) return st;
     }
+    st = defer_setup(ctx, A, B, E, stream == ctx->compute ? 0 : 1, &S);
+    if (st) return st;
     // tile_kernel keeps a tile's counts in shared memory; dense_kernel keeps them in L2
     if (!S.dense_pairs && smem > kMaxSmem)
         return fail(ctx, SKD_ERR_UNSUPPORTED, "%d k-mer lengths at %u bins need %zu B of shared memory per tile", E.nk,
@@ -783,6 +817,8 @@ skd_status run_knn_symmetric(skd_ctx *ctx, const skd_db *db, const EpiParams &E,
             st = dense_scratch(ctx, E, 0, &S.counts_scratch);
             if (st) return st;
         }
+        st = defer_setup(ctx, db, db, E, 0, &S);
+        if (st) return st;
         if (!S.dense_pairs && smem > kMaxSmem)
             return fail(ctx, SKD_ERR_UNSUPPORTED, "%d k-mer lengths at %u bins need %zu B of shared memory per tile", E.nk,
                         E.nbins, smem);
@@ -1050,6 +1086,8 @@ skd_status skd_ctx_create(int device, skd_ctx **out) {
     }
     if (const char *e = getenv("SKD_ZEROCOPY")) ctx->zero_copy = atoi(e) != 0;
     if (const char *e = getenv("SKD_DENSE_V1")) ctx->dense_v2 = atoi(e) == 0;
+    if (const char *e = getenv("SKD_EARLY_OUT")) ctx->early_out = atoi(e) != 0;
+    if (const char *e = getenv("SKD_DEFER_MAX")) ctx->defer_max = (uint32_t)std::max(0, atoi(e));
     if (const char *e = getenv("SKD_GROUP")) ctx->group = (uint32_t)std::max(1, atoi(e));
     if (const char *e = getenv("SKD_UPLOAD_CHUNK_MB")) ctx->upload_chunk_bytes = (size_t)std::max(1, atoi(e)) << 20;
     if (const char *e = getenv("SKD_KNN_SYMMETRIC")) ctx->knn_symmetric = atoi(e) != 0;
@@ -1062,7 +1100,28 @@ skd_status skd_ctx_create(int device, skd_ctx **out) {
         cudaEventCreateWithFlags(&ctx->ev_a[i], cudaEventDisableTiming);
         cudaEventCreateWithFlags(&ctx->ev_b[i], cudaEventDisableTiming);
     }
+    if (cudaMalloc(&ctx->work_stats, 4 * sizeof(unsigned long long)) == cudaSuccess)
+        cudaMemset(ctx->work_stats, 0, 4 * sizeof(unsigned long long));
+    else
+        ctx->work_stats = nullptr;
     *out = ctx;
+    return SKD_OK;
+}
+
+skd_status skd_ctx_work_counters(skd_ctx *ctx, uint64_t *steps_computed, uint64_t *steps_total, uint64_t *pairs_deferred,
+                                 int reset) {
+    if (!ctx) return SKD_ERR_INVALID;
+    CU(ctx, cudaSetDevice(ctx->device));
+    unsigned long long v[4] = {0, 0, 0, 0};
+    if (ctx->work_stats) {
+        CU(ctx, cudaStreamSynchronize(ctx->compute));
+        CU(ctx, cudaStreamSynchronize(ctx->aux[1]));
+        CU(ctx, cudaMemcpy(v, ctx->work_stats, sizeof v, cudaMemcpyDeviceToHost));
+        if (reset) CU(ctx, cudaMemset(ctx->work_stats, 0, sizeof v));
+    }
+    if (steps_computed) *steps_computed = v[1] - v[3];
+    if (steps_total) *steps_total = v[1];
+    if (pairs_deferred) *pairs_deferred = v[2];
     return SKD_OK;
 }
 
@@ -1082,6 +1141,7 @@ void skd_ctx_destroy(skd_ctx *ctx) {
         cudaEventDestroy(t.first);
         cudaEventDestroy(t.second);
     }
+    if (ctx->work_stats) cudaFree(ctx->work_stats);
     if (ctx->compute) cudaStreamDestroy(ctx->compute);
     if (ctx->copy) cudaStreamDestroy(ctx->copy);
     for (int i = 0; i < 2; ++i)
@@ -1198,6 +1258,7 @@ void skd_db_free(skd_db *db) {
     }
     if (db->tiled) cudaFreeAsync(db->tiled, st);  // back to the device pool: the next upload reuses it
     if (db->lny_dev) cudaFreeAsync(db->lny_dev, st);
+    if (db->rows) cudaFreeAsync(db->rows, st);
     delete db;
 }
 skd_status skd_db_adopt(skd_ctx *ctx, skd_db *db) {

@@ -36,6 +36,10 @@ struct skd_ctx {
     bool knn_symmetric = true;  // SKD_KNN_SYMMETRIC=0: whole-matrix self kNN evaluates both (i,j) and (j,i)
     bool dense_v2 = true;    // dense modes run the persistent barrier-free dense_kernel (SKD_DENSE_V1=1: tile_kernel)
     bool zero_copy = true;   // dense kernels store straight into pinned host results (SKD_ZEROCOPY=0 disables)
+    bool early_out = true;   // core/accessory dense_kernel: warps stop counting after the third k-mer length when (almost)
+                             // all their pairs are final, the rest goes to defer_kernel (SKD_EARLY_OUT=0 disables)
+    uint32_t defer_max = 32; // SKD_DEFER_MAX: open pairs of a 16 x 64 warp block that may be deferred
+    unsigned long long *work_stats = nullptr;  // device: [1] warp x word steps in all, [3] steps skipped, [2] deferred pairs
     // Tunables, read once from the environment when the context is created.
     size_t upload_chunk_bytes = 64ull << 20;  // SKD_UPLOAD_CHUNK_MB: staging chunk of a pageable/file upload
     size_t result_chunk_bytes = 64ull << 20;  // SKD_RESULT_CHUNK_MB: staged D2H chunk of dense results
@@ -55,6 +59,7 @@ struct skd_db {
     std::vector<uint64_t> kmers;
     uint64_t sketch_size = 0, W = 0, n = 0;
     double *lny_dev = nullptr;  // [nbins + 1]
+    uint64_t *rows = nullptr;   // sample-major copy of the planes, made on demand for the early exit's pair kernel
     // skd_db_upload_async: the raw planes are still arriving (copy stream, one event per chunk of whole sample
     // blocks); they are re-tiled by the first compute call -- band by band, interleaved with the tile kernel, when
     // that call is a dense self run, so that the PCIe transfer overlaps the distance computation.

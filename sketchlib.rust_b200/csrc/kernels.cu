@@ -117,6 +117,39 @@ void launch_repack(const uint64_t *raw, uint64_t raw_samples, uint64_t sample_st
     repack_kernel<<<grid, 256, 0, st>>>(raw, raw_samples, sample_stride, kmer_stride, tiled, db, b0);
 }
 
+// The inverse, tiled -> sample-major u64 [sample][k][w][plane] (the reference's .skd layout): one sample's planes of one
+// k-mer length are W x 112 contiguous bytes.  Built on demand for defer_kernel, which compares single pairs: from the
+// tiled layout a pair costs 16-byte pieces out of 2 x 8 x W x 8 different slabs (half of every 32-byte sector wasted).
+__global__ void __launch_bounds__(256) untile_kernel(const __grid_constant__ DevDb db, uint64_t *__restrict__ rows) {
+    __shared__ uint64_t sh[TS][BBITS + 1];
+    const uint32_t b = blockIdx.x, w = blockIdx.y, k = blockIdx.z;
+    const uint32_t *src = db.tiled + slab_index(db, k, w, b) * STAGE_U32;
+    for (int t = threadIdx.x; t < TS * BBITS; t += blockDim.x) {
+        const int p = t / TS, sm = t % TS;  // consecutive threads: consecutive samples of one plane
+        const int q = p / 4;
+        uint32_t lo, hi;
+        if (q < 3) {
+            lo = src[q * QUAD_U32 + sm * 4 + (p - 4 * q)];
+            hi = src[HALF_U32 + q * QUAD_U32 + sm * 4 + (p - 4 * q)];
+        } else {
+            lo = src[TAIL_U32 + sm * 2 + (p - 12)];
+            hi = src[HALF_U32 + TAIL_U32 + sm * 2 + (p - 12)];
+        }
+        sh[sm][p] = (uint64_t)lo | ((uint64_t)hi << 32);
+    }
+    __syncthreads();
+    const uint64_t sample_stride = (uint64_t)db.K * db.W * BBITS;
+    for (int t = threadIdx.x; t < TS * BBITS; t += blockDim.x) {
+        const int sm = t / BBITS, p = t % BBITS;
+        const uint64_t gs = (uint64_t)b * TS + sm;
+        if (gs < db.n) rows[gs * sample_stride + ((uint64_t)k * db.W + w) * BBITS + p] = sh[sm][p];
+    }
+}
+void launch_untile(const DevDb &db, uint64_t *rows, cudaStream_t st) {
+    if (db.n == 0) return;
+    untile_kernel<<<dim3(db.nb, db.W, db.K), 256, 0, st>>>(db, rows);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Epilogue arithmetic.  All f64 operations use the explicit round-to-nearest intrinsics so that no
 // FMA contraction can change a rounding relative to the reference's (jaccard.rs) operation order.
@@ -614,6 +647,7 @@ __global__ void __launch_bounds__(THREADS, 2)
 constexpr int DNST = SKD_DNST;
 static_assert(DNST >= 2 && DNST <= 10, "ring depth");
 constexpr int TRING = 16;                          // published tiles kept in shared memory
+constexpr uint32_t kCutUnset = 0xffffffffu;
 constexpr int DSTAGE_U32 = 3 * STAGE_U32;          // row slab + two column slabs
 constexpr int DENSE_THREADS = 288;                 // 8 consumer warps + 1 producer warp
 constexpr int DJ = 8;                              // column groups per thread (4 x 8 pair tile)
@@ -731,7 +765,7 @@ __device__ __forceinline__ float2 pair_epilogue_k(const uint32_t *words, size_t 
     return make_float2(d0, d1);
 }
 
-template <typename CountT>
+template <typename CountT, bool DEFER>
 __global__ void __launch_bounds__(DENSE_THREADS, 1)
     dense_kernel(const __grid_constant__ DevDb A, const __grid_constant__ DevDb B, const __grid_constant__ EpiParams E,
                  const __grid_constant__ SchedParams S, const uint64_t n_tiles, unsigned long long *__restrict__ tile_counter,
@@ -742,7 +776,11 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1)
     uint64_t *empty_bar = full_bar + DNST;  // 8 arrivals (one per consumer warp) release a stage
     uint2 *tiles = reinterpret_cast<uint2 *>(empty_bar + DNST);
     volatile uint32_t *published = reinterpret_cast<volatile uint32_t *>(tiles + TRING);  // tiles[j % TRING] valid for j < it
-    uint16_t *warp_lists = reinterpret_cast<uint16_t *>(const_cast<uint32_t *>(published) + 4);  // [8 warps][1024]
+    // early exit: votes[q] = consumer warps that stopped counting tile q; cut[q] = stages the producer issued for it
+    // (kCutUnset while it may still issue more)
+    uint32_t *votes = const_cast<uint32_t *>(published) + 4;
+    volatile uint32_t *cut = votes + TRING;
+    uint16_t *warp_lists = reinterpret_cast<uint16_t *>(votes + 2 * TRING);  // [8 warps][1024]
     unsigned char *out_stage = reinterpret_cast<unsigned char *>(warp_lists + 8 * 1024);          // [8 warps][16][64] float2
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -805,6 +843,10 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1)
         auto publish_tile = [&]() -> uint2 {
             const uint2 rc = fetch_tile();
             tiles[n_pub % TRING] = rc;
+            if (DEFER) {
+                votes[n_pub % TRING] = 0;
+                cut[n_pub % TRING] = kCutUnset;
+            }
             __threadfence_block();
             *published = ++n_pub;
             return rc;
@@ -819,7 +861,11 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1)
             // the second column block may not exist (odd count, end of a band): its slab is then not loaded and its
             // columns are masked in the epilogue
             const uint32_t b_bytes = rc.y + 1 < cb_limit ? 2u * STAGE_BYTES : (uint32_t)STAGE_BYTES;
-            for (uint32_t it = 0; it < n_it; ++it) {
+            const uint32_t q = (n_pub - 2) % TRING;  // this tile's slot (the one after it is published already)
+            uint32_t it = 0;
+            for (; it < n_it; ++it) {
+                // every consumer warp has stopped counting this tile: the rest of its words need not be loaded
+                if (DEFER && it > 3 * W && *reinterpret_cast<volatile uint32_t *>(votes + q) == 8u) break;
                 // wait (asleep between probes) until all 8 consumer warps have released the stage's previous word
 #ifndef SKD_ABL_NOWAIT
                 if (use > 0) mbar_wait_sleep(&empty_bar[s], (use - 1) & 1u);
@@ -838,6 +884,10 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1)
                     s = 0;
                     ++use;
                 }
+            }
+            if (DEFER) {  // tell the draining warps where this tile ends, BEFORE any stage of the next tile is issued
+                cut[q] = it;
+                __threadfence_block();
             }
             rc = next;
         }
@@ -861,6 +911,12 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1)
         for (int j = 0; j < DJ; ++j) mism[i][j] = 0;
     uint32_t s = 0, ph = 0, w_in_k = 0, kk = 0;
     bool ready = false;
+    // Early exit (the reference's own break, jaccard.rs:89-91, at the granularity a warp can afford): once the third
+    // k-mer length is counted every pair without a match at one of them is final, (1, 1).  If at most defer_max pairs
+    // of the warp's 16 x 64 block are left, they are handed to defer_kernel (one warp per pair, all k) and the warp
+    // does not count the remaining k-mer lengths of the tile: it only passes the stages on.  All of it lives in the
+    // once-per-k block below; the counting loop carries no extra state (the kernel sits at its 168-register cap).
+    const bool may_defer = DEFER && S.defer_cap != 0 && E.kind == KIND_CORE_ACC && nk > 3;
     // core/accessory: bit c of `dead` = pair c is known to be (1, 1); with fewer than three k-mer lengths every pair is
     const bool track_dead = E.kind == KIND_CORE_ACC;
     const uint32_t dead_init = (E.kind == KIND_CORE_ACC && nk < 3) ? 0xffffffffu : 0u;
@@ -929,6 +985,107 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1)
                     for (int j = 0; j < DJ; ++j) mism[i][j] = 0;
                 w_in_k = 0;
                 if (++kk == nk) kk = 0;
+                if (may_defer && kk == 3) {
+                    // pairs of this thread that are still open: in range, above the diagonal (self), not dead
+                    uint32_t open = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const uint64_t gi = (uint64_t)rc.x * TS + arow0 + 4 * i;
+                        if (gi < S.row_begin || gi >= S.row_end) continue;
+#pragma unroll
+                        for (int j = 0; j < DJ; ++j) {
+                            const uint64_t gj = (uint64_t)rc.y * TS + bcol0 + 8 * j;
+                            if (gj < col_end && !(S.mode == MODE_DENSE_SELF && gj <= gi)) open |= 1u << (i * DJ + j);
+                        }
+                    }
+                    open &= ~dead;
+                    const uint32_t cnt = __popc(open);
+                    uint32_t incl = cnt;
+#pragma unroll
+                    for (int dlt = 1; dlt < 32; dlt <<= 1) {
+                        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, dlt);
+                        if (lane >= dlt) incl += t;
+                    }
+                    const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                    if (total <= S.defer_max) {
+                        unsigned long long base = 0;
+                        if (total) {
+                            if (lane == 0) base = atomicAdd(reinterpret_cast<unsigned long long *>(tile_counter) + 1, (unsigned long long)total);
+                            base = __shfl_sync(0xffffffffu, base, 0);
+                        }
+                        const bool fits = base + total <= (unsigned long long)S.defer_cap;
+                        unsigned long long slot = base + incl - cnt;
+                        for (uint32_t m = open; m; m &= m - 1, ++slot) {
+                            if (slot >= (unsigned long long)S.defer_cap) break;
+                            uint4 e = make_uint4(0xffffffffu, 0u, 0u, 0u);  // reserved but unused (list overflow)
+                            uint4 e2 = make_uint4(0u, 0u, 0u, 0u);           // the three counts already known
+                            if (fits) {
+                                const int c = __ffs(m) - 1;
+                                {   // this thread's own count words of k-mer lengths 0..2 (stored a moment ago)
+                                    const uint32_t *cw = my_words + (size_t)(c / PACK) * 256;
+                                    const int sh = PACK == 2 ? 16 * (c % PACK) : 0;
+                                    const uint32_t msk = PACK == 2 ? 0xffffu : 0xffffffffu;
+                                    e2.x = (__ldcg(cw) >> sh) & msk;
+                                    e2.y = (__ldcg(cw + kstride) >> sh) & msk;
+                                    e2.z = (__ldcg(cw + 2 * kstride) >> sh) & msk;
+                                }
+                                const uint64_t gi = (uint64_t)rc.x * TS + arow0 + 4 * (c / DJ);
+                                const uint64_t gj = (uint64_t)rc.y * TS + bcol0 + 8 * (c % DJ);
+                                uint64_t idx;  // output position, the rule of row_base_of below
+                                if (rect) idx = (gi - S.row_begin) * S.rect_ld - (S.mode == MODE_DENSE_SELF ? S.rect_c0 : 0) + gj;
+                                else if (S.mode == MODE_DENSE_SELF) idx = nA * gi - ((gi * (gi + 1)) >> 1) - 1 - gi - S.out_base + gj;
+                                else idx = (gi - S.row_begin) * B.n + gj;
+                                e = make_uint4((uint32_t)gi, (uint32_t)gj, (uint32_t)idx, (uint32_t)(idx >> 32));
+                            }
+                            S.defer_list[2 * slot] = e;
+                            S.defer_list[2 * slot + 1] = e2;
+                        }
+                        if (fits) {  // (warp-uniform)
+                            // deferred pairs look dead from here on: the epilogue writes (1, 1) for them and
+                            // defer_kernel, which runs after this kernel, overwrites that with their distances
+                            dead |= open;
+                            if (S.work_stats && lane == 0) {
+                                atomicAdd(S.work_stats + 3, (unsigned long long)(n_it - (it + 1)));
+                                if (total) atomicAdd(S.work_stats + 2, (unsigned long long)total);
+                            }
+                            // Pass the remaining stages of this tile on without counting.  When all 8 warps have
+                            // voted the producer stops loading the tile and publishes how many stages it issued
+                            // (cut); until then a stage that lands belongs to this tile -- the producer sets cut
+                            // before it issues anything of the next one.
+                            const uint32_t q = tj % TRING;
+                            if (lane == 0) atomicAdd(votes + q, 1u);
+                            for (uint32_t it2 = it + 1; it2 < n_it; ++it2) {
+                                uint32_t s1 = s + 1, ph1 = ph;
+                                if (s1 == (uint32_t)DNST) {
+                                    s1 = 0;
+                                    ph1 ^= 1u;
+                                }
+                                uint32_t c;
+                                bool landed = false;
+                                for (;;) {
+                                    c = cut[q];
+                                    if (c != kCutUnset) break;
+                                    if (mbar_test(&full_bar[s1], ph1)) {
+                                        c = cut[q];  // read again: unset now means the stage that landed is ours
+                                        landed = true;
+                                        break;
+                                    }
+                                    __nanosleep(32);
+                                    spin_guard();
+                                }
+                                if (c != kCutUnset && it2 >= c) break;  // (warp-uniform: shared-memory broadcast reads)
+                                s = s1;
+                                ph = ph1;
+                                if (!landed) mbar_wait(&full_bar[s], ph);
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(&empty_bar[s]);
+                            }
+                            it = n_it - 1;  // the loop's tail advances the ring once more and ends the tile
+                            kk = 0;
+                            ready = false;
+                        }
+                    }
+                }
             }
             if (++s == (uint32_t)DNST) {
                 s = 0;
@@ -1052,11 +1209,85 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1)
             }
         }
         dead = dead_init;
+        if (S.work_stats && lane == 0) atomicAdd(S.work_stats + 1, (unsigned long long)n_it);  // steps of this warp and tile
+    }
+}
+
+// Finishes the pairs dense_kernel deferred: one warp per pair.  The match counts of the first three k-mer lengths come
+// with the list entry; the others are counted from the sample-major copies of the planes (untile_kernel): the two
+// half-warps take two consecutive k-mer lengths, a lane compares the 14 planes of a 64-bin word (2 x 112 contiguous
+// bytes) -- the reference's own loop (jaccard.rs:15-25) spread over 16 lanes.  Then the arithmetic of pair_epilogue
+// (jaccard.rs:61-142) in the reference's order, and the result goes to its place in the dense or rect output.
+// Runs after dense_kernel on the same stream; the entry count comes from the scratch header.
+__global__ void __launch_bounds__(256) defer_kernel(const uint64_t *__restrict__ a_rows, const uint64_t *__restrict__ b_rows,
+                                                    uint32_t W, const __grid_constant__ EpiParams E,
+                                                    const uint4 *__restrict__ list,
+                                                    const unsigned long long *__restrict__ count, uint32_t cap,
+                                                    float2 *__restrict__ out) {
+    const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
+    const unsigned long long n = min(*count, (unsigned long long)cap);
+    const bool comp = E.has_c != 0;
+    const uint64_t kmer_stride = (uint64_t)W * BBITS, sample_stride = (uint64_t)E.nk * kmer_stride;
+    for (unsigned long long p = (unsigned long long)blockIdx.x * (blockDim.x / 32) + threadIdx.x / 32; p < n;
+         p += (unsigned long long)gridDim.x * (blockDim.x / 32)) {
+        const uint4 e = list[2 * p], e2 = list[2 * p + 1];
+        if (e.x == 0xffffffffu) continue;
+        const uint64_t gi = e.x, gj = e.y, idx = (uint64_t)e.z | ((uint64_t)e.w << 32);
+        double c1 = 0.0, c2 = 0.0;
+        if (comp) {
+            c1 = E.a_comp[gi];
+            c2 = E.b_comp[gj];
+        }
+        double ysum = 0.0, xysum = 0.0, ysq = 0.0;
+        int cnt = 0;
+        bool alive = true;
+        auto take = [&](int k, uint32_t c) {  // the reference's loop body: stop at the first k without a usable Jaccard
+            if (!alive) return;
+            const double y = comp ? log(corrected_jaccard(c, c1, c2, E)) : E.lny[c];
+            if (y < E.tolerance) {
+                alive = false;
+                return;
+            }
+            ysum = __dadd_rn(ysum, y);
+            xysum = __dadd_rn(xysum, __dmul_rn(E.kf[k], y));
+            ysq = __dadd_rn(ysq, __dmul_rn(y, y));
+            ++cnt;
+        };
+        take(0, e2.x);
+        take(1, e2.y);
+        take(2, e2.z);
+        const ulonglong2 *pa = reinterpret_cast<const ulonglong2 *>(a_rows + gi * sample_stride);
+        const ulonglong2 *pb = reinterpret_cast<const ulonglong2 *>(b_rows + gj * sample_stride);
+        for (int k0 = 3; k0 < E.nk && alive; k0 += 2) {
+            const int k = k0 + half;
+            uint32_t mism = 0;
+            if (k < E.nk) {
+                for (uint32_t w = hl; w < W; w += 16) {
+                    const size_t o = ((size_t)k * kmer_stride + (size_t)w * BBITS) / 2;
+                    unsigned long long d = 0;
+#pragma unroll
+                    for (int t = 0; t < BBITS / 2; ++t) {
+                        const ulonglong2 x = __ldg(pa + o + t), y = __ldg(pb + o + t);
+                        d |= (x.x ^ y.x) | (x.y ^ y.y);
+                    }
+                    mism += __popcll(d);
+                }
+            }
+            for (int o = 8; o > 0; o >>= 1) mism += __shfl_xor_sync(0xffffffffu, mism, o);  // within each half-warp
+            const uint32_t m0 = __shfl_sync(0xffffffffu, mism, 0), m1 = __shfl_sync(0xffffffffu, mism, 16);
+            take(k0, E.nbins - m0);
+            if (k0 + 1 < E.nk) take(k0 + 1, E.nbins - m1);
+        }
+        if (lane == 0) {
+            float d0, d1;
+            regress(ysum, xysum, ysq, cnt, E, d0, d1);
+            out[idx] = make_float2(d0, d1);
+        }
     }
 }
 
 size_t dense_kernel_smem() {
-    return (size_t)DNST * DSTAGE_U32 * 4 + 2 * DNST * 8 + TRING * sizeof(uint2) + 16 + 8 * 1024 * sizeof(uint16_t) +
+    return (size_t)DNST * DSTAGE_U32 * 4 + 2 * DNST * 8 + TRING * sizeof(uint2) + 16 + 2 * TRING * 4 + 8 * 1024 * sizeof(uint16_t) +
            8 * 16 * 64 * sizeof(float2);
 }
 // per-CTA count scratch (one CTA per SM, 64 x 128 pairs each, nk <= kp words of 4 bytes per pair slot) + 256 bytes
@@ -1324,21 +1555,25 @@ cudaError_t launch_tiles(const DevDb &A, const DevDb &B, const EpiParams &E, con
             sm_count = 148;
         const uint64_t max_ctas = (uint64_t)sm_count;  // one CTA per SM
         const size_t dsmem = dense_kernel_smem();
-        if (count32)
-            err = cudaFuncSetAttribute(dense_kernel<uint32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem);
-        else
-            err = cudaFuncSetAttribute(dense_kernel<uint16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem);
+        // the early-exit instantiation only where it can act: the plain one carries none of its code
+        const bool defer = S.defer_cap != 0 && E.kind == KIND_CORE_ACC && E.nk > 3;
+        const void *kern = count32 ? (defer ? (const void *)dense_kernel<uint32_t, true> : (const void *)dense_kernel<uint32_t, false>)
+                                   : (defer ? (const void *)dense_kernel<uint16_t, true> : (const void *)dense_kernel<uint16_t, false>);
+        err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dsmem);
         if (err != cudaSuccess) return err;
         // the tile counter sits in front of the count scratch and is reset (stream-ordered) before every launch
         unsigned long long *counter = reinterpret_cast<unsigned long long *>(S.counts_scratch);
         unsigned char *counts = reinterpret_cast<unsigned char *>(S.counts_scratch) + 256;
-        err = cudaMemsetAsync(counter, 0, 8, st);
+        err = cudaMemsetAsync(counter, 0, 16, st);  // tile counter + fill count of the deferred-pair list
         if (err != cudaSuccess) return err;
         const unsigned grid = (unsigned)std::min<uint64_t>(n_ctas, max_ctas);
-        if (count32)
-            dense_kernel<uint32_t><<<grid, DENSE_THREADS, dsmem, st>>>(A, B, E, S, n_ctas, counter, (uint32_t *)counts);
-        else
-            dense_kernel<uint16_t><<<grid, DENSE_THREADS, dsmem, st>>>(A, B, E, S, n_ctas, counter, (uint16_t *)counts);
+        void *cptr = counts;
+        void *args[] = {(void *)&A, (void *)&B, (void *)&E, (void *)&S, (void *)&n_ctas, (void *)&counter, (void *)&cptr};
+        err = cudaLaunchKernel(kern, dim3(grid), dim3(DENSE_THREADS), args, dsmem, st);
+        if (err != cudaSuccess) return err;
+        if (defer)
+            defer_kernel<<<8 * sm_count, 256, 0, st>>>(S.a_rows, S.b_rows, A.W, E, S.defer_list, counter + 1, S.defer_cap,
+                                                      reinterpret_cast<float2 *>(S.out));
         return cudaGetLastError();
     }
 #define SKD_LAUNCH(T, C)                                                                                      \
@@ -1982,8 +2217,12 @@ cudaError_t preload_kernels() {
     SKD_PRELOAD(tile_kernel<uint32_t, 16>);
     SKD_PRELOAD(tile_kernel<uint32_t, 32>);
     SKD_PRELOAD(tile_kernel<uint32_t, TS>);
-    SKD_PRELOAD(dense_kernel<uint16_t>);
-    SKD_PRELOAD(dense_kernel<uint32_t>);
+    SKD_PRELOAD((dense_kernel<uint16_t, false>));
+    SKD_PRELOAD((dense_kernel<uint16_t, true>));
+    SKD_PRELOAD((dense_kernel<uint32_t, false>));
+    SKD_PRELOAD((dense_kernel<uint32_t, true>));
+    SKD_PRELOAD(defer_kernel);
+    SKD_PRELOAD(untile_kernel);
     SKD_PRELOAD((stream_kernel<1, false>));
     SKD_PRELOAD((stream_kernel<2, false>));
     SKD_PRELOAD((stream_kernel<4, false>));

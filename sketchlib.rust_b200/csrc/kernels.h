@@ -12,6 +12,8 @@ namespace skd {
 void launch_repack(const uint64_t *raw, uint64_t raw_samples, uint64_t sample_stride, uint64_t kmer_stride,
                    uint32_t *tiled, const DevDb &db, uint32_t b0, uint32_t n_blocks, cudaStream_t st);
 
+void launch_untile(const DevDb &db, uint64_t *rows, cudaStream_t st);  // tiled -> sample-major u64 [sample][k][w][plane]
+
 int counts_per_pair(int nk, bool count32);
 size_t tile_kernel_smem(int nk, bool count32, bool knn_mode, uint32_t cap, bool with_aux);
 

@@ -112,6 +112,13 @@ struct SchedParams {
     void *counts_scratch;
     // the launch goes to dense_kernel (tile groups were built over column block PAIRS); 0 = tile_kernel
     uint32_t dense_pairs;
+    // dense_kernel, core/accessory: early exit of a warp's 16 x 64 pair block after the third k-mer length when at
+    // most defer_max of its pairs can still need the regression; those go to this list (defer_cap entries, fill
+    // count in the scratch header) and are finished by defer_kernel.  defer_cap == 0 disables.
+    uint4 *defer_list;               // two uint4 per entry: (row, column, output index lo, hi), (count k0, k1, k2, -)
+    uint32_t defer_cap, defer_max;
+    const uint64_t *a_rows, *b_rows; // sample-major copies of the planes (u64 [sample][k][w][plane]) for defer_kernel
+    unsigned long long *work_stats;  // nullable: [1] += warp x word steps in all, [3] += steps skipped, [2] += deferred pairs
 };
 
 }  // namespace skd

@@ -59,6 +59,11 @@ def main():
         out["knn_tile_ms"] = min(tile[1:])
         out["knn_tile_tlop3"] = kp * 3584 / (min(tile[1:]) * 1e-3) / 1e12
         out["knn_checksum"] = float(r.d0.astype("float64").sum() + r.d1.astype("float64").sum())
+        ctx.work_counters(reset=True)
+        sk.self_dists_knn(g, knn=50, dist_type=sk.set_k(g))
+        done, total, deferred = ctx.work_counters()
+        out["knn_steps_computed_frac"] = done / max(total, 1)
+        out["knn_pairs_deferred_frac"] = deferred / kp
     print(json.dumps(out), flush=True)
 
 
