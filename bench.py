@@ -360,14 +360,34 @@ def main():
     launches = ctx.launch_count - launches0
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     op_ms = sum(r[0] for r in recs) / len(recs)
-    tile_ms = sum(r[1] for r in recs) / len(recs)
-    kern_ms = sum(r[2] for r in recs) / len(recs)
+    tile_ms_ee = sum(r[1] for r in recs) / len(recs)
+    kern_ms_ee = sum(r[2] for r in recs) / len(recs)
     xchg_ms = sum(r[3] for r in recs) / len(recs)
     ms_per_step = max_over_ranks(op_ms)
     value = total_pairs / (ms_per_step * 1e-3)
-    tile_ms_all = gather_floats(tile_ms)
     pairs_all = gather_floats(float(my_pairs))
     xchg_all = gather_floats(xchg_ms)
+    # how much of the match counting the early exit left (this rank), measured on one more step
+    ctx.work_counters(reset=True)
+    step_resident()
+    steps_done, steps_total, pairs_deferred = ctx.work_counters(reset=True)
+
+    # ---- roofline leg: the same job with the kernel's early exit OFF (every k-mer length of every pair is counted --
+    # the 3584 LOP3 per pair the roofline is quoted on); not part of `value`
+    ctx.set_early_exit(False)
+    step_resident()
+    barrier()
+    recs_full = []
+    for _ in range(max(2, args.steps // 2)):
+        flush.fill_(1)
+        barrier()
+        recs_full.append(step_resident())
+    barrier()
+    ctx.set_early_exit(True)
+    op_ms_full = max_over_ranks(sum(r[0] for r in recs_full) / len(recs_full))
+    tile_ms = sum(r[1] for r in recs_full) / len(recs_full)
+    kern_ms = sum(r[2] for r in recs_full) / len(recs_full)
+    tile_ms_all = gather_floats(tile_ms)
 
     # ---- e2e: pinned host bit planes (1/N per rank) -> HBM -> peers -> distances -> exchange -> host rows on rank 0
     h_idx = ctx.pinned((n, KNN), np.uint64) if is_root else None
@@ -424,11 +444,24 @@ def main():
         roofline = {
             "bound": "int",
             "bound_note": "integer ALU (LOP3) issue: the kernel is bitwise, neither HBM- nor tensor-core-bound",
-            "kernel": "skd::dense_kernel<uint16_t> (rect mode: kNN keys of upper-triangle row groups, persistent 64x128 tiles)",
+            "kernel": "skd::dense_kernel<uint16_t, false> (rect mode: kNN keys of upper-triangle row groups, persistent 64x128 tiles)",
             "achieved": achieved, "peak": lop3_peak, "unit": "TLOP3/s", "frac": achieved / lop3_peak,
             "per_gpu_frac": [a / lop3_peak for a in per_gpu],
             "tile_kernel_ms_per_step": tile_ms, "all_kernels_ms_per_step": kern_ms,
-            "tile_kernel_share_of_step": tile_ms / op_ms,
+            "tile_kernel_share_of_step": tile_ms / kern_ms,
+            "measured_on": "the same job with the kernel's early exit switched off (skd_ctx_set_early_exit(0)): every "
+                           "k-mer length of every pair is counted, 3584 LOP3 per pair; ms_per_step of that run: "
+                           f"{op_ms_full:.2f}",
+            "early_exit": {
+                "what": "default mode, the one `value` and `e2e` are measured in: like the reference's loop (break at the "
+                        "first k-mer length without a match, jaccard.rs:89-91; n < 3 -> (1, 1)) a warp stops counting its "
+                        "16 x 64 pair block after the third k-mer length when at most 32 of its pairs are still open and "
+                        "hands those to defer_kernel; results are identical (parity_sample, resident_equals_e2e)",
+                "match_count_steps_executed_frac": steps_done / max(steps_total, 1),
+                "pairs_finished_by_defer_kernel_frac": pairs_deferred / max(my_pairs, 1),
+                "tile_and_defer_kernel_ms_per_step": tile_ms_ee, "all_kernels_ms_per_step": kern_ms_ee,
+                "executed_tlop3_per_s": my_pairs * LOP3_PER_PAIR * (steps_done / max(steps_total, 1)) / (tile_ms_ee * 1e-3) / 1e12,
+            },
             "peak_source": peak_src,
             "algorithmic_ops_per_pair": {"lop3": LOP3_PER_PAIR, "popc": POPC_PER_PAIR},
             "popc_frac": (pairs_all[0] * POPC_PER_PAIR / (tile_ms * 1e-3)) / peaks["popc_per_s"] if peaks and peaks.get("popc_per_s") else None,
@@ -521,6 +554,17 @@ def dense_leg(args, sk, ctx, grp, rank, world, dev, barrier, max_over_ranks, flu
     barrier()
     my_ms = sum(ms) / len(ms)
     ms_per_step = max_over_ranks(my_ms)
+    # the kernel-quality figure: the same launch with the early exit off (3584 LOP3 for every pair)
+    ctx.set_early_exit(False)
+    step_resident()
+    ms_full = []
+    for _ in range(steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        ms_full.append(step_resident())
+    ctx.set_early_exit(True)
+    my_ms_full = sum(ms_full) / len(ms_full)
+    barrier()
     pin_out = ctx.pinned((max(my_pairs * 2, 2),), np.float32)
 
     def step_e2e():
@@ -551,7 +595,8 @@ def dense_leg(args, sk, ctx, grp, rank, world, dev, barrier, max_over_ranks, flu
         "pairs": total_pairs, "steps": steps, "value": total_pairs / (ms_per_step * 1e-3), "unit": "pairs/s",
         "ms_per_step": ms_per_step,
         "roofline_frac_lop3_rank0": None,   # filled by the caller's peak if wanted: achieved below
-        "achieved_tlop3_rank0": my_pairs * LOP3_PER_PAIR / (my_ms * 1e-3) / 1e12,
+        "achieved_tlop3_rank0": my_pairs * LOP3_PER_PAIR / (my_ms_full * 1e-3) / 1e12,
+        "ms_per_step_early_exit_off_rank0": my_ms_full,
         "e2e": {"value": total_pairs / e2e_s, "unit": "pairs/s", "ms_per_step": e2e_s * 1e3,
                 "h2d_bytes_per_step_per_rank": (s1 - s0) * PER_SAMPLE * 8, "d2h_bytes_per_step_per_rank": out_bytes},
         "result_checksum_rank0": checksum,

@@ -72,6 +72,10 @@ uint64_t skd_ctx_launch_count(const skd_ctx *ctx);
  * steps_computed / steps_total = the share of the (warp, 64-bin word) match-count steps that were executed;
  * pairs_deferred = pairs finished one by one afterwards.  SKD_EARLY_OUT=0 in the environment disables the early exit
  * (steps_computed == steps_total).  Measurement aid; synchronises the context's streams. */
+/* Turns that early exit off (0) or back on (non-zero; the default unless SKD_EARLY_OUT=0): with it off the kernel
+ * counts every k-mer length of every pair, which is the work the roofline figures are quoted on.  Results are the
+ * same either way. */
+skd_status skd_ctx_set_early_exit(skd_ctx *ctx, int enabled);
 skd_status skd_ctx_work_counters(skd_ctx *ctx, uint64_t *steps_computed, uint64_t *steps_total, uint64_t *pairs_deferred,
                                  int reset);
 /* Device time in ms of the distance kernels of the last compute call, measured with CUDA events on

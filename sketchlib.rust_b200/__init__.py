@@ -63,6 +63,7 @@ def load_library(build=True):
         "skd_last_error": (C.c_char_p, [vp]),
         "skd_ctx_device": (C.c_int, [vp]),
         "skd_ctx_launch_count": (u64, [vp]),
+        "skd_ctx_set_early_exit": (C.c_int, [vp, C.c_int]),
         "skd_ctx_work_counters": (C.c_int, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_int]),
         "skd_ctx_last_kernel_ms": (C.c_float, [vp]),
         "skd_ctx_last_tile_kernel_ms": (C.c_float, [vp]),
@@ -188,6 +189,10 @@ class Context:
     @property
     def launch_count(self):
         return int(self.lib.skd_ctx_launch_count(self.handle))
+
+    def set_early_exit(self, enabled):
+        """skd_ctx_set_early_exit: the dense core/accessory kernel's early exit (on by default; same results)."""
+        self._check(self.lib.skd_ctx_set_early_exit(self.handle, int(bool(enabled))))
 
     def work_counters(self, reset=False):
         """(steps_computed, steps_total, pairs_deferred) of the dense core/accessory kernel (skd_ctx_work_counters)."""

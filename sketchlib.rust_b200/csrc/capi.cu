@@ -1108,6 +1108,12 @@ skd_status skd_ctx_create(int device, skd_ctx **out) {
     return SKD_OK;
 }
 
+skd_status skd_ctx_set_early_exit(skd_ctx *ctx, int enabled) {
+    if (!ctx) return SKD_ERR_INVALID;
+    ctx->early_out = enabled != 0;
+    return SKD_OK;
+}
+
 skd_status skd_ctx_work_counters(skd_ctx *ctx, uint64_t *steps_computed, uint64_t *steps_total, uint64_t *pairs_deferred,
                                  int reset) {
     if (!ctx) return SKD_ERR_INVALID;

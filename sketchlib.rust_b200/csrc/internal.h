@@ -45,7 +45,9 @@ struct skd_ctx {
     size_t result_chunk_bytes = 64ull << 20;  // SKD_RESULT_CHUNK_MB: staged D2H chunk of dense results
     uint32_t group = 24;                      // SKD_GROUP: row blocks per L2 group of the tile scheduler (B200: DRAM reads of a
                                               // dense 10k run 1.52 GB at 8, 0.75 GB at 24, 1.07 GB at 48, 1.61 GB at 64)
-    size_t sym_chunk_bytes = 2ull << 30;      // SKD_SYM_CHUNK_MB: HBM key buffer of one symmetric-kNN row group
+    size_t sym_chunk_bytes = 8ull << 30;      // SKD_SYM_CHUNK_MB: HBM key buffer of one symmetric-kNN row group (100k kNN
+                                              // step on B200: 547 ms at 2 GB, 519 ms at 8 GB, 513 ms at 16 GB: fewer, longer
+                                              // column folds in select_sym_kernel)
     uint64_t few_queries = 1ull << 20;        // SKD_FEW_QUERIES: cross kNN up to this many queries goes dense keys + select
     size_t read_threads = 8;                  // SKD_READ_THREADS: host threads copying an .skd chunk into pinned staging
                                               // (default: the host's hardware threads, at most 16)

@@ -507,6 +507,52 @@ def test_self_knn_partials_merge_like_ranks(sk, ctx):
     assert np.array_equal(merged.d0, whole.d0) and np.array_equal(merged.d1, whole.d1)
 
 
+# ------------------------------------------------------------------ early exit of the dense core/accessory kernel
+def test_early_exit_gives_the_same_results_and_skips_work(sk, ctx):
+    """The dense kernel stops counting a warp's pair block after the third k-mer length when (almost) all of its
+    pairs are final and finishes the few open ones pair by pair (defer_kernel); with the exit switched off every
+    k-mer length of every pair is counted.  Both must give bit-identical outputs -- dense self, dense cross, rect keys
+    under the symmetric kNN, with and without completeness vectors -- and equal the oracle."""
+    kmers = [15, 17, 19, 21, 23, 25, 27, 29]
+    db = synth_db(1500, 16, kmers, seed=90, n_families=40, unrelated_frac=0.3)
+    ref, qry = synth_pair(900, 300, 16, kmers, seed=91, n_families=25, unrelated_frac=0.3)
+    g, gr, gq = up(sk, ctx, db), up(sk, ctx, ref), up(sk, ctx, qry)
+    rng = np.random.default_rng(3)
+    cv = rng.uniform(0.7, 1.0, size=1500)
+
+    def run_all():
+        ctx.work_counters(reset=True)
+        out = [sk.self_dists_all(g, dist_type=sk.set_k(g)).distances,
+               sk.self_dists_all(g, dist_type=sk.set_k(g), completeness_vec=cv).distances,
+               sk.cross_dists_all(gr, gq, dist_type=sk.set_k(gr)).distances]
+        knn = sk.self_dists_knn(g, knn=30, dist_type=sk.set_k(g))
+        return out + [knn.idx, knn.d0, knn.d1], ctx.work_counters()
+
+    try:
+        ctx.set_early_exit(False)
+        full, (done_f, total_f, deferred_f) = run_all()
+        ctx.set_early_exit(True)
+        fast, (done, total, deferred) = run_all()
+    finally:
+        ctx.set_early_exit(True)
+    for a, b in zip(full, fast):
+        assert np.array_equal(a, b)
+    assert done_f == total_f and deferred_f == 0          # nothing skipped with the exit off
+    assert total == total_f and done < 0.8 * total         # ... a good part of the counting skipped with it on
+    assert 0 < deferred < 0.05 * (1500 * 1499 // 2 * 3)   # a few per cent of the pairs went through defer_kernel
+    check_close(fast[0], oracle.self_dists_all(db, threads=16))
+    check_close(fast[1], oracle.self_dists_all(db, completeness=cv, threads=16))
+    check_close(fast[2], oracle.cross_dists_all(ref, qry, threads=16))
+    # one species: every pair is related, so only warps at the diagonal / the ragged edge (few valid pairs) leave early
+    same = synth_db(700, 16, kmers, seed=92, n_families=1)
+    gs = up(sk, ctx, same)
+    ctx.work_counters(reset=True)
+    d = sk.self_dists_all(gs, dist_type=sk.set_k(gs)).distances
+    done, total, deferred = ctx.work_counters()
+    assert done > 0.8 * total and deferred < 0.02 * (700 * 699 // 2)
+    check_close(d, oracle.self_dists_all(same, threads=16))
+
+
 # ------------------------------------------------------------------ the reference's envelope (no knn or k-mer limits)
 def test_knn_beyond_list_capacity_and_up_to_n_minus_1(sk, ctx):
     """--knn is clamped to n - 1 and runs (src/lib.rs:379-382): knn = 2000 (more than the row-owned kernel's 1984
