@@ -415,6 +415,16 @@ __device__ __forceinline__ void pair_epilogue(const CountT *counts, int pair, co
     }
 }
 
+// No key exceeds 1.0 (distances and 1 - ANI lie in [0, 1]).  A candidate with key 1.0 and neighbour index j is
+// preceded in (key, index) order by every sample with a smaller index, and all of those are candidates of the same
+// row somewhere in the run -- so it can only be among the row's knn best if fewer than knn samples precede it.
+// Composites at or above this bound never reach a final list; rejecting them up front keeps the lists from filling
+// (and being sorted) with the distance-1 pairs that make up nearly everything between unrelated samples.
+// first_useless = knn + 1 in self mode (the row itself is no candidate), knn in cross mode.
+__device__ __forceinline__ unsigned long long useless_from(uint32_t first_useless) {
+    return ((unsigned long long)float_order_bits(1.0f) << 32) | first_useless;
+}
+
 // Warp-level bitonic sort of P (power of two) u64 keys (+ optional aux payload) in shared memory.
 __device__ __forceinline__ void warp_bitonic_sort(unsigned long long *key, float *aux, int P, int lane) {
     for (int size = 2; size <= P; size <<= 1) {
@@ -572,7 +582,7 @@ __global__ void __launch_bounds__(THREADS, 2)
     };
 
     for (int r = tid; r < TS; r += THREADS) {
-        thr[r] = ~0ull;
+        thr[r] = useless_from(knn + (S.self_mode ? 1u : 0u));
         cand_cnt[r] = 0;
     }
     __syncthreads();
@@ -1699,7 +1709,7 @@ __global__ void __launch_bounds__(256) select_few_kernel(const float *__restrict
     for (int q = 0; q < 8; ++q) {
         cnt[q] = 0;
         // the slice's list from earlier reference chunks (~0 padded): nothing at or above its knn-th key can enter
-        thr[q] = q < (int)nq ? Lkey[(uint64_t)q * knn + knn - 1] : 0ull;
+        thr[q] = q < (int)nq ? min(Lkey[(uint64_t)q * knn + knn - 1], useless_from(knn)) : 0ull;
     }
     for (uint64_t r0 = w_lo; r0 < w_hi; r0 += 32) {
         const uint64_t row = r0 + lane;
@@ -1806,7 +1816,9 @@ __global__ void __launch_bounds__(256) select_sym_kernel(const float *__restrict
     constexpr int CAP = 128;
     extern __shared__ __align__(16) unsigned char sm_raw[];
     unsigned long long *buf = reinterpret_cast<unsigned long long *>(sm_raw);  // [8 warps][8 targets][CAP]
-    float *baux = reinterpret_cast<float *>(buf + TS * CAP);
+    unsigned long long *gbuf = buf + TS * CAP;                                 // [8 targets][CAP]: gather buffer of the merge
+    float *baux = reinterpret_cast<float *>(gbuf + 8 * CAP);
+    float *gaux = baux + TS * CAP;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint64_t tbase = t0 + (uint64_t)blockIdx.x * 8;
     const uint32_t nt = (uint32_t)(t1 - tbase < 8 ? t1 - tbase : 8);
@@ -1826,14 +1838,16 @@ __global__ void __launch_bounds__(256) select_sym_kernel(const float *__restrict
         unsigned long long *list = buf + (warp * 8 + q) * CAP;
         for (int e = lane; e < CAP; e += 32) list[e] = ~0ull;
         cnt[q] = 0;
-        thr[q] = q < (int)nt ? Lkey[(tbase + q) * knn + knn - 1] : 0ull;  // ~0 while the list is not full
+        thr[q] = q < (int)nt ? min(Lkey[(tbase + q) * knn + knn - 1], useless_from(knn + 1)) : 0ull;
     }
     __syncwarp();
 
-    for (uint64_t c0 = w_lo; c0 < w_hi; c0 += 32) {
+    // One step = 32 candidates (one per lane) against the CTA's 8 targets.  The keys of the next step are requested
+    // before the current one is folded: the loop is bound by the latency of these loads (16 warps per SM, one
+    // 64-byte request per lane and step), not by the folding.
+    auto load_step = [&](uint64_t c0, float (&key)[8], float (&av)[8]) {
         const uint64_t cand = c0 + lane;
         const bool in = cand < w_hi;
-        float key[8], av[8];
         if (COLS) {  // one row, 8 consecutive columns
             const size_t off = (size_t)(cand - g0) * ld + (tbase - g0);
             if (in) {
@@ -1874,6 +1888,10 @@ __global__ void __launch_bounds__(256) select_sym_kernel(const float *__restrict
                 }
             }
         }
+    };
+    auto fold_step = [&](uint64_t c0, const float (&key)[8], const float (&av)[8]) {
+        const uint64_t cand = c0 + lane;
+        const bool in = cand < w_hi;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             if (q >= (int)nt) break;
@@ -1901,21 +1919,67 @@ __global__ void __launch_bounds__(256) select_sym_kernel(const float *__restrict
                 thr[q] = list[knn - 1] < thr[q] ? list[knn - 1] : thr[q];
             }
         }
-    }
+    };
+    {
+        float keyA[8], avA[8], keyB[8], avB[8];
 #pragma unroll
-    for (int q = 0; q < 8; ++q)
-        if (q < (int)nt && cnt[q] > 0)
-            warp_bitonic_sort(buf + (warp * 8 + q) * CAP, AUX ? baux + (warp * 8 + q) * CAP : nullptr, CAP, lane);
+        for (int q = 0; q < 8; ++q) keyA[q] = avA[q] = keyB[q] = avB[q] = 0.0f;
+        if (w_lo < w_hi) load_step(w_lo, keyA, avA);
+        for (uint64_t c0 = w_lo; c0 < w_hi; c0 += 64) {
+            if (c0 + 32 < w_hi) load_step(c0 + 32, keyB, avB);
+            fold_step(c0, keyA, avA);
+            if (c0 + 64 < w_hi) load_step(c0 + 64, keyA, avA);
+            if (c0 + 32 < w_hi) fold_step(c0 + 32, keyB, avB);
+        }
+    }
+    // ---- merge.  Usually only a handful of candidates survived per target (everything at distance 1 beyond the
+    // first knn indices is rejected up front): then the 8 warps' entries of a target are gathered unsorted behind the
+    // stored list and ONE sort finishes it.  Otherwise every warp sorts its lists and they are merged one by one.
+    __shared__ uint32_t wcnt[8][8];
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) wcnt[warp][q] = cnt[q];
+    }
     __syncthreads();
-    // warp q merges: the list accumulated so far + the 8 warp lists of target q (each sorted, best knn first)
+    uint32_t total[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        total[q] = 0;
+        for (int w = 0; w < 8; ++w) total[q] += wcnt[w][q];
+        if (q < (int)nt && cnt[q] > 0 && total[q] > CAP - knn)
+            warp_bitonic_sort(buf + (warp * 8 + q) * CAP, AUX ? baux + (warp * 8 + q) * CAP : nullptr, CAP, lane);
+    }
+    __syncthreads();
     if (warp < (int)nt) {
         const int q = warp;
         const uint64_t tg = tbase + q;
+        if (total[q] == 0) return;  // no candidate beat the threshold: the stored list stands
+        if (total[q] <= CAP - knn) {
+            unsigned long long *acc = gbuf + q * CAP;
+            float *acc_a = AUX ? gaux + q * CAP : nullptr;
+            for (int e = lane; e < CAP; e += 32) {
+                acc[e] = e < (int)knn ? Lkey[tg * knn + e] : ~0ull;
+                if (AUX) acc_a[e] = e < (int)knn ? Laux[tg * knn + e] : 0.f;
+            }
+            uint32_t at = knn;
+            for (int w = 0; w < 8; ++w) {
+                const uint32_t c = wcnt[w][q];
+                for (uint32_t e = lane; e < c; e += 32) {
+                    acc[at + e] = buf[(w * 8 + q) * CAP + e];
+                    if (AUX) acc_a[at + e] = baux[(w * 8 + q) * CAP + e];
+                }
+                at += c;
+            }
+            __syncwarp();
+            warp_bitonic_sort(acc, acc_a, CAP, lane);
+            for (uint32_t e = lane; e < knn; e += 32) {
+                Lkey[tg * knn + e] = acc[e];
+                if (AUX) Laux[tg * knn + e] = acc_a[e];
+            }
+            return;
+        }
         unsigned long long *acc = buf + q * CAP;  // warp 0's list of this target doubles as the accumulator
         float *acc_a = AUX ? baux + q * CAP : nullptr;
-        bool any = false;
-        for (int w = 0; w < 8; ++w) any |= buf[(w * 8 + q) * CAP] != ~0ull;
-        if (!any) return;  // no candidate beat the threshold: the stored list stands
         for (int w = 0; w < 8; ++w) {
             // source: w == 0 -> the stored list; otherwise warp w's list
             const unsigned long long *src = w == 0 ? Lkey + tg * knn : buf + (w * 8 + q) * CAP;
@@ -1940,7 +2004,7 @@ cudaError_t launch_select_sym(bool cols, bool aux, const float *D, uint64_t ld, 
                               cudaStream_t st) {
     if (t1 <= t0) return cudaSuccess;
     const unsigned grid = (unsigned)((t1 - t0 + 7) / 8);
-    const size_t smem = (size_t)TS * 128 * 8 + (aux ? (size_t)TS * 128 * 4 : 0);
+    const size_t smem = (size_t)(TS + 8) * 128 * 8 + (aux ? (size_t)(TS + 8) * 128 * 4 : 0);
     cudaError_t err;
 #define SKD_SEL(C, A)                                                                                                \
     do {                                                                                                             \
