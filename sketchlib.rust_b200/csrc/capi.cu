@@ -281,7 +281,6 @@ skd_status dense_scratch(skd_ctx *ctx, const EpiParams &E, int slot, void **out)
                        dense_kernel_scratch_bytes(E.kp, E.nbins >= 65536, ctx->sm_count), out);
 }
 // The early exit of dense_kernel (core/accessory, more than three k-mer lengths): list for the deferred pairs.
-constexpr uint32_t kDeferCap = 8u << 20;  // entries of 32 bytes
 skd_status ensure_rows(skd_ctx *ctx, const skd_db *cdb) {
     skd_db *db = const_cast<skd_db *>(cdb);
     if (db->rows || db->n == 0 || db->is_pending()) return SKD_OK;
@@ -303,10 +302,10 @@ skd_status defer_setup(skd_ctx *ctx, const skd_db *A, const skd_db *B, const Epi
     if (st) return st;
     if ((st = ensure_rows(ctx, B))) return st;
     void *p;
-    st = scratch_get(ctx, "defer_list0", (size_t)kDeferCap * 2 * sizeof(uint4), &p);
+    st = scratch_get(ctx, "defer_list0", (size_t)ctx->defer_cap * 2 * sizeof(uint4), &p);
     if (st) return st;
     S->defer_list = (uint4 *)p;
-    S->defer_cap = kDeferCap;
+    S->defer_cap = ctx->defer_cap;
     S->defer_max = ctx->defer_max;
     S->a_rows = A->rows;
     S->b_rows = B->rows;
@@ -1088,6 +1087,7 @@ skd_status skd_ctx_create(int device, skd_ctx **out) {
     if (const char *e = getenv("SKD_DENSE_V1")) ctx->dense_v2 = atoi(e) == 0;
     if (const char *e = getenv("SKD_EARLY_OUT")) ctx->early_out = atoi(e) != 0;
     if (const char *e = getenv("SKD_DEFER_MAX")) ctx->defer_max = (uint32_t)std::max(0, atoi(e));
+    if (const char *e = getenv("SKD_DEFER_CAP")) ctx->defer_cap = (uint32_t)std::max(1, atoi(e));
     if (const char *e = getenv("SKD_GROUP")) ctx->group = (uint32_t)std::max(1, atoi(e));
     if (const char *e = getenv("SKD_UPLOAD_CHUNK_MB")) ctx->upload_chunk_bytes = (size_t)std::max(1, atoi(e)) << 20;
     if (const char *e = getenv("SKD_KNN_SYMMETRIC")) ctx->knn_symmetric = atoi(e) != 0;

@@ -39,6 +39,8 @@ struct skd_ctx {
     bool early_out = true;   // core/accessory dense_kernel: warps stop counting after the third k-mer length when (almost)
                              // all their pairs are final, the rest goes to defer_kernel (SKD_EARLY_OUT=0 disables)
     uint32_t defer_max = 32; // SKD_DEFER_MAX: open pairs of a 16 x 64 warp block that may be deferred
+    uint32_t defer_cap = 8u << 20;  // SKD_DEFER_CAP: entries (32 B) of the deferred-pair list of one launch; warps that
+                                    // find it full keep counting
     unsigned long long *work_stats = nullptr;  // device: [1] warp x word steps in all, [3] steps skipped, [2] deferred pairs
     // Tunables, read once from the environment when the context is created.
     size_t upload_chunk_bytes = 64ull << 20;  // SKD_UPLOAD_CHUNK_MB: staging chunk of a pageable/file upload

@@ -543,6 +543,15 @@ def test_early_exit_gives_the_same_results_and_skips_work(sk, ctx):
     check_close(fast[0], oracle.self_dists_all(db, threads=16))
     check_close(fast[1], oracle.self_dists_all(db, completeness=cv, threads=16))
     check_close(fast[2], oracle.cross_dists_all(ref, qry, threads=16))
+    # a deferred-pair list that is far too small: warps that find it full keep counting, the result does not change
+    tiny = fresh_ctx(sk, SKD_DEFER_CAP=50)
+    gt = up(sk, tiny, db)
+    assert np.array_equal(sk.self_dists_all(gt, dist_type=sk.set_k(gt)).distances, full[0])
+    knn_t = sk.self_dists_knn(gt, knn=30, dist_type=sk.set_k(gt))
+    assert np.array_equal(knn_t.idx, full[3]) and np.array_equal(knn_t.d0, full[4]) and np.array_equal(knn_t.d1, full[5])
+    done_t, total_t, deferred_t = tiny.work_counters()
+    assert done < done_t <= total_t and deferred_t <= 2 * 50 + 64   # (two launches, lists of 50)
+    tiny.close()
     # one species: every pair is related, so only warps at the diagonal / the ragged edge (few valid pairs) leave early
     same = synth_db(700, 16, kmers, seed=92, n_families=1)
     gs = up(sk, ctx, same)
