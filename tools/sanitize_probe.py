@@ -59,4 +59,26 @@ pin = ctx.pinned((db.bins.size,), np.uint64)
 pin.array[:] = db.bins
 ga = sk.SketchDb.upload(ctx, pin.array, db.n, db.kmers, db.W, async_upload=True)
 sk.self_dists_all(ga, dist_type=sk.set_k(ga))
-print("sanitize probe done, launches:", ctx.launch_count)
+# round 2: early exit (deferred pairs, producer cut), tiny deferred-pair list, sorted kNN path, many k-mer lengths
+k8 = [15, 17, 19, 21, 23, 25, 27, 29]
+mix = synth_db(450, 16, k8, seed=7, n_families=12, unrelated_frac=0.3)
+gm = up(mix)
+sk.self_dists_all(gm, dist_type=sk.set_k(gm))
+sk.self_dists_knn(gm, knn=20, dist_type=sk.set_k(gm))
+print("work counters (computed, total, deferred):", ctx.work_counters())
+rm, qm = synth_pair(400, 150, 16, k8, seed=8, n_families=10, unrelated_frac=0.3)
+grm, gqm = up(rm), up(qm)
+sk.cross_dists_all(grm, gqm, dist_type=sk.set_k(grm))
+sk.cross_dists_knn(grm, gqm, knn=12, dist_type=sk.set_k(grm))
+sk.self_dists_knn(gm, knn=449, dist_type=sk.set_k(gm, 19))        # knn = n - 1: dense keys + full row sort
+sk.self_dists_knn(gm, knn=449, dist_type=sk.set_k(gm), rows=(64, 128))
+k30 = list(range(5, 65, 2))
+many = synth_db(150, 16, k30, seed=9, n_families=3)
+gk = up(many)
+sk.self_dists_all(gk, dist_type=sk.set_k(gk))
+sk.self_dists_knn(gk, knn=10, dist_type=sk.set_k(gk))
+os.environ["SKD_DEFER_CAP"] = "40"
+ctx2 = sk.Context(0)
+gm2 = sk.SketchDb.upload(ctx2, mix.bins, mix.n, mix.kmers, mix.W)
+sk.self_dists_all(gm2, dist_type=sk.set_k(gm2))
+print("sanitize probe done, launches:", ctx.launch_count + ctx2.launch_count)
