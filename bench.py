@@ -269,6 +269,8 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
+    os.environ.setdefault("SKD_BIND_CPU", "1")  # one process per GPU: sit on the GPU's NUMA node (skd_ctx_create)
+    all_cpus = os.sched_getaffinity(0)           # restored before any CPU-oracle work (it uses every host core)
     import sketchlib.rust_b200 as sk
 
     rank = int(os.environ.get("RANK", "0"))
@@ -305,6 +307,7 @@ def main():
     n = N_KNN
     total_pairs = n * (n - 1) // 2
     ctx = sk.Context(local)
+    gpu_cpus = os.sched_getaffinity(0)           # where skd_ctx_create left this thread (SKD_BIND_CPU)
     n_dense = dense_n_for_gpus(world)
 
     # ---- the peer group: windows sized for the kNN rows, the loader slices of both databases
@@ -413,6 +416,7 @@ def main():
 
     parity = None
     if is_root and args.parity_rows > 0:
+        os.sched_setaffinity(0, all_cpus)  # the oracle's threads inherit this thread's affinity
         parity = parity_sample(h_idx.array, h_d0.array, h_d1.array, host_bins, args.parity_rows, os.cpu_count() or 1)
         # the resident leg's rows (left in HBM) must be the same rows
         chk = np.empty((n, KNN), dtype=np.float32)
@@ -420,6 +424,7 @@ def main():
         parity["resident_equals_e2e"] = bool(np.array_equal(chk, h_d0.array))
         parity["checksum_core"] = float(h_d0.array.astype(np.float64).sum())
         parity["checksum_accessory"] = float(h_d1.array.astype(np.float64).sum())
+        os.sched_setaffinity(0, gpu_cpus)
     g.free()
 
     dense = None
@@ -496,6 +501,7 @@ def main():
             line["roofline_hbm"] = stream_roofline(ctx, sk, synth, torch)
         if not args.no_cpu_baseline and world == 1:
             import oracle
+            os.sched_setaffinity(0, all_cpus)
             threads = os.cpu_count() or 1
             db = oracle.Db(host_bins, n, KMERS, W)
             ordered, rows_done, secs = oracle_knn_rate(db, 8 * threads, threads, args.ref_seconds)

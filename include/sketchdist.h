@@ -59,6 +59,9 @@ typedef struct skd_db skd_db; /* a MultiSketch resident in HBM (src/sketch/multi
 /* ---- context ---------------------------------------------------------------------------- */
 /* Number of CUDA devices visible to the process (0 without a driver or GPU). */
 int skd_device_count(void);
+/* One context per GPU and host thread/process.  With SKD_BIND_CPU=1 in the environment the calling thread is first
+ * bound to the CPUs next to the GPU (NVML's ideal affinity), so that the pinned host buffers of skd_host_alloc and the
+ * thread filling them sit on the GPU's NUMA node; off by default because it changes the caller's affinity. */
 skd_status skd_ctx_create(int device, skd_ctx **out);
 void skd_ctx_destroy(skd_ctx *ctx);
 /* Message of the last failing call on this context (or of a failed skd_ctx_create when ctx == NULL). */

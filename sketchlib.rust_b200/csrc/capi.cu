@@ -2,6 +2,7 @@
 // the distance drivers (tile schedules, chunked result streaming).  No CPU fallback exists: every compute
 // entry point launches the CUDA kernels of kernels.cu or fails.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 #include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -1037,6 +1038,22 @@ int skd_device_count(void) {
     return count;
 }
 
+// SKD_BIND_CPU=1: bind the calling thread to the CPUs next to the GPU (NVML's ideal affinity) before the context
+// allocates anything, so that the pinned host buffers it hands out (first touch) and the thread that fills them sit on
+// the GPU's NUMA node.  One process (or thread) per GPU is the intended arrangement; opt-in because it changes the
+// caller's affinity.  Best effort: without NVML nothing happens.
+static void bind_cpu_to_device(int device) {
+    char bus[32];
+    if (cudaDeviceGetPCIBusId(bus, (int)sizeof bus, device) != cudaSuccess) return;
+    void *lib = dlopen("libnvidia-ml.so.1", RTLD_NOW);
+    if (!lib) return;
+    auto init = (int (*)())dlsym(lib, "nvmlInit_v2");
+    auto by_pci = (int (*)(const char *, void **))dlsym(lib, "nvmlDeviceGetHandleByPciBusId_v2");
+    auto set_aff = (int (*)(void *))dlsym(lib, "nvmlDeviceSetCpuAffinity");
+    void *h = nullptr;
+    if (init && by_pci && set_aff && init() == 0 && by_pci(bus, &h) == 0) (void)set_aff(h);
+}
+
 skd_status skd_ctx_create(int device, skd_ctx **out) {
     if (!out) return fail(nullptr, SKD_ERR_INVALID, "null output pointer");
     *out = nullptr;
@@ -1046,6 +1063,8 @@ skd_status skd_ctx_create(int device, skd_ctx **out) {
         return fail(nullptr, SKD_ERR_CUDA, "no CUDA device available (%s); libsketchdist has no CPU fallback",
                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
     if (device < 0 || device >= count) return fail(nullptr, SKD_ERR_INVALID, "device %d out of range [0, %d)", device, count);
+    if (const char *b = getenv("SKD_BIND_CPU"))
+        if (atoi(b) != 0) bind_cpu_to_device(device);
     skd_ctx *ctx = new (std::nothrow) skd_ctx;
     if (!ctx) return fail(nullptr, SKD_ERR_NOMEM, "out of host memory");
     ctx->device = device;
