@@ -339,9 +339,13 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     peaks = int_peaks() if rank == 0 else None
 
+    def pairs_of_last_call():
+        a, b = grp.last_row_block if world > 1 else (r0, r1)   # the split adapts to the ranks' measured times
+        return int(ctx.lib.skd_self_pairs_in_rows(n, a, b))
+
     def step_resident():
         grp.self_dists_knn(g, KNN, dt_ca, root=0, out=(d_idx, d_d0, d_d1), out_loc=sk.SKD_DEVICE)
-        return grp.last_op_ms, ctx.last_tile_kernel_ms, ctx.last_kernel_ms, grp.last_exchange_ms
+        return grp.last_op_ms, ctx.last_tile_kernel_ms, ctx.last_kernel_ms, grp.last_exchange_ms, pairs_of_last_call()
 
     # ---- value: database resident in HBM, final rows left in rank 0's HBM
     for _ in range(args.warmup):
@@ -368,11 +372,11 @@ def main():
     xchg_ms = sum(r[3] for r in recs) / len(recs)
     ms_per_step = max_over_ranks(op_ms)
     value = total_pairs / (ms_per_step * 1e-3)
-    pairs_all = gather_floats(float(my_pairs))
+    my_pairs = sum(r[4] for r in recs) / len(recs)   # pairs this rank evaluated per step (adaptive split)
     xchg_all = gather_floats(xchg_ms)
     # how much of the match counting the early exit left (this rank), measured on one more step
     ctx.work_counters(reset=True)
-    step_resident()
+    pairs_counted_step = step_resident()[4]
     steps_done, steps_total, pairs_deferred = ctx.work_counters(reset=True)
 
     # ---- roofline leg: the same job with the kernel's early exit OFF (every k-mer length of every pair is counted --
@@ -391,6 +395,7 @@ def main():
     tile_ms = sum(r[1] for r in recs_full) / len(recs_full)
     kern_ms = sum(r[2] for r in recs_full) / len(recs_full)
     tile_ms_all = gather_floats(tile_ms)
+    pairs_all = gather_floats(sum(r[4] for r in recs_full) / len(recs_full))   # per rank, in the roofline leg
 
     # ---- e2e: pinned host bit planes (1/N per rank) -> HBM -> peers -> distances -> exchange -> host rows on rank 0
     h_idx = ctx.pinned((n, KNN), np.uint64) if is_root else None
@@ -463,7 +468,7 @@ def main():
                         "16 x 64 pair block after the third k-mer length when at most 32 of its pairs are still open and "
                         "hands those to defer_kernel; results are identical (parity_sample, resident_equals_e2e)",
                 "match_count_steps_executed_frac": steps_done / max(steps_total, 1),
-                "pairs_finished_by_defer_kernel_frac": pairs_deferred / max(my_pairs, 1),
+                "pairs_finished_by_defer_kernel_frac": pairs_deferred / max(pairs_counted_step, 1),
                 "tile_and_defer_kernel_ms_per_step": tile_ms_ee, "all_kernels_ms_per_step": kern_ms_ee,
                 "executed_tlop3_per_s": my_pairs * LOP3_PER_PAIR * (steps_done / max(steps_total, 1)) / (tile_ms_ee * 1e-3) / 1e12,
             },
@@ -476,11 +481,15 @@ def main():
             "traffic_note": (ncu or {}).get("traffic_note"),
             "int_peaks": peaks,
         }
+        config = knn_workload_config(world)
+        if world > 1:
+            config["sharding"] += ("; the first call splits the triangle into equal pair counts, later calls re-split it "
+                                   "from the ranks' measured times (skd_comm_last_row_block)")
         line = {
             "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "u32 bit planes (LOP3/POPC) + f64 epilogue -> f32", "data": "synthetic",
-            "config": knn_workload_config(world),
+            "config": config,
             "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": int(sum(h2d_all)),
                     "d2h_bytes_per_step": n * KNN * 16, "ms_per_step": e2e_s * 1e3,
                     "h2d_bytes_per_rank": [int(x) for x in h2d_all],

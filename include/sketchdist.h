@@ -234,6 +234,11 @@ int skd_comm_world(const skd_comm *comm);
 float skd_comm_last_op_ms(const skd_comm *comm);
 /* The part of it spent after the local distance kernels: barriers + peer merge + gather of the final rows. */
 float skd_comm_last_exchange_ms(const skd_comm *comm);
+/* The triangle rows this rank evaluated in its last skd_comm_self_dists_knn call (knn <= 64).  The first call of a
+ * problem shape splits the triangle into blocks of equal pair counts (skd_triangle_rows); later calls of the same
+ * shape re-split it from the ranks' measured times so that they finish together (SKD_ADAPTIVE_SPLIT=0: never).  The
+ * results do not depend on the split. */
+void skd_comm_last_row_block(const skd_comm *comm, uint64_t *row_begin, uint64_t *row_end);
 /* Window sizes the collective calls need (the window must hold the largest one used). */
 size_t skd_comm_window_bytes_knn(uint64_t n_rows, uint64_t knn, int world);
 size_t skd_comm_window_bytes_db(uint64_t n_samples, uint64_t sketchsize64, uint32_t n_kmers, int world);

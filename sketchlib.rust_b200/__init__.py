@@ -106,6 +106,7 @@ def load_library(build=True):
         "skd_comm_world": (C.c_int, [vp]),
         "skd_comm_last_op_ms": (C.c_float, [vp]),
         "skd_comm_last_exchange_ms": (C.c_float, [vp]),
+        "skd_comm_last_row_block": (None, [vp, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
         "skd_comm_window_bytes_knn": (C.c_size_t, [u64, u64, C.c_int]),
         "skd_comm_window_bytes_db": (C.c_size_t, [u64, u64, u32, C.c_int]),
         "skd_triangle_rows": (None, [u64, C.c_int, C.c_int, C.POINTER(u64), C.POINTER(u64)]),
@@ -492,6 +493,13 @@ class PeerGroup:
     @property
     def last_exchange_ms(self):
         return float(self.ctx.lib.skd_comm_last_exchange_ms(self.handle))
+
+    @property
+    def last_row_block(self):
+        """Triangle rows this rank evaluated in its last self_dists_knn call (the split adapts to measured times)."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self.ctx.lib.skd_comm_last_row_block(self.handle, C.byref(a), C.byref(b))
+        return int(a.value), int(b.value)
 
     def barrier(self):
         self.ctx._check(self.ctx.lib.skd_comm_barrier(self.handle))

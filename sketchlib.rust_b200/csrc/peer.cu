@@ -66,6 +66,8 @@ struct skd_comm {
     double timeout_s = 60.0;
     cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};  // op begin / local kernels done / op end
     float last_ms = 0.f, last_xchg_ms = 0.f;
+    bool adaptive_split = true;  // SKD_ADAPTIVE_SPLIT=0: always the analytic equal-pair triangle split
+    uint64_t last_r0 = 0, last_r1 = 0;  // triangle rows this rank evaluated in the last symmetric self-kNN call
     unsigned char *data(int r) const { return peers.base[r] + kFlagBytes; }
 };
 
@@ -235,6 +237,70 @@ bool g_debug = getenv("SKD_PEER_DEBUG") != nullptr;
     } while (0)
 
 skd_status comm_fail(skd_comm *c, skd_status st, const char *msg) { return fail(c ? c->ctx : nullptr, st, "%s", msg); }
+
+// What a rank leaves in the flag area of its window (offset kSplitOff) at the end of a symmetric self-kNN call: how long
+// its local part took and how many pairs that was.  The next call with the same tag (same problem shape) re-splits the
+// triangle so that every rank's predicted time is the same: equal pair counts are not equal times (the ranks' key
+// matrices differ in shape -- few long rows at the top of the triangle, many short ones at the bottom -- and so do
+// their select kernels and diagonal waste).  Every rank reads the same N records after the entry barrier, so all
+// compute the same boundaries; results do not depend on the split.
+constexpr size_t kSplitOff = 2048;
+struct SplitStat {
+    float local_ms;
+    uint32_t tag;
+    uint64_t pairs;
+};
+uint64_t triangle_bound(uint64_t n, double f) {  // row after a fraction f of the pairs, the rule of skd_triangle_rows
+    if (f <= 0.0) return 0;
+    if (f >= 1.0) return n;
+    const double x = (double)n * (1.0 - std::sqrt(1.0 - f));
+    return std::min<uint64_t>(n, (uint64_t)std::llround(x / TS) * TS);
+}
+skd_status split_triangle(skd_comm *c, uint64_t n, uint32_t tag, uint64_t *bounds /* world + 1 */) {
+    const int W = c->world;
+    double share[kMaxWorld];
+    for (int p = 0; p < W; ++p) share[p] = 1.0 / W;
+    if (c->adaptive_split && W > 1) {
+        SplitStat st[kMaxWorld];
+        for (int p = 0; p < W; ++p)
+            CU(c->ctx, cudaMemcpyAsync(&st[p], c->peers.base[p] + kSplitOff, sizeof(SplitStat), cudaMemcpyDeviceToHost,
+                                       c->ctx->compute));
+        CU(c->ctx, cudaStreamSynchronize(c->ctx->compute));
+        bool ok = true;
+        double pairs_all = 0.0, speed_all = 0.0;
+        for (int p = 0; p < W; ++p) {
+            ok = ok && st[p].tag == tag && st[p].pairs > 0 && st[p].local_ms > 0.f && std::isfinite(st[p].local_ms);
+            if (ok) {
+                pairs_all += (double)st[p].pairs;
+                speed_all += (double)st[p].pairs / st[p].local_ms;
+            }
+        }
+        if (ok) {
+            double sum = 0.0;
+            for (int p = 0; p < W; ++p) {
+                const double prev = (double)st[p].pairs / pairs_all;                    // what the rank had
+                const double want = ((double)st[p].pairs / st[p].local_ms) / speed_all;  // what its speed deserves
+                share[p] = std::min(2.0 / W, std::max(0.5 / W, 0.25 * prev + 0.75 * want));  // damped, bounded
+                sum += share[p];
+            }
+            for (int p = 0; p < W; ++p) share[p] /= sum;
+        }
+    }
+    double cum = 0.0;
+    bounds[0] = 0;
+    for (int p = 0; p < W; ++p) {
+        cum += share[p];
+        bounds[p + 1] = p + 1 == W ? n : std::max(bounds[p], triangle_bound(n, cum));
+    }
+    return SKD_OK;
+}
+skd_status leave_split_stat(skd_comm *c, uint32_t tag, uint64_t pairs) {
+    if (c->world == 1) return SKD_OK;
+    const SplitStat st{c->last_ms - c->last_xchg_ms, tag, pairs};
+    CU(c->ctx, cudaMemcpyAsync(c->window + kSplitOff, &st, sizeof st, cudaMemcpyHostToDevice, c->ctx->compute));
+    CU(c->ctx, cudaStreamSynchronize(c->ctx->compute));  // st is a local; the next call's entry barrier publishes it
+    return SKD_OK;
+}
 
 // One flag barrier on the compute stream; returns when every rank has reached it (the stream is idle then).
 skd_status enqueue_barrier(skd_comm *c) {
@@ -528,6 +594,7 @@ skd_status skd_comm_create(skd_ctx *ctx, int rank, int world, size_t window_byte
     c->world = world;
     c->window_bytes = align_up(std::max<size_t>(window_bytes, 256));
     if (const char *e = getenv("SKD_PEER_TIMEOUT_S")) c->timeout_s = std::max(1.0, atof(e));
+    if (const char *e = getenv("SKD_ADAPTIVE_SPLIT")) c->adaptive_split = atoi(e) != 0;
     cudaError_t e = cudaMalloc((void **)&c->window, kFlagBytes + c->window_bytes);  // plain cudaMalloc: IPC-exportable
     if (e == cudaSuccess) e = cudaMemset(c->window, 0, kFlagBytes);
     if (e == cudaSuccess) e = cudaHostAlloc((void **)&c->err_host, 64, cudaHostAllocMapped);
@@ -625,6 +692,10 @@ int skd_comm_rank(const skd_comm *c) { return c ? c->rank : -1; }
 int skd_comm_world(const skd_comm *c) { return c ? c->world : 0; }
 float skd_comm_last_op_ms(const skd_comm *c) { return c ? c->last_ms : 0.f; }
 float skd_comm_last_exchange_ms(const skd_comm *c) { return c ? c->last_xchg_ms : 0.f; }
+void skd_comm_last_row_block(const skd_comm *c, uint64_t *row_begin, uint64_t *row_end) {
+    if (row_begin) *row_begin = c ? c->last_r0 : 0;
+    if (row_end) *row_end = c ? c->last_r1 : 0;
+}
 
 skd_status skd_comm_barrier(skd_comm *c) {
     skd_status st = begin_op(c);
@@ -703,10 +774,18 @@ skd_status skd_comm_self_dists_knn(skd_comm *c, const skd_db *db, uint64_t knn, 
     timers_reset(ctx);
     const bool symmetric = knn <= kSymKnnMax && ctx->knn_symmetric;
     uint64_t first_row[kMaxWorld] = {};
+    // problem shape the split statistics belong to (never 0: a fresh window reads as tag 0)
+    const uint32_t split_tag = (uint32_t)((n * 2654435761ull) ^ (knn << 20) ^ ((uint64_t)E.kind << 28) ^ ((uint64_t)E.nk << 8)) | 1u;
+    uint64_t my_pairs = 0;
     if (symmetric) {
-        uint64_t r0, r1;
-        skd_triangle_rows(n, c->rank, c->world, &r0, &r1);
-        for (int p = 0; p < c->world; ++p) skd_triangle_rows(n, p, c->world, &first_row[p], nullptr);
+        uint64_t bounds[kMaxWorld + 1];
+        st = split_triangle(c, n, split_tag, bounds);
+        if (st) return st;
+        const uint64_t r0 = bounds[c->rank], r1 = bounds[c->rank + 1];
+        for (int p = 0; p < c->world; ++p) first_row[p] = bounds[p];
+        my_pairs = skd_self_pairs_in_rows(n, r0, std::max(r0, r1));
+        c->last_r0 = r0;
+        c->last_r1 = std::max(r0, r1);
         st = run_knn_symmetric(ctx, db, E, knn, r0, std::max(r0, r1), reinterpret_cast<unsigned long long *>(mine + L.keys),
                                reinterpret_cast<float *>(mine + L.aux));
     } else {  // every rank computes its owned rows against all columns: final rows straight into the window
@@ -717,7 +796,9 @@ skd_status skd_comm_self_dists_knn(skd_comm *c, const skd_db *db, uint64_t knn, 
                          reinterpret_cast<float *>(mine + L.fin_d0), reinterpret_cast<float *>(mine + L.fin_d1), SKD_DEVICE);
     }
     if (st) return st;
-    return exchange_rows(c, L, n, knn, E.kind, symmetric, first_row, root, idx_out, d0_out, d1_out, out_loc);
+    st = exchange_rows(c, L, n, knn, E.kind, symmetric, first_row, root, idx_out, d0_out, d1_out, out_loc);
+    if (st || !symmetric) return st;
+    return leave_split_stat(c, split_tag, my_pairs);
 }
 
 skd_status skd_comm_cross_dists_knn(skd_comm *c, const skd_db *ref_shard, const skd_db *query, uint64_t knn,
