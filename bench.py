@@ -269,7 +269,6 @@ def main():
     import numpy as np
     import torch
     import torch.distributed as dist
-    os.environ.setdefault("SKD_BIND_CPU", "1")  # one process per GPU: sit on the GPU's NUMA node (skd_ctx_create)
     all_cpus = os.sched_getaffinity(0)           # restored before any CPU-oracle work (it uses every host core)
     import sketchlib.rust_b200 as sk
 

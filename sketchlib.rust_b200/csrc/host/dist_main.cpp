@@ -340,9 +340,6 @@ struct Rendezvous {
 
 void run_peer_group(int world, int first_device, size_t window_bytes,
                     const std::function<void(int, skd_ctx *, skd_comm *)> &body) {
-    // one host thread per GPU: let each sit next to its GPU (pinned buffers, loader threads), unless told otherwise
-    // (set here, before the threads exist: setenv must not race with their getenv)
-    if (world > 1) setenv("SKD_BIND_CPU", "1", 0);
     std::vector<skd_ctx *> ctxs(world, nullptr);
     std::vector<skd_comm *> comms(world, nullptr);
     std::vector<unsigned char> handles((size_t)world * SKD_COMM_HANDLE_BYTES);

@@ -296,7 +296,9 @@ skd_status split_triangle(skd_comm *c, uint64_t n, uint32_t tag, uint64_t *bound
 }
 skd_status leave_split_stat(skd_comm *c, uint32_t tag, uint64_t pairs) {
     if (c->world == 1) return SKD_OK;
-    const SplitStat st{c->last_ms - c->last_xchg_ms, tag, pairs};
+    // the device time of this rank's own kernels (distance tiles, deferred pairs, list folds): CUDA-event timers around
+    // the launches, so neither the waits at the barriers nor host-side skew between the ranks enter the split
+    const SplitStat st{c->ctx->last_ms, tag, pairs};
     CU(c->ctx, cudaMemcpyAsync(c->window + kSplitOff, &st, sizeof st, cudaMemcpyHostToDevice, c->ctx->compute));
     CU(c->ctx, cudaStreamSynchronize(c->ctx->compute));  // st is a local; the next call's entry barrier publishes it
     return SKD_OK;

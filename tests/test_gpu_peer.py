@@ -91,11 +91,25 @@ def test_peer_group_self_knn_equals_single_device(sk, world):
             out["single_jac"] = sk.self_dists_knn(g, knn=9, dist_type=sk.set_k(g, 21))
             out["single_ani70"] = sk.self_dists_knn(g, knn=70, dist_type=sk.set_k(g, 21, ani=True))
         out["xchg_ms"] = grp.last_exchange_ms
+        # repeated calls of one problem shape re-split the triangle from the ranks' measured times: the blocks may
+        # move (and stay a partition of the rows), the rows must not change
+        blocks = []
+        for _ in range(3):
+            again = grp.self_dists_knn(g, knn=50, dist_type=sk.set_k(g), root=0)
+            blocks.append(grp.last_row_block)
+            if rank == 0:
+                assert np.array_equal(again.idx, out["ca"].idx) and np.array_equal(again.d0, out["ca"].d0)
+                assert np.array_equal(again.d1, out["ca"].d1)
+        out["blocks"] = blocks
         g.free()
         return out
 
     res = run_group(sk, world, win, body)
     r0 = res[0]
+    for call in range(3):   # every call's blocks tile [0, n) in rank order, on 64-sample boundaries
+        edges = [res[r]["blocks"][call] for r in range(world)]
+        assert edges[0][0] == 0 and edges[-1][1] == db.n
+        assert all(edges[r][1] == edges[r + 1][0] and edges[r][1] % 64 == 0 for r in range(world - 1))
     assert all(r["ca"] is None for r in res[1:]) and all(r["ani70"] is None for r in res[:-1])
     for a, b in ((r0["ca"], r0["single_ca"]), (r0["jac"], r0["single_jac"]), (res[-1]["ani70"], r0["single_ani70"])):
         assert np.array_equal(a.idx, b.idx) and np.array_equal(a.d0, b.d0)

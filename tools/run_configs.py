@@ -27,8 +27,6 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
-
-os.environ.setdefault("SKD_BIND_CPU", "1")  # one process per GPU: sit on the GPU's NUMA node (skd_ctx_create)
 import sketchlib.rust_b200 as sk  # noqa: E402
 from sketchlib.rust_b200 import synth  # noqa: E402
 
