@@ -50,7 +50,10 @@ skd_status scratch_get(skd_ctx *ctx, const char *name, size_t bytes, void **out)
     if (slot.second < bytes) {
         if (slot.first) CU(ctx, cudaFreeAsync(slot.first, ctx->compute));
         slot = {nullptr, 0};
+        // large buffers get 1/8 of headroom: the sizes of the key-matrix chunks follow the row blocks of a call, and a
+        // peer group re-splits those slightly from call to call -- regrowing an 8 GB buffer stalls a rank for ~50 ms
         size_t want = std::max<size_t>(bytes, 256);
+        if (want >= (64u << 20)) want += want / 8;
         CU(ctx, cudaMallocAsync(&slot.first, want, ctx->compute));
         slot.second = want;
     }
