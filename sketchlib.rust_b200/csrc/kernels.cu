@@ -1070,20 +1070,25 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1)
                                     s1 = 0;
                                     ph1 ^= 1u;
                                 }
-                                uint32_t c;
-                                bool landed = false;
-                                for (;;) {
-                                    c = cut[q];
-                                    if (c != kCutUnset) break;
-                                    if (mbar_test(&full_bar[s1], ph1)) {
-                                        c = cut[q];  // read again: unset now means the stage that landed is ours
-                                        landed = true;
-                                        break;
+                                // lane 0 watches, the warp follows its verdict (one decision per warp, whatever the
+                                // lanes would have read individually)
+                                uint32_t c = kCutUnset, landed = 0;
+                                if (lane == 0) {
+                                    for (;;) {
+                                        c = cut[q];
+                                        if (c != kCutUnset) break;
+                                        if (mbar_test(&full_bar[s1], ph1)) {
+                                            c = cut[q];  // read again: unset now means the stage that landed is ours
+                                            landed = 1;
+                                            break;
+                                        }
+                                        __nanosleep(32);
+                                        spin_guard();
                                     }
-                                    __nanosleep(32);
-                                    spin_guard();
                                 }
-                                if (c != kCutUnset && it2 >= c) break;  // (warp-uniform: shared-memory broadcast reads)
+                                c = __shfl_sync(0xffffffffu, c, 0);
+                                landed = __shfl_sync(0xffffffffu, landed, 0);
+                                if (c != kCutUnset && it2 >= c) break;
                                 s = s1;
                                 ph = ph1;
                                 if (!landed) mbar_wait(&full_bar[s], ph);
