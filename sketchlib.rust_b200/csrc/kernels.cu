@@ -794,7 +794,7 @@ __global__ void __launch_bounds__(DENSE_THREADS, 1)
     unsigned char *out_stage = reinterpret_cast<unsigned char *>(warp_lists + 8 * 1024);          // [8 warps][16][64] float2
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const uint32_t W = A.W, nk = (uint32_t)E.nk, kp = (uint32_t)E.kp;
+    const uint32_t W = A.W, nk = (uint32_t)E.nk;
     const uint32_t n_it = nk * W;
     const uint32_t nbins = 64u * W;
     // column blocks this launch may touch: [.., cb_limit) (a band of an upload in flight ends at cb_hi)
