@@ -250,6 +250,10 @@ size_t skd_comm_window_bytes_db(uint64_t n_samples, uint64_t sketchsize64, uint3
  *   distributed loader (align 64), reference shards (align 64), owned result rows (align 1). */
 void skd_triangle_rows(uint64_t n, int rank, int world, uint64_t *row_begin, uint64_t *row_end);
 void skd_slice_rows(uint64_t n, int rank, int world, uint64_t align, uint64_t *begin, uint64_t *end);
+/* The triangle split for given pair shares (shares[world], summing to 1; NULL = equal shares = skd_triangle_rows):
+ * bounds[world + 1], bounds[0] = 0, bounds[world] = n, rank r takes rows [bounds[r], bounds[r + 1]).  What
+ * skd_comm_self_dists_knn uses when it re-splits the triangle from the ranks' measured times. */
+void skd_triangle_rows_weighted(uint64_t n, int world, const double *shares, uint64_t *bounds);
 
 /* Distributed form of read_sketch_data (multisketch.rs:167-184): every rank ends up with the WHOLE database in its
  * HBM, but moves only its own slice skd_slice_rows(n_total, rank, world, 64) over PCIe: `bins_slice` points at the

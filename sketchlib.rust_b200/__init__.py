@@ -111,6 +111,7 @@ def load_library(build=True):
         "skd_comm_window_bytes_db": (C.c_size_t, [u64, u64, u32, C.c_int]),
         "skd_triangle_rows": (None, [u64, C.c_int, C.c_int, C.POINTER(u64), C.POINTER(u64)]),
         "skd_slice_rows": (None, [u64, C.c_int, C.c_int, u64, C.POINTER(u64), C.POINTER(u64)]),
+        "skd_triangle_rows_weighted": (None, [u64, C.c_int, C.c_void_p, C.c_void_p]),
         "skd_comm_db_upload": (C.c_int, [vp, vp, C.c_int, u64, u64, u64, u64, u64, vp, u32, C.POINTER(vp)]),
         "skd_comm_db_load_skd": (C.c_int, [vp, C.c_char_p, vp, u64, u64, u64, u64, u64, vp, u32, C.POINTER(vp)]),
         "skd_comm_self_dists_knn": (C.c_int, [vp, vp, u64, _DistType, vp, dbl, C.c_int, vp, vp, vp, C.c_int]),
@@ -434,6 +435,14 @@ def triangle_row_partition(n, rank, world, align=64):
         x = n * (1.0 - (1.0 - r / world) ** 0.5)
         return min(n, int(x / align + 0.5) * align)   # llround: halves away from zero, like the C library
     return bound(rank), bound(rank + 1)
+
+
+def triangle_rows_weighted(n, shares):
+    """skd_triangle_rows_weighted: row boundaries [world + 1] of the triangle split for the given pair shares."""
+    sh = np.ascontiguousarray(shares, dtype=np.float64)
+    out = np.zeros(len(sh) + 1, dtype=np.uint64)
+    load_library().skd_triangle_rows_weighted(int(n), len(sh), sh.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    return [int(x) for x in out]
 
 
 def slice_rows(n, rank, world, align=1):

@@ -286,12 +286,7 @@ skd_status split_triangle(skd_comm *c, uint64_t n, uint32_t tag, uint64_t *bound
             for (int p = 0; p < W; ++p) share[p] /= sum;
         }
     }
-    double cum = 0.0;
-    bounds[0] = 0;
-    for (int p = 0; p < W; ++p) {
-        cum += share[p];
-        bounds[p + 1] = p + 1 == W ? n : std::max(bounds[p], triangle_bound(n, cum));
-    }
+    skd_triangle_rows_weighted(n, W, share, bounds);
     return SKD_OK;
 }
 skd_status leave_split_stat(skd_comm *c, uint32_t tag, uint64_t pairs) {
@@ -552,6 +547,16 @@ cudaError_t skdi::preload_peer_kernels() {
 
 // =================================================================================================================
 extern "C" {
+
+void skd_triangle_rows_weighted(uint64_t n, int world, const double *shares, uint64_t *bounds) {
+    if (world < 1 || !bounds) return;
+    double cum = 0.0;
+    bounds[0] = 0;
+    for (int p = 0; p < world; ++p) {
+        cum += shares ? shares[p] : 1.0 / world;
+        bounds[p + 1] = p + 1 == world ? n : std::max(bounds[p], triangle_bound(n, cum));
+    }
+}
 
 void skd_triangle_rows(uint64_t n, int rank, int world, uint64_t *row_begin, uint64_t *row_end) {
     auto bound = [&](int r) -> uint64_t {

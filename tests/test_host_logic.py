@@ -253,3 +253,28 @@ def test_matrix_writers_match_python_display(tmp_path):
         assert open(tmp_path / "d.tsv").read() == str(spx)
     with pytest.raises(sk.HostError):
         sp.write(str(tmp_path / "no_such_dir" / "x.tsv"))
+
+
+def test_weighted_triangle_split():
+    """The split skd_comm_self_dists_knn uses when it re-balances the ranks from their measured times: equal shares give
+    skd_triangle_rows; any shares give a partition of [0, n) on tile boundaries whose pair counts follow the shares."""
+    import sketchlib.rust_b200 as sk
+    lib = sk.load_library()
+    for n in (1, 63, 64, 1000, 10_000, 100_000, 1_234_567):
+        for world in (1, 2, 3, 8, 16):
+            b = sk.triangle_rows_weighted(n, [1.0 / world] * world)
+            assert b[0] == 0 and b[-1] == n and all(x <= y for x, y in zip(b, b[1:]))
+            for r in range(world):
+                assert (b[r], b[r + 1]) == sk.triangle_row_partition(n, r, world)
+    rng = np.random.default_rng(5)
+    n = 100_000
+    total = n * (n - 1) // 2
+    for world in (2, 5, 8):
+        w = rng.uniform(0.5, 1.5, size=world)
+        shares = w / w.sum()
+        b = sk.triangle_rows_weighted(n, shares)
+        assert b[0] == 0 and b[-1] == n and all(x < y for x, y in zip(b, b[1:]))
+        assert all(x % 64 == 0 for x in b[1:-1])
+        for r in range(world):
+            pairs = int(lib.skd_self_pairs_in_rows(n, b[r], b[r + 1]))
+            assert abs(pairs / total - shares[r]) < 2e-3   # off by at most a tile row or two
