@@ -185,13 +185,17 @@ skd_status skd_cross_dists_knn(skd_ctx *ctx, const skd_db *ref, const skd_db *qu
 /* ---- partial kNN lists for multi-GPU runs that split the COLUMNS of the problem -----------------------------
  * A partial list is, per row, `knn` opaque 64-bit composites (distance key and neighbour index) in ascending
  * order, padded with UINT64_MAX, plus (core/accessory only) the accessory distance of each entry.  Ranks exchange
- * them (one NCCL all-gather / gather: rows x knn x 12 bytes per rank) and skd_knn_merge turns `n_parts` of them
- * into the reference's sparse rows.  Each candidate must appear in exactly one partial.
+ * them (rows x knn x 12 bytes per rank: through the peer groups below, or any transport of the host's) and
+ * skd_knn_merge turns `n_parts` of them into the reference's sparse rows.  Each candidate must appear in exactly one
+ * partial.  A list may hold fewer than knn real entries even when more candidates were seen: candidates at distance 1
+ * whose neighbour index exceeds knn can never reach a final row (every sample with a smaller index precedes them)
+ * and are dropped at the source.
  *
  * skd_self_knn_partial: symmetric self mode -- evaluates every unordered pair (i, j > i) with i in
  *   [row_begin, row_end) ONCE and credits it to both rows, so the lists cover ALL n rows (n x knn entries); the
  *   union over a partition of the rows (row_begin a multiple of 64; use equal-pair triangle blocks) is the
- *   result of self_dists_knn (src/distances/mod.rs:133-224) at half its pair evaluations.  knn <= 64.
+ *   result of self_dists_knn (src/distances/mod.rs:133-224) at half its pair evaluations.  For knn > 64 the rows
+ *   [row_begin, row_end) are evaluated against all columns instead and only they get lists (same merged result).
  * skd_cross_knn_partial: cross mode with the REFERENCES sharded -- the best knn of this shard for every query
  *   (n_query x knn entries); neighbour indices are shifted by ref_index_offset (the shard's first reference). */
 skd_status skd_self_knn_partial(skd_ctx *ctx, const skd_db *db, uint64_t knn, skd_dist_type dist,
